@@ -1,0 +1,225 @@
+/*
+ * jvgpu.h — C-ABI of libjvgpu.so, the B200 (sm_100a) implementation of the
+ * opensearch-jvector query hot path.
+ *
+ * This header is the whole drop-in boundary: the Java codec
+ * (JVectorReader / JVectorWriter / JVectorIndexQuantization) binds these
+ * symbols with java.lang.foreign (Panama FFM) downcall handles — see
+ * INTEGRATION.md for the binding a maintainer would add.  Everything is plain
+ * pointers, sizes and int32 status codes: no structs by value, no callbacks,
+ * no C++ / torch types.
+ *
+ * Conventions
+ *  - every function returns 0 (JV_OK) or a negative jv_status; the message is
+ *    available from jv_last_error() (thread local).  Nothing throws or aborts
+ *    across the boundary.  There is NO CPU fallback: without a usable CUDA
+ *    device every compute entry point returns JV_ERR_CUDA.
+ *  - all entry points are re-entrant and thread-safe; an index handle may be
+ *    searched from many threads concurrently (reference behaviour:
+ *    KNNJVectorTests.java:982-1028).
+ *  - the caller owns every in/out buffer; jv_index_create() copies what it
+ *    needs to the device and retains no host pointer.
+ *  - "host" entry points take host pointers and do their own H2D/D2H; the
+ *    "_dev" variants take device pointers that live on the index's device
+ *    (used by the multi-GPU driver and by the resident-input benchmark).
+ *
+ * Reference citations are relative to /root/reference/src/main/java/org/
+ * opensearch/knn/index/codec/jvector/ unless a longer path is given.
+ */
+#ifndef JVGPU_H
+#define JVGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define JV_API __attribute__((visibility("default")))
+#else
+#define JV_API
+#endif
+
+#define JVGPU_VERSION_MAJOR 0
+#define JVGPU_VERSION_MINOR 1
+
+/* ---- status codes --------------------------------------------------- */
+typedef enum jv_status {
+    JV_OK = 0,
+    JV_ERR_INVALID_ARGUMENT = -1, /* Java side: IllegalArgumentException          */
+    JV_ERR_CUDA = -2,             /* Java side: IOException (no device / CUDA err) */
+    JV_ERR_OUT_OF_MEMORY = -3,    /* Java side: IOException                        */
+    JV_ERR_UNSUPPORTED = -4,      /* Java side: UnsupportedOperationException      */
+    JV_ERR_INTERNAL = -5
+} jv_status;
+
+/* ---- similarity ordinals --------------------------------------------
+ * Same ordinals as the meta file's simOrd, JVectorReader.java:389-394
+ * (VectorSimilarityMapper.JVECTOR_SUPPORTED_SIMILARITY_FUNCTIONS):
+ *   0 EUCLIDEAN  score = 1/(1+||a-b||^2)
+ *   1 DOT        score = (1+a.b)/2
+ *   2 COSINE     score = (1+cos)/2
+ *   3 MIP        Lucene MAXIMUM_INNER_PRODUCT -> jVector DOT_PRODUCT.  On the
+ *                un-quantised traversal (JVectorReader.java:220-239,358-363)
+ *                and the brute-force scorer (JVectorVectorScorer.java:43-50)
+ *                the score is doubled (= 1+a.b); the PQ reranker is NOT
+ *                wrapped (JVectorReader.java:352-356) and stays (1+a.b)/2.
+ */
+#define JV_SIM_EUCLIDEAN 0
+#define JV_SIM_DOT 1
+#define JV_SIM_COSINE 2
+#define JV_SIM_MIP 3
+
+/* ---- index description ------------------------------------------------
+ * Decoded arrays of one field of one segment, i.e. what FieldEntry holds
+ * after JVectorReader.java:284-337 loaded OnDiskGraphIndex + PQVectors +
+ * GraphNodeIdToDocMap.  All pointers are HOST pointers, read during
+ * jv_index_create() only.
+ */
+#define JV_INDEX_FLAG_FUSED_LAYOUT 1u /* also keep a neighbour-interleaved copy of the PQ codes
+                                          (R*M bytes per node) so one expansion is one contiguous read */
+#define JV_INDEX_FLAG_LUT_F16 2u      /* hold the per-query ADC table in fp16 in shared memory
+                                          (steering scores only; final scores are the exact rerank) */
+#define JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE 4u /* keep the fp32 vectors in pinned host memory (cfg 5) */
+
+typedef struct jv_index_desc {
+    int32_t struct_size;       /* = sizeof(jv_index_desc), for forward compatibility          */
+    int32_t similarity;        /* JV_SIM_*                                                      */
+    int32_t dim;               /* vector dimension                                              */
+    int32_t max_degree;        /* R: row stride of `adjacency`                                  */
+    int64_t n;                 /* number of graph nodes (ordinals 0..n-1)                       */
+    int32_t entry_node;        /* OnDiskGraphIndex.View.entryNode()                             */
+    int32_t max_doc;           /* Lucene maxDoc of the segment (size of accept bitsets)         */
+    const int32_t *adjacency;  /* [n * max_degree] level-0 neighbours, -1 padded                */
+    const float *vectors;      /* [n * dim] inline fp32 vectors (InlineVectors feature)         */
+    const int32_t *ord_to_doc; /* [n] GraphNodeIdToDocMap.getLuceneDocId; NULL = identity; -1 = deleted */
+    /* product quantisation (all NULL/0 when the segment is not quantised: n < 1024) */
+    int32_t pq_m;              /* number of subspaces M (0 = no PQ)                             */
+    int32_t pq_k;              /* centroids per subspace K <= 256                               */
+    const float *pq_codebooks; /* concatenated per subspace: [K * sub_m] fp32, sub sizes per A.3 */
+    const float *pq_global_centroid; /* [dim] or NULL (only EUCLIDEAN is centred, JVectorIndexQuantization.java:127) */
+    const uint8_t *pq_codes;   /* [n * M]                                                       */
+    int32_t device;            /* CUDA device ordinal                                           */
+    uint32_t flags;            /* JV_INDEX_FLAG_*                                               */
+} jv_index_desc;
+
+typedef struct jv_index jv_index; /* opaque */
+
+/* ---- per-query statistics -----------------------------------------------
+ * The four counters JVectorReader.java:183-193 feeds into KNNCounter.
+ */
+typedef struct jv_query_stats {
+    int32_t visited;        /* SearchResult.getVisitedCount()            */
+    int32_t expanded;       /* SearchResult.getExpandedCount()           */
+    int32_t expanded_base;  /* SearchResult.getExpandedCountBaseLayer()  */
+    int32_t reranked;       /* SearchResult.getRerankedCount()           */
+} jv_query_stats;
+
+/* Device-side durations of the last batch, CUDA events on the launching stream. */
+typedef struct jv_batch_timing {
+    float h2d_ms;
+    float search_ms;  /* LUT build + graph traversal + ADC scoring kernel (K1+K2 / K4) */
+    float rerank_ms;  /* exact rerank + top-k kernel (K3)                              */
+    float d2h_ms;
+    float total_ms;
+    int32_t launches; /* kernels launched for this batch                               */
+    int32_t reserved;
+} jv_batch_timing;
+
+typedef struct jv_search_params {
+    int32_t struct_size;   /* = sizeof(jv_search_params)                                        */
+    int32_t k;             /* topK  = KnnCollector.k()                                           */
+    int32_t rerank_k;      /* k * overQueryFactor, JVectorReader.java:168-169; must be >= k      */
+    float threshold;       /* JVectorKnnCollector.getThreshold(), default 0                      */
+    float rerank_floor;    /* JVectorKnnCollector.getRerankFloor(), default 0                    */
+    int32_t reserved;
+    /* AcceptDocs by Lucene docId (FixedBitSet words: bit d = word d>>6, bit d&63), NULL = accept all.
+     * accept_stride_words == 0: one bitset shared by the batch; else query i uses
+     * accept_bits + i*accept_stride_words.  An ordinal is accepted iff ord_to_doc[ord] != -1 and its
+     * doc bit is set (JVectorReader.java:157-163).  Rejected nodes are still traversed. */
+    const uint64_t *accept_bits;
+    int64_t accept_stride_words;
+} jv_search_params;
+
+/* ---- library ---------------------------------------------------------- */
+JV_API int32_t jv_version(void);                 /* (major << 16) | minor */
+JV_API const char *jv_last_error(void);          /* thread-local, never NULL */
+JV_API int32_t jv_device_count(int32_t *out_count);
+
+/* ---- index lifetime: FieldEntry ctor / close, JVectorReader.java:284-337, 367-378 ---- */
+JV_API int32_t jv_index_create(const jv_index_desc *desc, jv_index **out_index);
+JV_API int32_t jv_index_destroy(jv_index *index);
+JV_API int32_t jv_index_device_bytes(const jv_index *index, int64_t *out_bytes);
+/* diagnostics since index creation: which = 0 -> queries whose shared-memory visited set filled up
+ * (those searches stop admitting new nodes early; results stay valid but recall may drop) */
+JV_API int32_t jv_index_debug_counter(jv_index *index, int32_t which, int64_t *out_value);
+
+/* ---- K1+K2(+K4)+K3: replaces the body of JVectorReader.search, JVectorReader.java:130-210 ----
+ * queries [nq*dim] fp32; out_doc/out_score [nq*k] sorted by (score desc, doc asc), unused slots
+ * doc=-1, score=0; out_count [nq]; stats [nq] (nullable); timing (nullable).  nq = 1 is legal. */
+JV_API int32_t jv_search_batch(jv_index *index, const float *queries, int32_t nq, const jv_search_params *params,
+                        int32_t *out_doc, float *out_score, int32_t *out_count, jv_query_stats *stats,
+                        jv_batch_timing *timing);
+/* same, device pointers on the index's device (params->accept_bits is a device pointer too) */
+JV_API int32_t jv_search_batch_dev(jv_index *index, const float *d_queries, int32_t nq, const jv_search_params *params,
+                            int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, jv_query_stats *d_stats,
+                            jv_batch_timing *timing);
+
+/* ---- K5: brute-force exact top-k; replaces JVectorVectorScorer.score() driven by Lucene exactSearch,
+ * JVectorVectorScorer.java:36-53, JVectorFloatVectorValues.java:189-191.  Scores are jVector-scaled
+ * (MIP doubled).  Ties -> lower docId.  accept bits as in jv_search_params (nullable). */
+JV_API int32_t jv_exact_topk(jv_index *index, const float *queries, int32_t nq, int32_t k, const uint64_t *accept_bits,
+                      int64_t accept_stride_words, int32_t *out_doc, float *out_score, int32_t *out_count);
+JV_API int32_t jv_exact_topk_dev(jv_index *index, const float *d_queries, int32_t nq, int32_t k, const uint64_t *d_accept_bits,
+                          int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count);
+
+/* ---- K6: PQ encode; replaces PQVectors.encodeAndBuild, JVectorIndexQuantization.java:133 and
+ * JVectorWriter.java:1124.  codebooks as in jv_index_desc; global_centroid nullable.
+ * out_codes [n*m]; code = first argmin_c ||x_m - C_m[c]||^2 (strict <). */
+JV_API int32_t jv_pq_encode(int32_t device, const float *vectors, int64_t n, int32_t dim, int32_t m, int32_t k,
+                     const float *codebooks, const float *global_centroid, uint8_t *out_codes, float *out_kernel_ms);
+JV_API int32_t jv_pq_encode_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t m, int32_t k,
+                         const float *d_codebooks, const float *d_global_centroid, uint8_t *d_out_codes,
+                         float *out_kernel_ms);
+
+/* ---- K1 alone (test hook for the ADC table): PQVectors.precomputedScoreFunctionFor, JVectorReader.java:354.
+ * out_lut [nq * m * k] fp32: dot (DOT/COSINE/MIP) or squared L2 of the (centred) query sub-vector. */
+JV_API int32_t jv_pq_lut(jv_index *index, const float *queries, int32_t nq, float *out_lut);
+/* ADC scores of explicit (query, node) pairs through the same device code as the traversal. */
+JV_API int32_t jv_pq_adc_scores(jv_index *index, const float *queries, int32_t nq, const int32_t *nodes, int32_t nodes_per_query,
+                         float *out_scores);
+
+/* ---- K7: merge per-shard top-k lists (Lucene TopDocs.merge analogue).  lists are laid out
+ * [g][nq][k] with doc=-1 padding; docs must already be global ids.  Ties -> lower doc. */
+JV_API int32_t jv_merge_topk(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *docs, const float *scores,
+                      int32_t *out_doc, float *out_score, int32_t *out_count);
+JV_API int32_t jv_merge_topk_dev(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *d_docs, const float *d_scores,
+                          int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, float *out_kernel_ms);
+
+/* ---- "next" rows: fixtures built on the device ---------------------------
+ * PQ codebook training: ProductQuantization.compute(ravv, M, K, center, UNWEIGHTED, ...),
+ * JVectorIndexQuantization.java:123-131: k-means++ init + `iters` Lloyd iterations per subspace on
+ * the given training sample.  out_codebooks as in jv_index_desc; out_global_centroid [dim] written
+ * iff center != 0. */
+JV_API int32_t jv_pq_train(int32_t device, const float *vectors, int64_t n, int32_t dim, int32_t m, int32_t k, int32_t center,
+                    int32_t iters, uint64_t seed, float *out_codebooks, float *out_global_centroid);
+JV_API int32_t jv_pq_train_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t m, int32_t k,
+                        int32_t center, int32_t iters, uint64_t seed, float *d_out_codebooks,
+                        float *d_out_global_centroid);
+
+/* Vamana graph construction: GraphIndexBuilder(bsp, dim, M, beamWidth, neighborOverflow, alpha, false),
+ * JVectorWriter.java:1383-1422.  Batched-insert variant (prefix doubling) with exact build scores.
+ * out_adjacency [n*max_degree] (-1 padded), out_entry_node. */
+JV_API int32_t jv_graph_build(int32_t device, const float *vectors, int64_t n, int32_t dim, int32_t similarity,
+                       int32_t max_degree, int32_t beam_width, float neighbor_overflow, float alpha,
+                       int32_t *out_adjacency, int32_t *out_entry_node);
+JV_API int32_t jv_graph_build_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t similarity,
+                           int32_t max_degree, int32_t beam_width, float neighbor_overflow, float alpha,
+                           int32_t *d_out_adjacency, int32_t *out_entry_node);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JVGPU_H */

@@ -1,0 +1,368 @@
+"""Host-side mirror of the reference's codec adapter for the hot path (Python because no JVM exists in
+this image; the Java binding a maintainer would add is in INTEGRATION.md).
+
+Same names, argument meaning and error behaviour as
+  org.opensearch.knn.index.codec.jvector.{JVectorReader, JVectorWriter, JVectorKnnCollector,
+  JVectorKnnFloatVectorQuery, GraphNodeIdToDocMap, JVectorIndexQuantization, JVectorFormat}
+so the parity tests read like the reference's own (KNNJVectorTests.java).  Everything numeric goes
+through libjvgpu's C-ABI; nothing here computes scores on the CPU.
+"""
+from __future__ import annotations
+
+import enum
+import heapq
+import threading
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import native as N
+from .index import GpuIndex, graph_build, make_accept_bits, pq_encode, pq_train
+
+# ---- constants (KNNConstants.java:83-114, JVectorFormat.java:22-35) -------------------------------
+DEFAULT_MAX_CONN = 32
+DEFAULT_BEAM_WIDTH = 100
+DEFAULT_NEIGHBOR_OVERFLOW = 1.2
+DEFAULT_ALPHA = 1.2
+DEFAULT_MINIMUM_BATCH_SIZE_FOR_QUANTIZATION = 1024
+DEFAULT_OVER_QUERY_FACTOR = 5
+DEFAULT_QUERY_SIMILARITY_THRESHOLD = 0.0
+DEFAULT_QUERY_RERANK_FLOOR = 0.0
+PQ_TRAINING_SAMPLE_LIMIT = 128_000  # jVector ProductQuantization.MAX_PQ_TRAINING_SET_SIZE
+PQ_LLOYD_ITERATIONS = 6
+
+
+class VectorSimilarityFunction(enum.Enum):
+    """Lucene's enum; `.jvector_ord` is the meta-file simOrd (JVectorReader.java:389-394)."""
+
+    EUCLIDEAN = N.SIM_EUCLIDEAN
+    DOT_PRODUCT = N.SIM_DOT
+    COSINE = N.SIM_COSINE
+    MAXIMUM_INNER_PRODUCT = N.SIM_MIP
+
+    @property
+    def jvector_ord(self) -> int:
+        return self.value
+
+
+def default_num_subspaces(original_dimension: int) -> int:
+    """JVectorIndexQuantization.PQ.defaultNumSubspaces, JVectorIndexQuantization.java:428-446."""
+    d = original_dimension
+    if d <= 32:
+        return d
+    if d <= 64:
+        return 32
+    if d <= 200:
+        return int(d * 0.5)
+    if d <= 400:
+        return 100
+    if d <= 768:
+        return int(d * 0.25)
+    if d <= 1536:
+        return 192
+    return int(d * 0.125)
+
+
+class GraphNodeIdToDocMap:
+    """GraphNodeIdToDocMap.java: ordinal <-> Lucene docId arrays."""
+
+    NO_VECTOR_OR_DELETED_DOC = -1
+
+    def __init__(self, ordinals_to_doc_ids: Sequence[int], max_docs: Optional[int] = None):
+        self.graph_node_ids_to_doc_ids = np.ascontiguousarray(ordinals_to_doc_ids, dtype=np.int32)
+        live = self.graph_node_ids_to_doc_ids[self.graph_node_ids_to_doc_ids >= 0]
+        self.max_docs = int(max_docs) if max_docs is not None else (int(live.max()) + 1 if live.size else 0)
+        if live.size and int(live.max()) >= self.max_docs:
+            raise ValueError("docId exceeds maxDocs")
+        self.doc_ids_to_graph_node_ids = np.full(self.max_docs, -1, dtype=np.int32)
+        ords = np.nonzero(self.graph_node_ids_to_doc_ids >= 0)[0]
+        self.doc_ids_to_graph_node_ids[self.graph_node_ids_to_doc_ids[ords]] = ords
+
+    def get_lucene_doc_id(self, graph_node_id: int) -> int:
+        return int(self.graph_node_ids_to_doc_ids[graph_node_id])
+
+    def get_jvector_node_id(self, doc_id: int) -> int:
+        return int(self.doc_ids_to_graph_node_ids[doc_id])
+
+
+# ---- collectors (Lucene TopKnnCollector + JVectorKnnCollector.java) -------------------------------
+@dataclass(order=True)
+class ScoreDoc:
+    score: float
+    doc: int
+
+
+class TopKnnCollector:
+    """Lucene TopKnnCollector: bounded min-heap of (score, doc); ties prefer the lower docId."""
+
+    def __init__(self, k: int, visit_limit: int = 2**31 - 1):
+        self._k = k
+        self._heap: List[tuple] = []  # (score, -doc): worst on top
+        self._visited = 0
+        self._visit_limit = visit_limit
+
+    def k(self) -> int:
+        return self._k
+
+    def collect(self, doc_id: int, similarity: float) -> bool:
+        item = (float(similarity), -int(doc_id))
+        if len(self._heap) < self._k:
+            heapq.heappush(self._heap, item)
+            return True
+        if item > self._heap[0]:
+            heapq.heapreplace(self._heap, item)
+            return True
+        return False
+
+    def inc_visited_count(self, count: int) -> None:
+        self._visited += count
+
+    def visited_count(self) -> int:
+        return self._visited
+
+    def visit_limit(self) -> int:
+        return self._visit_limit
+
+    def early_terminated(self) -> bool:
+        return self._visited >= self._visit_limit
+
+    def min_competitive_similarity(self) -> float:
+        return self._heap[0][0] if len(self._heap) >= self._k else float("-inf")
+
+    def top_docs(self) -> List[ScoreDoc]:
+        return [ScoreDoc(s, -nd) for s, nd in sorted(self._heap, reverse=True)]
+
+
+@dataclass
+class JVectorKnnCollector:
+    """JVectorKnnCollector.java:16-21 — carries threshold / rerankFloor / overQueryFactor to the reader."""
+
+    delegate: TopKnnCollector
+    threshold: float = DEFAULT_QUERY_SIMILARITY_THRESHOLD
+    rerank_floor: float = DEFAULT_QUERY_RERANK_FLOOR
+    over_query_factor: int = DEFAULT_OVER_QUERY_FACTOR
+
+    def k(self):
+        return self.delegate.k()
+
+    def collect(self, doc_id, similarity):
+        return self.delegate.collect(doc_id, similarity)
+
+    def inc_visited_count(self, count):
+        self.delegate.inc_visited_count(count)
+
+    def visited_count(self):
+        return self.delegate.visited_count()
+
+    def top_docs(self):
+        return self.delegate.top_docs()
+
+
+class KNNCounter:
+    """plugin/stats/KNNCounter.java:30-37 — the counters JVectorReader.java:189-193 bumps."""
+
+    _lock = threading.Lock()
+    KNN_QUERY_VISITED_NODES = 0
+    KNN_QUERY_RERANKED_COUNT = 0
+    KNN_QUERY_EXPANDED_NODES = 0
+    KNN_QUERY_EXPANDED_BASE_LAYER_NODES = 0
+
+    @classmethod
+    def add(cls, visited, reranked, expanded, expanded_base):
+        with cls._lock:
+            cls.KNN_QUERY_VISITED_NODES += int(visited)
+            cls.KNN_QUERY_RERANKED_COUNT += int(reranked)
+            cls.KNN_QUERY_EXPANDED_NODES += int(expanded)
+            cls.KNN_QUERY_EXPANDED_BASE_LAYER_NODES += int(expanded_base)
+
+
+# ---- segment container ------------------------------------------------------------------------------
+@dataclass
+class FieldData:
+    """Decoded arrays of one field of one flushed/merged segment (what OnDiskGraphIndex + PQVectors + the
+    meta record hold; persisted layout: SURVEY Appendix B)."""
+
+    similarity: VectorSimilarityFunction
+    vectors: np.ndarray                     # [n, dim] fp32, ordinal order (InlineVectors)
+    adjacency: np.ndarray                   # [n, R] int32, -1 padded
+    entry_node: int
+    doc_map: GraphNodeIdToDocMap
+    pq_m: int = 0
+    pq_k: int = 0
+    pq_codebooks: Optional[np.ndarray] = None
+    pq_global_centroid: Optional[np.ndarray] = None
+    pq_codes: Optional[np.ndarray] = None
+
+
+@dataclass
+class Segment:
+    max_doc: int
+    fields: Dict[str, FieldData] = field(default_factory=dict)
+
+
+class JVectorIndexQuantization:
+    """PQ strategy of JVectorIndexQuantization.java:114-140 on the GPU (train = K8, encode = K6)."""
+
+    @staticmethod
+    def compute_pq_vectors(vectors: np.ndarray, similarity: VectorSimilarityFunction, num_subspaces: int, device: int = 0,
+                           seed: int = 0):
+        n = vectors.shape[0]
+        clusters = min(256, n)                                        # :122
+        center = similarity == VectorSimilarityFunction.EUCLIDEAN     # :127
+        sample = vectors
+        if n > PQ_TRAINING_SAMPLE_LIMIT:
+            rng = np.random.default_rng(seed)
+            sample = vectors[np.sort(rng.choice(n, PQ_TRAINING_SAMPLE_LIMIT, replace=False))]
+        codebooks, gcent = pq_train(sample, num_subspaces, clusters, center, PQ_LLOYD_ITERATIONS, seed, device)
+        codes = pq_encode(vectors, num_subspaces, clusters, codebooks, gcent, device)     # :133
+        return num_subspaces, clusters, codebooks, gcent, codes
+
+
+class JVectorWriter:
+    """Flush path of JVectorWriter.java:216-283: buffer vectors, quantise when n >= minBatch, build the
+    Vamana graph, hand back the decoded segment arrays.  Graph build and PQ training run on the GPU through
+    the C-ABI "next" entry points (jv_graph_build / jv_pq_train)."""
+
+    def __init__(self, max_conn: int = DEFAULT_MAX_CONN, beam_width: int = DEFAULT_BEAM_WIDTH,
+                 neighbor_overflow: float = DEFAULT_NEIGHBOR_OVERFLOW, alpha: float = DEFAULT_ALPHA,
+                 min_batch_size_for_quantization: int = DEFAULT_MINIMUM_BATCH_SIZE_FOR_QUANTIZATION,
+                 num_pq_subspaces=default_num_subspaces, device: int = 0):
+        self.max_conn, self.beam_width = max_conn, beam_width
+        self.neighbor_overflow, self.alpha = neighbor_overflow, alpha
+        self.min_batch = min_batch_size_for_quantization
+        self.num_pq_subspaces = num_pq_subspaces
+        self.device = device
+        self._fields: Dict[str, dict] = {}
+
+    def add_field(self, name: str, similarity: VectorSimilarityFunction):
+        self._fields[name] = {"sim": similarity, "docs": [], "vecs": []}
+
+    def add_value(self, name: str, doc_id: int, vector: Sequence[float]):
+        f = self._fields[name]
+        v = np.asarray(vector)
+        if v.dtype.kind not in "fiu" or v.dtype == np.uint8 or v.dtype == np.int8:
+            raise NotImplementedError("Byte vectors are not supported by jVector (JVectorWriter.java:176-184)")
+        f["docs"].append(int(doc_id))
+        f["vecs"].append(np.asarray(v, dtype=np.float32))
+
+    def flush(self, max_doc: int) -> Segment:
+        seg = Segment(max_doc=max_doc)
+        for name, f in self._fields.items():
+            vecs = np.stack(f["vecs"]).astype(np.float32) if f["vecs"] else np.zeros((0, 1), np.float32)
+            sim: VectorSimilarityFunction = f["sim"]
+            doc_map = GraphNodeIdToDocMap(f["docs"], max_doc)
+            n = vecs.shape[0]
+            fd = FieldData(sim, vecs, np.zeros((n, self.max_conn), np.int32), 0, doc_map)
+            if n > 0:
+                fd.adjacency, fd.entry_node = graph_build(vecs, sim.jvector_ord, self.max_conn, self.beam_width,
+                                                          self.neighbor_overflow, self.alpha, self.device)
+            if n >= self.min_batch:                                   # JVectorWriter.java:267-279
+                m = self.num_pq_subspaces(vecs.shape[1])
+                fd.pq_m, fd.pq_k, fd.pq_codebooks, fd.pq_global_centroid, fd.pq_codes = \
+                    JVectorIndexQuantization.compute_pq_vectors(vecs, sim, m, self.device)
+            seg.fields[name] = fd
+        return seg
+
+
+class JVectorReader:
+    """JVectorReader.java — per-segment reader; `search` is the drop-in for JVectorReader.java:130-210."""
+
+    def __init__(self, segment: Segment, device: int = 0, flags: int = 0):
+        self._segment = segment
+        self._entries: Dict[str, GpuIndex] = {}
+        self._closed = False
+        for name, fd in segment.fields.items():   # FieldEntry ctor, :284-337
+            self._entries[name] = GpuIndex(
+                fd.similarity.jvector_ord, fd.vectors, fd.adjacency, fd.entry_node,
+                ord_to_doc=fd.doc_map.graph_node_ids_to_doc_ids, max_doc=segment.max_doc, pq_m=fd.pq_m, pq_k=fd.pq_k,
+                pq_codebooks=fd.pq_codebooks, pq_global_centroid=fd.pq_global_centroid, pq_codes=fd.pq_codes,
+                device=device, flags=flags)
+
+    def field_index(self, field: str) -> GpuIndex:
+        return self._entries[field]
+
+    @staticmethod
+    def _wrap(knn_collector) -> JVectorKnnCollector:
+        if isinstance(knn_collector, JVectorKnnCollector):
+            return knn_collector
+        # JVectorReader.java:133-144: re-wrap a plain collector with the defaults
+        return JVectorKnnCollector(knn_collector, DEFAULT_QUERY_SIMILARITY_THRESHOLD, DEFAULT_QUERY_RERANK_FLOOR,
+                                   DEFAULT_OVER_QUERY_FACTOR)
+
+    def search(self, field: str, target, knn_collector, accept_docs=None) -> None:
+        """KnnVectorsReader.search(String, float[], KnnCollector, AcceptDocs).  `accept_docs`: None or a
+        bool mask / FixedBitSet words over Lucene docIds."""
+        t = np.asarray(target)
+        if t.dtype in (np.int8, np.uint8):
+            raise NotImplementedError("Byte vector search is not supported yet with jVector")  # :241-245
+        self.search_batch(field, t.reshape(1, -1), [knn_collector], accept_docs)
+
+    def search_batch(self, field: str, targets, knn_collectors: Sequence, accept_docs=None) -> None:
+        """New entry point: one call for many queries of one field (same k / parameters per batch)."""
+        if self._closed:
+            raise ValueError("reader is closed")
+        ix = self._entries[field]
+        cols = [self._wrap(c) for c in knn_collectors]
+        c0 = cols[0]
+        k = c0.k()
+        bits = None
+        if accept_docs is not None:
+            a = np.asarray(accept_docs)
+            bits = a if a.dtype == np.uint64 else make_accept_bits(a)
+        if ix.n == 0:
+            return
+        res = ix.search(np.asarray(targets, dtype=np.float32), k, k * c0.over_query_factor, c0.threshold, c0.rerank_floor,
+                        bits)
+        for i, col in enumerate(cols):
+            for j in range(int(res.counts[i])):
+                col.collect(int(res.docs[i, j]), float(res.scores[i, j]))            # :175-177
+            visited, expanded, expanded_base, reranked = (int(x) for x in res.stats[i])
+            KNNCounter.add(visited, reranked, expanded, expanded_base)                  # :189-193
+            if visited + expanded > 0:
+                col.inc_visited_count(visited + expanded)                               # :204-207
+
+    def exact_search(self, field: str, target, k: int, accept_docs=None) -> List[ScoreDoc]:
+        """Lucene exactSearch over FloatVectorValues.scorer(target) (JVectorVectorScorer.java:36-53)."""
+        ix = self._entries[field]
+        bits = None
+        if accept_docs is not None:
+            a = np.asarray(accept_docs)
+            bits = a if a.dtype == np.uint64 else make_accept_bits(a)
+        if ix.n == 0:
+            return []
+        docs, scores, counts = ix.exact_topk(np.asarray(target, dtype=np.float32).reshape(1, -1), k, bits)
+        return [ScoreDoc(float(scores[0, j]), int(docs[0, j])) for j in range(int(counts[0]))]
+
+    def get_float_vector_values(self, field: str) -> np.ndarray:
+        return self._segment.fields[field].vectors
+
+    def close(self):
+        for ix in self._entries.values():
+            ix.close()
+        self._entries.clear()
+        self._closed = True
+
+
+@dataclass
+class JVectorKnnFloatVectorQuery:
+    """JVectorKnnFloatVectorQuery.java:50-70 — per-leaf approximateSearch with the jVector parameters."""
+
+    field: str
+    target: Sequence[float]
+    k: int
+    over_query_factor: int = DEFAULT_OVER_QUERY_FACTOR
+    threshold: float = DEFAULT_QUERY_SIMILARITY_THRESHOLD
+    rerank_floor: float = DEFAULT_QUERY_RERANK_FLOOR
+
+    def search(self, readers: Sequence[JVectorReader], accept_docs: Optional[Sequence] = None,
+               doc_bases: Optional[Sequence[int]] = None) -> List[ScoreDoc]:
+        """Per-leaf search + TopDocs.merge(k) across leaves (ties -> lower global docId)."""
+        merged: List[ScoreDoc] = []
+        for li, r in enumerate(readers):
+            col = JVectorKnnCollector(TopKnnCollector(self.k), self.threshold, self.rerank_floor, self.over_query_factor)
+            r.search(self.field, self.target, col, None if accept_docs is None else accept_docs[li])
+            base = 0 if doc_bases is None else doc_bases[li]
+            merged += [ScoreDoc(sd.score, sd.doc + base) for sd in col.top_docs()]
+        merged.sort(key=lambda sd: (-sd.score, sd.doc))
+        return merged[: self.k]

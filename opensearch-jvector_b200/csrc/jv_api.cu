@@ -1,0 +1,584 @@
+// jv_api.cu — the extern "C" boundary of libjvgpu.so (include/jvgpu.h): argument validation, index
+// lifetime, per-call context pool, H2D/D2H staging, timing.  No torch, no CPU compute fallback.
+#include <stdarg.h>
+
+#include "jv_internal.h"
+
+namespace jv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+int32_t SearchCtx::init(int) {
+    JV_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto &e : ev) JV_CUDA_TRY(cudaEventCreate(&e));
+    return JV_OK;
+}
+int32_t SearchCtx::ensure_pinned(size_t bytes) {
+    if (bytes <= pinned_bytes) return JV_OK;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_bytes = 0;
+    JV_CUDA_TRY(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
+    pinned_bytes = bytes;
+    return JV_OK;
+}
+void SearchCtx::destroy() {
+    if (stream) cudaStreamDestroy(stream);
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e);
+    if (pinned) cudaFreeHost(pinned);
+    stream = nullptr;
+    pinned = nullptr;
+}
+
+}  // namespace jv
+
+jv::SearchCtx *jv_index::acquire() {
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pool.empty()) {
+            jv::SearchCtx *c = pool.back();
+            pool.pop_back();
+            return c;
+        }
+    }
+    auto *c = new jv::SearchCtx();
+    if (c->init(device) != JV_OK) {
+        c->destroy();
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+void jv_index::release(jv::SearchCtx *c) {
+    std::lock_guard<std::mutex> lk(mu);
+    pool.push_back(c);
+}
+
+using namespace jv;
+
+namespace {
+
+struct CtxLease {
+    jv_index *ix;
+    SearchCtx *c;
+    explicit CtxLease(jv_index *i) : ix(i), c(i->acquire()) {}
+    ~CtxLease() {
+        if (c) ix->release(c);
+    }
+};
+
+int32_t check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no usable CUDA device (%s); libjvgpu has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        return JV_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (0..%d)", device, count - 1);
+        return JV_ERR_INVALID_ARGUMENT;
+    }
+    return JV_OK;
+}
+
+int32_t upload(DevBuf &b, const void *src, size_t bytes, int64_t *total) {
+    JV_TRY(b.alloc(bytes));
+    if (bytes) JV_CUDA_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    *total += (int64_t)bytes;
+    return JV_OK;
+}
+
+int32_t validate_params(const jv_index *ix, int32_t nq, const jv_search_params *p) {
+    JV_REQUIRE(ix != nullptr, "index is NULL");
+    JV_REQUIRE(p != nullptr, "params is NULL");
+    JV_REQUIRE(p->struct_size == (int32_t)sizeof(jv_search_params), "jv_search_params.struct_size mismatch");
+    JV_REQUIRE(nq >= 0, "nq must be >= 0");
+    JV_REQUIRE(p->k >= 1, "k must be >= 1");
+    JV_REQUIRE(p->rerank_k >= p->k, "rerankK must be >= topK (GraphSearcher contract)");
+    JV_REQUIRE(p->rerank_k <= 4096, "rerank_k > 4096 not supported");
+    JV_REQUIRE(p->accept_stride_words >= 0, "accept_stride_words must be >= 0");
+    return JV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t jv_version(void) { return (JVGPU_VERSION_MAJOR << 16) | JVGPU_VERSION_MINOR; }
+
+const char *jv_last_error(void) { return get_error(); }
+
+int32_t jv_device_count(int32_t *out_count) {
+    JV_REQUIRE(out_count != nullptr, "out_count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *out_count = 0;
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return JV_ERR_CUDA;
+    }
+    *out_count = c;
+    return JV_OK;
+}
+
+int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
+    JV_REQUIRE(d != nullptr && out != nullptr, "desc/out is NULL");
+    *out = nullptr;
+    JV_REQUIRE(d->struct_size == (int32_t)sizeof(jv_index_desc), "jv_index_desc.struct_size mismatch (%d vs %zu)", d->struct_size,
+               sizeof(jv_index_desc));
+    JV_REQUIRE(d->similarity >= JV_SIM_EUCLIDEAN && d->similarity <= JV_SIM_MIP, "unknown similarity ordinal %d", d->similarity);
+    JV_REQUIRE(d->dim >= 1 && d->n >= 0 && d->n < 0x7fffffffLL, "bad dim/n");
+    JV_REQUIRE(d->max_degree >= 1 && d->max_degree <= 128, "max_degree must be in [1,128]");
+    JV_REQUIRE(d->n == 0 || (d->adjacency && d->vectors), "adjacency/vectors are NULL");
+    JV_REQUIRE(d->n == 0 || (d->entry_node >= 0 && d->entry_node < d->n), "entry_node out of range");
+    const bool has_pq = d->pq_m > 0;
+    if (has_pq) {
+        JV_REQUIRE(d->pq_codes && d->pq_codebooks, "pq_codes/pq_codebooks are NULL");
+        JV_REQUIRE(d->pq_k >= 1 && d->pq_k <= 256 && d->pq_m <= d->dim, "bad PQ shape M=%d K=%d", d->pq_m, d->pq_k);
+        if (d->pq_global_centroid && d->similarity != JV_SIM_EUCLIDEAN) {
+            set_error("a PQ global centroid is only defined for EUCLIDEAN (JVectorIndexQuantization.java:127)");
+            return JV_ERR_UNSUPPORTED;
+        }
+    }
+    JV_TRY(check_device(d->device));
+    DeviceGuard guard(d->device);
+
+    auto *ix = new jv_index();
+    ix->device = d->device;
+    ix->sim = d->similarity;
+    ix->dim = d->dim;
+    ix->R = d->max_degree;
+    ix->entry = d->entry_node;
+    ix->max_doc = d->max_doc;
+    ix->n = d->n;
+    ix->flags = d->flags;
+    ix->has_pq = has_pq;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) == cudaSuccess) {
+        ix->sm_count = prop.multiProcessorCount;
+        ix->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    int64_t total = 0;
+    int32_t st = JV_OK;
+    auto fail = [&](int32_t s) {
+        jv_index_destroy(ix);
+        return s;
+    };
+    if ((st = ix->dbg.alloc(16)) != JV_OK) return fail(st);
+    cudaMemset(ix->dbg.p, 0, 16);
+    const size_t n = (size_t)d->n;
+    if ((st = upload(ix->adjacency, d->adjacency, n * d->max_degree * 4, &total)) != JV_OK) return fail(st);
+    if (d->flags & JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE) {
+        // cfg 5: fp32 rerank vectors stay in pinned, device-mapped host memory
+        cudaError_t e = cudaHostAlloc(&ix->vectors_host, n * d->dim * 4 + 16, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            set_error("cudaHostAlloc(vectors): %s", cudaGetErrorString(e));
+            return fail(JV_ERR_OUT_OF_MEMORY);
+        }
+        memcpy(ix->vectors_host, d->vectors, n * d->dim * 4);
+        void *dp = nullptr;
+        e = cudaHostGetDevicePointer(&dp, ix->vectors_host, 0);
+        if (e != cudaSuccess) {
+            set_error("cudaHostGetDevicePointer: %s", cudaGetErrorString(e));
+            return fail(JV_ERR_CUDA);
+        }
+        ix->vectors_dev = static_cast<float *>(dp);
+        ix->vectors_on_host = true;
+    } else {
+        if ((st = upload(ix->vectors, d->vectors, n * d->dim * 4, &total)) != JV_OK) return fail(st);
+        ix->vectors_dev = ix->vectors.as<float>();
+    }
+    if (d->ord_to_doc)
+        if ((st = upload(ix->ord_to_doc, d->ord_to_doc, n * 4, &total)) != JV_OK) return fail(st);
+    if (d->similarity == JV_SIM_COSINE && n > 0) {
+        if ((st = ix->vec_norm.alloc(n * 4)) != JV_OK) return fail(st);
+        total += (int64_t)n * 4;
+        if ((st = launch_vec_norms(nullptr, ix->vectors_dev, d->n, d->dim, ix->vec_norm.as<float>())) != JV_OK) return fail(st);
+    }
+    if (has_pq) {
+        ix->pq.init(d->dim, d->pq_m, d->pq_k);
+        ix->code_stride = (d->pq_m + 15) & ~15;
+        if ((st = upload(ix->codebooks, d->pq_codebooks, (size_t)ix->pq.cb_floats * 4, &total)) != JV_OK) return fail(st);
+        if (d->pq_global_centroid)
+            if ((st = upload(ix->gcent, d->pq_global_centroid, (size_t)d->dim * 4, &total)) != JV_OK) return fail(st);
+        std::vector<int32_t> cbo(d->pq_m);
+        for (int m = 0; m < d->pq_m; m++) cbo[m] = (int32_t)ix->pq.cb_off[m];
+        if ((st = upload(ix->pq_size, ix->pq.size.data(), (size_t)d->pq_m * 4, &total)) != JV_OK) return fail(st);
+        if ((st = upload(ix->pq_off, ix->pq.off.data(), (size_t)d->pq_m * 4, &total)) != JV_OK) return fail(st);
+        if ((st = upload(ix->pq_cboff, cbo.data(), (size_t)d->pq_m * 4, &total)) != JV_OK) return fail(st);
+        if ((st = ix->codes.alloc(n * ix->code_stride)) != JV_OK) return fail(st);
+        total += (int64_t)n * ix->code_stride;
+        if (n > 0) {
+            if (cudaMemset(ix->codes.p, 0, n * ix->code_stride) != cudaSuccess ||
+                cudaMemcpy2D(ix->codes.p, ix->code_stride, d->pq_codes, d->pq_m, d->pq_m, n, cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("uploading PQ codes failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return fail(JV_ERR_CUDA);
+            }
+        }
+        if (d->similarity == JV_SIM_COSINE && n > 0) {
+            if ((st = ix->node_norm.alloc(n * 4)) != JV_OK) return fail(st);
+            total += (int64_t)n * 4;
+            if ((st = launch_node_norms(nullptr, ix, ix->node_norm.as<float>())) != JV_OK) return fail(st);
+        }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("index creation kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(JV_ERR_CUDA);
+    }
+    ix->device_bytes = total;
+    *out = ix;
+    return JV_OK;
+}
+
+int32_t jv_index_destroy(jv_index *ix) {
+    if (!ix) return JV_OK;
+    DeviceGuard guard(ix->device);
+    for (auto *c : ix->pool) {
+        c->destroy();
+        delete c;
+    }
+    ix->pool.clear();
+    if (ix->vectors_host) cudaFreeHost(ix->vectors_host);
+    delete ix;
+    return JV_OK;
+}
+
+int32_t jv_index_device_bytes(const jv_index *ix, int64_t *out_bytes) {
+    JV_REQUIRE(ix && out_bytes, "NULL argument");
+    *out_bytes = ix->device_bytes;
+    return JV_OK;
+}
+
+int32_t jv_index_debug_counter(jv_index *ix, int32_t which, int64_t *out_value) {
+    JV_REQUIRE(ix && out_value && which >= 0 && which < 4, "bad arguments");
+    DeviceGuard guard(ix->device);
+    int32_t v[4] = {0, 0, 0, 0};
+    JV_CUDA_TRY(cudaMemcpy(v, ix->dbg.p, 16, cudaMemcpyDeviceToHost));
+    *out_value = v[which];
+    return JV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// search
+// -------------------------------------------------------------------------------------------------
+static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, int32_t nq, const jv_search_params *p,
+                           const uint64_t *d_accept, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
+                           jv_query_stats *d_stats, int *launches) {
+    JV_TRY(c->approx_keys.ensure((size_t)nq * p->rerank_k * 8));
+    JV_TRY(c->approx_count.ensure((size_t)nq * 4));
+    SearchLaunch a;
+    a.d_queries = d_queries;
+    a.nq = nq;
+    a.rerank_k = p->rerank_k;
+    a.threshold = p->threshold;
+    a.d_accept = d_accept;
+    a.accept_stride_words = p->accept_stride_words;
+    a.d_approx_keys = c->approx_keys.as<uint64_t>();
+    a.d_approx_count = c->approx_count.as<int32_t>();
+    a.d_stats = d_stats;
+    a.entry_override = -1;
+    a.n_limit = ix->n;
+    JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    JV_TRY(launch_search(ix, c, a, launches));
+    JV_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    JV_TRY(launch_rerank(ix, c, d_queries, nq, p->k, p->rerank_k, p->rerank_floor, a.d_approx_keys, a.d_approx_count, d_out_doc,
+                         d_out_score, d_out_count, d_stats, launches));
+    JV_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    return JV_OK;
+}
+
+static void fill_timing(SearchCtx *c, jv_batch_timing *t, int launches, bool host) {
+    if (!t) return;
+    memset(t, 0, sizeof(*t));
+    cudaEventElapsedTime(&t->search_ms, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&t->rerank_ms, c->ev[2], c->ev[3]);
+    if (host) {
+        cudaEventElapsedTime(&t->h2d_ms, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&t->d2h_ms, c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&t->total_ms, c->ev[0], c->ev[4]);
+    } else {
+        cudaEventElapsedTime(&t->total_ms, c->ev[1], c->ev[3]);
+    }
+    t->launches = launches;
+}
+
+int32_t jv_search_batch_dev(jv_index *ix, const float *d_queries, int32_t nq, const jv_search_params *p, int32_t *d_out_doc,
+                            float *d_out_score, int32_t *d_out_count, jv_query_stats *d_stats, jv_batch_timing *timing) {
+    JV_TRY(validate_params(ix, nq, p));
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(d_queries && d_out_doc && d_out_score && d_out_count, "NULL buffer");
+    JV_REQUIRE(ix->n > 0, "index is empty");
+    DeviceGuard guard(ix->device);
+    CtxLease lease(ix);
+    JV_REQUIRE(lease.c != nullptr, "could not create a search context: %s", get_error());
+    SearchCtx *c = lease.c;
+    jv_query_stats *st = d_stats;
+    if (!st) {
+        JV_TRY(c->stats.ensure((size_t)nq * sizeof(jv_query_stats)));
+        st = c->stats.as<jv_query_stats>();
+    }
+    int launches = 0;
+    JV_TRY(search_core(ix, c, d_queries, nq, p, p->accept_bits, d_out_doc, d_out_score, d_out_count, st, &launches));
+    JV_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fill_timing(c, timing, launches, false);
+    return JV_OK;
+}
+
+int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv_search_params *p, int32_t *out_doc,
+                        float *out_score, int32_t *out_count, jv_query_stats *stats, jv_batch_timing *timing) {
+    JV_TRY(validate_params(ix, nq, p));
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(queries && out_doc && out_score && out_count, "NULL buffer");
+    if (ix->n == 0) { // empty segment: nothing to collect
+        for (int64_t i = 0; i < (int64_t)nq * p->k; i++) out_doc[i] = -1, out_score[i] = 0.f;
+        for (int i = 0; i < nq; i++) out_count[i] = 0;
+        if (stats) memset(stats, 0, sizeof(jv_query_stats) * (size_t)nq);
+        if (timing) memset(timing, 0, sizeof(*timing));
+        return JV_OK;
+    }
+    DeviceGuard guard(ix->device);
+    CtxLease lease(ix);
+    JV_REQUIRE(lease.c != nullptr, "could not create a search context: %s", get_error());
+    SearchCtx *c = lease.c;
+    const size_t qbytes = (size_t)nq * ix->dim * 4, kb = (size_t)nq * p->k * 4;
+    JV_TRY(c->queries.ensure(qbytes));
+    JV_TRY(c->out_doc.ensure(kb));
+    JV_TRY(c->out_score.ensure(kb));
+    JV_TRY(c->out_count.ensure((size_t)nq * 4));
+    JV_TRY(c->stats.ensure((size_t)nq * sizeof(jv_query_stats)));
+    const uint64_t *d_accept = nullptr;
+    size_t abytes = 0;
+    if (p->accept_bits) {
+        const size_t words = (size_t)((ix->max_doc + 63) / 64);
+        abytes = (p->accept_stride_words ? (size_t)(nq - 1) * p->accept_stride_words + words : words) * 8;
+        JV_TRY(c->accept.ensure(abytes));
+        d_accept = c->accept.as<uint64_t>();
+    }
+    JV_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+    if (abytes) JV_CUDA_TRY(cudaMemcpyAsync(c->accept.p, p->accept_bits, abytes, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    JV_TRY(search_core(ix, c, c->queries.as<float>(), nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
+                       c->out_count.as<int32_t>(), c->stats.as<jv_query_stats>(), &launches));
+    JV_CUDA_TRY(cudaMemcpyAsync(out_doc, c->out_doc.p, kb, cudaMemcpyDeviceToHost, c->stream));
+    JV_CUDA_TRY(cudaMemcpyAsync(out_score, c->out_score.p, kb, cudaMemcpyDeviceToHost, c->stream));
+    JV_CUDA_TRY(cudaMemcpyAsync(out_count, c->out_count.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (stats)
+        JV_CUDA_TRY(cudaMemcpyAsync(stats, c->stats.p, (size_t)nq * sizeof(jv_query_stats), cudaMemcpyDeviceToHost, c->stream));
+    JV_CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    JV_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fill_timing(c, timing, launches, true);
+    return JV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// brute force
+// -------------------------------------------------------------------------------------------------
+int32_t jv_exact_topk_dev(jv_index *ix, const float *d_queries, int32_t nq, int32_t k, const uint64_t *d_accept_bits,
+                          int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count) {
+    JV_REQUIRE(ix && nq >= 0 && k >= 1, "bad arguments");
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(d_queries && d_out_doc && d_out_score && d_out_count, "NULL buffer");
+    JV_REQUIRE(ix->n > 0, "index is empty");
+    DeviceGuard guard(ix->device);
+    CtxLease lease(ix);
+    JV_REQUIRE(lease.c != nullptr, "could not create a search context: %s", get_error());
+    int launches = 0;
+    JV_TRY(launch_exact_topk(ix, lease.c, d_queries, nq, k, d_accept_bits, accept_stride_words, d_out_doc, d_out_score,
+                             d_out_count, &launches));
+    JV_CUDA_TRY(cudaStreamSynchronize(lease.c->stream));
+    return JV_OK;
+}
+
+int32_t jv_exact_topk(jv_index *ix, const float *queries, int32_t nq, int32_t k, const uint64_t *accept_bits,
+                      int64_t accept_stride_words, int32_t *out_doc, float *out_score, int32_t *out_count) {
+    JV_REQUIRE(ix && nq >= 0 && k >= 1, "bad arguments");
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(queries && out_doc && out_score && out_count, "NULL buffer");
+    if (ix->n == 0) {
+        for (int64_t i = 0; i < (int64_t)nq * k; i++) out_doc[i] = -1, out_score[i] = 0.f;
+        for (int i = 0; i < nq; i++) out_count[i] = 0;
+        return JV_OK;
+    }
+    DeviceGuard guard(ix->device);
+    CtxLease lease(ix);
+    JV_REQUIRE(lease.c != nullptr, "could not create a search context: %s", get_error());
+    SearchCtx *c = lease.c;
+    const size_t qbytes = (size_t)nq * ix->dim * 4, kb = (size_t)nq * k * 4;
+    JV_TRY(c->queries.ensure(qbytes));
+    JV_TRY(c->out_doc.ensure(kb));
+    JV_TRY(c->out_score.ensure(kb));
+    JV_TRY(c->out_count.ensure((size_t)nq * 4));
+    const uint64_t *d_accept = nullptr;
+    if (accept_bits) {
+        const size_t words = (size_t)((ix->max_doc + 63) / 64);
+        const size_t abytes = (accept_stride_words ? (size_t)(nq - 1) * accept_stride_words + words : words) * 8;
+        JV_TRY(c->accept.ensure(abytes));
+        JV_CUDA_TRY(cudaMemcpyAsync(c->accept.p, accept_bits, abytes, cudaMemcpyHostToDevice, c->stream));
+        d_accept = c->accept.as<uint64_t>();
+    }
+    JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    JV_TRY(launch_exact_topk(ix, c, c->queries.as<float>(), nq, k, d_accept, accept_stride_words, c->out_doc.as<int32_t>(),
+                             c->out_score.as<float>(), c->out_count.as<int32_t>(), &launches));
+    JV_CUDA_TRY(cudaMemcpyAsync(out_doc, c->out_doc.p, kb, cudaMemcpyDeviceToHost, c->stream));
+    JV_CUDA_TRY(cudaMemcpyAsync(out_score, c->out_score.p, kb, cudaMemcpyDeviceToHost, c->stream));
+    JV_CUDA_TRY(cudaMemcpyAsync(out_count, c->out_count.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    JV_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return JV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// PQ
+// -------------------------------------------------------------------------------------------------
+int32_t jv_pq_encode_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t m, int32_t k,
+                         const float *d_codebooks, const float *d_gcent, uint8_t *d_out_codes, float *out_kernel_ms) {
+    JV_REQUIRE(n >= 0 && dim >= 1 && m >= 1 && m <= dim && k >= 1 && k <= 256, "bad PQ shape");
+    if (n == 0) return JV_OK;
+    JV_REQUIRE(d_vectors && d_codebooks && d_out_codes, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    PqShape s;
+    s.init(dim, m, k);
+    cudaEvent_t e0, e1;
+    JV_CUDA_TRY(cudaEventCreate(&e0));
+    JV_CUDA_TRY(cudaEventCreate(&e1));
+    cudaEventRecord(e0, nullptr);
+    int32_t st = launch_pq_encode(nullptr, s, d_vectors, n, d_codebooks, d_gcent, d_out_codes, m);
+    cudaEventRecord(e1, nullptr);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    JV_TRY(st);
+    JV_CUDA_TRY(e);
+    if (out_kernel_ms) *out_kernel_ms = ms;
+    return JV_OK;
+}
+
+int32_t jv_pq_encode(int32_t device, const float *vectors, int64_t n, int32_t dim, int32_t m, int32_t k, const float *codebooks,
+                     const float *gcent, uint8_t *out_codes, float *out_kernel_ms) {
+    JV_REQUIRE(n >= 0 && dim >= 1 && m >= 1 && m <= dim && k >= 1 && k <= 256, "bad PQ shape");
+    if (n == 0) return JV_OK;
+    JV_REQUIRE(vectors && codebooks && out_codes, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    PqShape s;
+    s.init(dim, m, k);
+    DevBuf dcb, dg, dx, dout;
+    JV_TRY(dcb.alloc((size_t)s.cb_floats * 4));
+    JV_CUDA_TRY(cudaMemcpy(dcb.p, codebooks, (size_t)s.cb_floats * 4, cudaMemcpyHostToDevice));
+    if (gcent) {
+        JV_TRY(dg.alloc((size_t)dim * 4));
+        JV_CUDA_TRY(cudaMemcpy(dg.p, gcent, (size_t)dim * 4, cudaMemcpyHostToDevice));
+    }
+    // chunked so arbitrarily large flushes/merges stream through a bounded device buffer
+    const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, ((int64_t)1 << 30) / ((int64_t)dim * 4)));
+    JV_TRY(dx.alloc((size_t)chunk * dim * 4));
+    JV_TRY(dout.alloc((size_t)chunk * m));
+    float total_ms = 0.f;
+    for (int64_t o = 0; o < n; o += chunk) {
+        const int64_t cn = std::min(chunk, n - o);
+        JV_CUDA_TRY(cudaMemcpy(dx.p, vectors + o * dim, (size_t)cn * dim * 4, cudaMemcpyHostToDevice));
+        float ms = 0.f;
+        JV_TRY(jv_pq_encode_dev(device, dx.as<float>(), cn, dim, m, k, dcb.as<float>(), dg.as<float>(), dout.as<uint8_t>(), &ms));
+        total_ms += ms;
+        JV_CUDA_TRY(cudaMemcpy(out_codes + o * m, dout.p, (size_t)cn * m, cudaMemcpyDeviceToHost));
+    }
+    if (out_kernel_ms) *out_kernel_ms = total_ms;
+    return JV_OK;
+}
+
+int32_t jv_pq_lut(jv_index *ix, const float *queries, int32_t nq, float *out_lut) {
+    JV_REQUIRE(ix && queries && out_lut && nq >= 0, "bad arguments");
+    JV_REQUIRE(ix->has_pq, "index has no PQ");
+    if (nq == 0) return JV_OK;
+    DeviceGuard guard(ix->device);
+    DevBuf dq, dl;
+    const size_t lb = (size_t)nq * ix->pq.M * ix->pq.K * 4;
+    JV_TRY(dq.alloc((size_t)nq * ix->dim * 4));
+    JV_TRY(dl.alloc(lb));
+    JV_CUDA_TRY(cudaMemcpy(dq.p, queries, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice));
+    JV_TRY(launch_pq_lut(ix, nullptr, dq.as<float>(), nq, dl.as<float>()));
+    JV_CUDA_TRY(cudaMemcpy(out_lut, dl.p, lb, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
+int32_t jv_pq_adc_scores(jv_index *ix, const float *queries, int32_t nq, const int32_t *nodes, int32_t per_query, float *out) {
+    JV_REQUIRE(ix && queries && nodes && out && nq >= 0 && per_query >= 1, "bad arguments");
+    JV_REQUIRE(ix->has_pq, "index has no PQ");
+    if (nq == 0) return JV_OK;
+    DeviceGuard guard(ix->device);
+    DevBuf dq, dn, dout;
+    JV_TRY(dq.alloc((size_t)nq * ix->dim * 4));
+    JV_TRY(dn.alloc((size_t)nq * per_query * 4));
+    JV_TRY(dout.alloc((size_t)nq * per_query * 4));
+    JV_CUDA_TRY(cudaMemcpy(dq.p, queries, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice));
+    JV_CUDA_TRY(cudaMemcpy(dn.p, nodes, (size_t)nq * per_query * 4, cudaMemcpyHostToDevice));
+    JV_TRY(launch_adc_pairs(ix, nullptr, dq.as<float>(), nq, dn.as<int32_t>(), per_query, dout.as<float>()));
+    JV_CUDA_TRY(cudaMemcpy(out, dout.p, (size_t)nq * per_query * 4, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// merge
+// -------------------------------------------------------------------------------------------------
+int32_t jv_merge_topk_dev(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *d_docs, const float *d_scores,
+                          int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, float *out_kernel_ms) {
+    JV_REQUIRE(g >= 1 && nq >= 0 && k >= 1, "bad arguments");
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(d_docs && d_scores && d_out_doc && d_out_score, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    cudaEvent_t e0, e1;
+    JV_CUDA_TRY(cudaEventCreate(&e0));
+    JV_CUDA_TRY(cudaEventCreate(&e1));
+    cudaEventRecord(e0, nullptr);
+    int32_t st = launch_merge_topk(nullptr, g, nq, k, d_docs, d_scores, d_out_doc, d_out_score, d_out_count);
+    cudaEventRecord(e1, nullptr);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    JV_TRY(st);
+    JV_CUDA_TRY(e);
+    if (out_kernel_ms) *out_kernel_ms = ms;
+    return JV_OK;
+}
+
+int32_t jv_merge_topk(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *docs, const float *scores, int32_t *out_doc,
+                      float *out_score, int32_t *out_count) {
+    JV_REQUIRE(g >= 1 && nq >= 0 && k >= 1, "bad arguments");
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(docs && scores && out_doc && out_score, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    const size_t inb = (size_t)g * nq * k * 4, outb = (size_t)nq * k * 4;
+    DevBuf dd, ds, od, os, oc;
+    JV_TRY(dd.alloc(inb));
+    JV_TRY(ds.alloc(inb));
+    JV_TRY(od.alloc(outb));
+    JV_TRY(os.alloc(outb));
+    JV_TRY(oc.alloc((size_t)nq * 4));
+    JV_CUDA_TRY(cudaMemcpy(dd.p, docs, inb, cudaMemcpyHostToDevice));
+    JV_CUDA_TRY(cudaMemcpy(ds.p, scores, inb, cudaMemcpyHostToDevice));
+    JV_TRY(jv_merge_topk_dev(device, g, nq, k, dd.as<int32_t>(), ds.as<float>(), od.as<int32_t>(), os.as<float>(), oc.as<int32_t>(),
+                             nullptr));
+    JV_CUDA_TRY(cudaMemcpy(out_doc, od.p, outb, cudaMemcpyDeviceToHost));
+    JV_CUDA_TRY(cudaMemcpy(out_score, os.p, outb, cudaMemcpyDeviceToHost));
+    if (out_count) JV_CUDA_TRY(cudaMemcpy(out_count, oc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// jv_internal.h — the opaque index handle and the kernel launchers shared by the .cu files.
+#pragma once
+#include "jv_common.cuh"
+
+namespace jv {
+
+// per-call scratch: one stream + buffers, recycled through a pool so concurrent Java threads
+// (KNNJVectorTests.java:982-1028) never share mutable state.
+struct SearchCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf queries, out_doc, out_score, out_count, stats, accept;
+    DevBuf approx_keys, approx_count; // [nq*rerank_k] uint64 keys (score, ordinal), best first
+    DevBuf counter;                   // persistent-grid work counter
+    DevBuf visited;                   // global visited tables (fallback when they do not fit in smem)
+    DevBuf slice_doc, slice_score;    // brute force: per-slice partial top-k
+    void *pinned = nullptr;           // host staging
+    size_t pinned_bytes = 0;
+    int32_t init(int device);
+    int32_t ensure_pinned(size_t bytes);
+    void destroy();
+};
+
+}  // namespace jv
+
+struct jv_index {
+    int device = 0;
+    int sim = 0, dim = 0, R = 0, entry = 0, max_doc = 0;
+    int64_t n = 0;
+    uint32_t flags = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    bool has_pq = false;
+    bool vectors_on_host = false;
+    jv::PqShape pq;
+    int code_stride = 0; // bytes per code row (M rounded up to 16)
+    jv::DevBuf adjacency, vectors, vec_norm, ord_to_doc, codes, codebooks, gcent, pq_size, pq_off, pq_cboff, node_norm;
+    jv::DevBuf dbg;   // int32[4] diagnostic counters
+    jv::DevBuf fused; // neighbour-interleaved records (optional)
+    int fused_stride = 0;
+    float *vectors_dev = nullptr; // device-visible pointer to the fp32 vectors (HBM or mapped pinned host)
+    void *vectors_host = nullptr;
+    int64_t device_bytes = 0;
+    std::mutex mu;
+    std::vector<jv::SearchCtx *> pool;
+    jv::SearchCtx *acquire();
+    void release(jv::SearchCtx *c);
+};
+
+namespace jv {
+
+// ---- kernel launchers (each returns a jv_status; all work is enqueued on `stream`) ----
+
+// K1+K2 / K4: graph traversal with ADC (PQ) or exact scoring; writes the approximate result list.
+struct SearchLaunch {
+    const float *d_queries;
+    int nq;
+    int rerank_k;
+    float threshold;
+    const uint64_t *d_accept;
+    int64_t accept_stride_words;
+    uint64_t *d_approx_keys; // [nq * rerank_k]
+    int32_t *d_approx_count; // [nq]
+    jv_query_stats *d_stats; // [nq]
+    int entry_override;      // -1 = index entry
+    int64_t n_limit;         // nodes >= n_limit are ignored (graph builder); n for queries
+};
+int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches);
+
+// K3: exact rerank of the approximate list + top-k + ordinal->doc mapping
+int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int rerank_k, float rerank_floor,
+                      const uint64_t *d_approx_keys, const int32_t *d_approx_count, int32_t *d_out_doc, float *d_out_score,
+                      int32_t *d_out_count, jv_query_stats *d_stats, int *launches);
+
+// K5
+int32_t launch_exact_topk(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, const uint64_t *d_accept,
+                          int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
+                          int *launches);
+
+// K7
+int32_t launch_merge_topk(cudaStream_t stream, int g, int nq, int k, const int32_t *d_docs, const float *d_scores,
+                          int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count);
+
+// K6
+int32_t launch_pq_encode(cudaStream_t stream, const PqShape &shape, const float *d_vectors, int64_t n,
+                         const float *d_codebooks, const float *d_gcent, uint8_t *d_out, int out_stride);
+
+// K1 (test hook) + ADC on explicit pairs
+int32_t launch_pq_lut(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, float *d_lut);
+int32_t launch_adc_pairs(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, const int32_t *d_nodes,
+                         int per_query, float *d_out);
+
+// index-creation helpers
+int32_t launch_vec_norms(cudaStream_t stream, const float *d_vectors, int64_t n, int dim, float *d_out);
+int32_t launch_node_norms(cudaStream_t stream, const jv_index *ix, float *d_out);
+int32_t launch_build_fused(cudaStream_t stream, jv_index *ix);
+
+}  // namespace jv

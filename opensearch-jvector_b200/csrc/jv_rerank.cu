@@ -1,0 +1,507 @@
+// jv_rerank.cu — K3 exact rerank + top-k, K5 brute-force exact top-k, K7 merge of per-shard lists.
+//
+// K3 replaces the rerank step inside GraphSearcher.search fed by view.rerankerFor(q, sim)
+//    (JVectorReader.java:355) plus the ordinal->doc mapping and collector hand-off (JVectorReader.java:175-177).
+// K5 replaces JVectorVectorScorer.score() driven by Lucene's exactSearch (JVectorVectorScorer.java:36-53).
+// K7 is the on-device analogue of Lucene TopDocs.merge across segments/shards.
+// All exact scores use the canonical fp32 reduction of jv_common.cuh, bit-identical to the oracle, so
+// top-k ids match exactly with ties broken towards the lower docId.
+#include "jv_internal.h"
+
+namespace jv {
+
+// ------------------------------------------------------------------------------------------------
+// K3: one CTA (4 warps) per query.  Gathers <= rerank_k inline fp32 vectors (dim*4 B each, coalesced
+// 16-byte loads), scores them exactly, selects the top k by rank counting.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRerankThreads = 128;
+
+__global__ void __launch_bounds__(kRerankThreads)
+rerank_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_norm, const int32_t *__restrict__ ord_to_doc,
+              int dim, int sim, int has_pq, const float *__restrict__ queries, int k, int L, float rerank_floor,
+              const uint64_t *__restrict__ approx_keys, const int32_t *__restrict__ approx_count, int32_t *out_doc,
+              float *out_score, int32_t *out_count, jv_query_stats *stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sq = reinterpret_cast<float *>(smem_raw);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw + ((((size_t)dim * 4) + 15) & ~(size_t)15));
+    __shared__ float s_qnorm;
+    __shared__ int s_valid, s_reranked;
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_valid = 0, s_reranked = 0;
+    const float *gq = queries + (int64_t)qi * dim;
+    const bool vec4 = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
+    const int cnt = approx_count[qi];
+    if (has_pq) {
+        for (int i = tid; i < dim; i += kRerankThreads) sq[i] = __ldg(gq + i);
+        __syncthreads();
+        if (warp == 0) {
+            float qn = jv_warp_reduce_pair<false>(sq, gq, dim, lane, vec4); // second operand must be global (__ldg)
+            if (lane == 0) s_qnorm = qn;
+        }
+        __syncthreads();
+    }
+    int reranked = 0;
+    for (int j = warp; j < cnt; j += kRerankThreads / 32) {
+        const uint64_t ak = approx_keys[(int64_t)qi * L + j];
+        const int32_t node = jv_key_id(ak);
+        float s = jv_key_score(ak);
+        uint64_t key = 0ull;
+        const int32_t doc = ord_to_doc ? __ldg(ord_to_doc + node) : node;
+        if (has_pq) {
+            if (s >= rerank_floor) {
+                const float *x = vectors + (int64_t)node * dim;
+                float raw = sim == JV_SIM_EUCLIDEAN ? jv_warp_reduce_pair<true>(sq, x, dim, lane, vec4)
+                                                    : jv_warp_reduce_pair<false>(sq, x, dim, lane, vec4);
+                float xn = sim == JV_SIM_COSINE ? __ldg(vec_norm + node) : 0.f;
+                s = jv_finish_score(sim, raw, s_qnorm, xn); // the PQ reranker is NOT x2-wrapped (JVectorReader.java:352-356)
+                key = jv_mk_key(s, doc);
+                reranked++;
+            }
+        } else {
+            key = jv_mk_key(s, doc); // traversal scores are already exact (and MIP-doubled)
+        }
+        if (lane == 0) keys[j] = key;
+    }
+    __syncthreads();
+    // rank selection: rank = number of strictly better keys (keys are unique: doc ids differ)
+    int valid_local = 0;
+    for (int j = tid; j < cnt; j += kRerankThreads) {
+        const uint64_t my = keys[j];
+        if (my == 0ull) continue;
+        valid_local++;
+        int rank = 0;
+        for (int t = 0; t < cnt; t++) rank += keys[t] > my ? 1 : 0;
+        if (rank < k) {
+            out_doc[(int64_t)qi * k + rank] = jv_key_id(my);
+            out_score[(int64_t)qi * k + rank] = jv_key_score(my);
+        }
+    }
+    if (valid_local) atomicAdd(&s_valid, valid_local);
+    if (lane == 0 && reranked) atomicAdd(&s_reranked, reranked); // `reranked` is warp-uniform
+    __syncthreads();
+    const int nout = s_valid < k ? s_valid : k;
+    for (int j = nout + tid; j < k; j += kRerankThreads) {
+        out_doc[(int64_t)qi * k + j] = -1;
+        out_score[(int64_t)qi * k + j] = 0.f;
+    }
+    if (tid == 0) {
+        out_count[qi] = nout;
+        if (stats) stats[qi].reranked = s_reranked;
+    }
+}
+
+int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int rerank_k, float rerank_floor,
+                      const uint64_t *d_approx_keys, const int32_t *d_approx_count, int32_t *d_out_doc, float *d_out_score,
+                      int32_t *d_out_count, jv_query_stats *d_stats, int *launches) {
+    if (nq <= 0) return JV_OK;
+    const size_t smem = ((((size_t)ix->dim * 4) + 15) & ~(size_t)15) + (size_t)rerank_k * 8;
+    JV_REQUIRE(smem <= ix->smem_optin - 1024, "rerank_k %d too large for shared memory", rerank_k);
+    JV_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rerank_kernel<<<nq, kRerankThreads, smem, ctx->stream>>>(
+        ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, ix->has_pq ? 1 : 0,
+        d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats);
+    JV_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: merge `group` lists of k (doc, score) per query into one sorted list of k.  One CTA per
+// (query, output group): keys to shared memory, bitonic sort descending, first k out.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMergeThreads = 256;
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_kernel(int g, int group, int nq, int k, const int32_t *__restrict__ docs, const float *__restrict__ scores,
+             int32_t *out_doc, float *out_score, int32_t *out_count, int n2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    const int qi = blockIdx.x, og = blockIdx.y, tid = threadIdx.x;
+    const int g0 = og * group, g1 = min(g, g0 + group);
+    const int nin = (g1 - g0) * k;
+    for (int i = tid; i < n2; i += kMergeThreads) {
+        uint64_t key = 0ull;
+        if (i < nin) {
+            const int s = g0 + i / k, j = i % k;
+            const int64_t idx = ((int64_t)s * nq + qi) * k + j;
+            const int32_t d = docs[idx];
+            if (d >= 0) key = jv_mk_key(scores[idx], d);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (n2 >> 1); i += kMergeThreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if (desc ? (a < b) : (a > b)) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    int cnt_local = 0;
+    for (int j = tid; j < k; j += kMergeThreads) {
+        const uint64_t key = j < n2 ? keys[j] : 0ull;
+        const int64_t o = ((int64_t)og * nq + qi) * k + j;
+        out_doc[o] = key ? jv_key_id(key) : -1;
+        out_score[o] = key ? jv_key_score(key) : 0.f;
+        cnt_local += key ? 1 : 0;
+    }
+    __shared__ int s_cnt;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (cnt_local) atomicAdd(&s_cnt, cnt_local);
+    __syncthreads();
+    if (tid == 0 && out_count && gridDim.y == 1) out_count[qi] = s_cnt;
+}
+
+int32_t launch_merge_topk(cudaStream_t stream, int g, int nq, int k, const int32_t *d_docs, const float *d_scores,
+                          int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count) {
+    if (nq <= 0) return JV_OK;
+    JV_REQUIRE(g >= 1 && k >= 1 && k <= 4096, "merge: need g >= 1 and 1 <= k <= 4096");
+    const int max_keys = 4096;
+    int group = max_keys / k;
+    if (group < 2) group = 2;
+    DevBuf tmp_doc[2], tmp_score[2];
+    const int32_t *in_d = d_docs;
+    const float *in_s = d_scores;
+    int cur_g = g, flip = 0;
+    for (;;) {
+        const int ng = (cur_g + group - 1) / group;
+        const int per = cur_g < group ? cur_g : group;
+        int n2 = 1;
+        while (n2 < per * k) n2 <<= 1;
+        int32_t *od = d_out_doc;
+        float *os = d_out_score;
+        if (ng > 1) {
+            JV_TRY(tmp_doc[flip].alloc((size_t)ng * nq * k * 4));
+            JV_TRY(tmp_score[flip].alloc((size_t)ng * nq * k * 4));
+            od = tmp_doc[flip].as<int32_t>();
+            os = tmp_score[flip].as<float>();
+        }
+        const size_t smem = (size_t)n2 * 8;
+        JV_CUDA_TRY(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        merge_kernel<<<dim3(nq, ng), kMergeThreads, smem, stream>>>(cur_g, group, nq, k, in_d, in_s, od, os, d_out_count, n2);
+        JV_CUDA_TRY(cudaGetLastError());
+        if (ng == 1) break;
+        in_d = od;
+        in_s = os;
+        cur_g = ng;
+        flip ^= 1;
+    }
+    if (tmp_doc[0].p || tmp_doc[1].p) JV_CUDA_TRY(cudaStreamSynchronize(stream)); // temporaries die with this scope
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: brute force.  Grid = (query tiles, doc slices).  A CTA stages TQ queries in shared memory; each
+// warp keeps DPW doc rows in registers (canonical lane layout: lane j owns float4 chunks j, j+32, ..)
+// and sweeps the query tile, so a doc row is read from HBM once per CTA and every query float4 read
+// from shared memory feeds DPW dot products.  Per-query top-k lists live in shared memory; inserts
+// are rare after warm-up (~k ln(n/k) per query) and serialised by a per-query lock.
+// ------------------------------------------------------------------------------------------------
+constexpr int kExactThreads = 256;
+
+template <int NCH, int DPW>
+__global__ void __launch_bounds__(kExactThreads)
+exact_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_norm, const int32_t *__restrict__ ord_to_doc,
+             int64_t n, int dim, int sim, float mul, const float *__restrict__ queries, int nq, int k, int TQ,
+             const uint64_t *__restrict__ accept, int64_t accept_stride, int64_t slice_len, int32_t *part_doc, float *part_score) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q0 = blockIdx.x * TQ;
+    const int tq = min(TQ, nq - q0);
+    const int n4 = dim >> 2;
+    float4 *sq4 = reinterpret_cast<float4 *>(smem_raw);
+    unsigned char *sp = smem_raw + (size_t)TQ * dim * 4;
+    uint64_t *topk = reinterpret_cast<uint64_t *>(sp); // [TQ][k] ascending, slot 0 = worst
+    sp += (size_t)TQ * k * 8;
+    float *qnorm = reinterpret_cast<float *>(sp);
+    sp += (size_t)TQ * 4;
+    int *cnt = reinterpret_cast<int *>(sp);
+    sp += (size_t)TQ * 4;
+    int *lock = reinterpret_cast<int *>(sp);
+    sp += (size_t)TQ * 4;
+    unsigned long long *thr = reinterpret_cast<unsigned long long *>(smem_raw + ((((size_t)(sp - smem_raw)) + 7) & ~(size_t)7));
+
+    for (int i = tid; i < tq * n4; i += kExactThreads) {
+        const int t = i / n4, c = i - t * n4;
+        sq4[t * n4 + c] = __ldg(reinterpret_cast<const float4 *>(queries + (int64_t)(q0 + t) * dim) + c);
+    }
+    for (int t = tid; t < TQ; t += kExactThreads) {
+        cnt[t] = 0;
+        lock[t] = 0;
+        thr[t] = 0ull;
+    }
+    __syncthreads();
+    for (int t = warp; t < tq; t += kExactThreads / 32) {
+        const float *qv = reinterpret_cast<const float *>(sq4 + t * n4);
+        float qn = jv_warp_reduce_pair<false>(qv, queries + (int64_t)(q0 + t) * dim, dim, lane, true);
+        if (lane == 0) qnorm[t] = qn;
+    }
+    __syncthreads();
+
+    const int64_t d_begin = (int64_t)blockIdx.y * slice_len;
+    const int64_t d_end = min(n, d_begin + slice_len);
+    const bool l2 = sim == JV_SIM_EUCLIDEAN;
+    for (int64_t base = d_begin + (int64_t)warp * DPW; base < d_end; base += (int64_t)(kExactThreads / 32) * DPW) {
+        float4 x[DPW][NCH];
+        int32_t doc[DPW];
+        float xn[DPW];
+#pragma unroll
+        for (int d = 0; d < DPW; d++) {
+            const int64_t o = base + d;
+            doc[d] = -1;
+            xn[d] = 0.f;
+            if (o < d_end) {
+                doc[d] = ord_to_doc ? __ldg(ord_to_doc + o) : (int32_t)o;
+                if (sim == JV_SIM_COSINE) xn[d] = __ldg(vec_norm + o);
+                const float4 *row = reinterpret_cast<const float4 *>(vectors + o * dim);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    const int i = lane + 32 * c;
+                    x[d][c] = i < n4 ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int d = 0; d < DPW; d++) any |= doc[d] >= 0;
+        if (!any) continue;
+        for (int t = 0; t < tq; t++) {
+            float p[DPW][4];
+#pragma unroll
+            for (int d = 0; d < DPW; d++) p[d][0] = p[d][1] = p[d][2] = p[d][3] = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int i = lane + 32 * c;
+                if (i < n4) {
+                    const float4 qv = sq4[t * n4 + i];
+#pragma unroll
+                    for (int d = 0; d < DPW; d++) {
+                        if (l2) {
+                            float e0 = qv.x - x[d][c].x, e1 = qv.y - x[d][c].y, e2 = qv.z - x[d][c].z, e3 = qv.w - x[d][c].w;
+                            p[d][0] = __fmaf_rn(e0, e0, p[d][0]);
+                            p[d][1] = __fmaf_rn(e1, e1, p[d][1]);
+                            p[d][2] = __fmaf_rn(e2, e2, p[d][2]);
+                            p[d][3] = __fmaf_rn(e3, e3, p[d][3]);
+                        } else {
+                            p[d][0] = __fmaf_rn(qv.x, x[d][c].x, p[d][0]);
+                            p[d][1] = __fmaf_rn(qv.y, x[d][c].y, p[d][1]);
+                            p[d][2] = __fmaf_rn(qv.z, x[d][c].z, p[d][2]);
+                            p[d][3] = __fmaf_rn(qv.w, x[d][c].w, p[d][3]);
+                        }
+                    }
+                }
+            }
+            const uint64_t *abits = accept ? accept + (int64_t)(q0 + t) * accept_stride : nullptr;
+#pragma unroll
+            for (int d = 0; d < DPW; d++) {
+                float v = __fadd_rn(__fadd_rn(p[d][0], p[d][1]), __fadd_rn(p[d][2], p[d][3]));
+                v = jv_warp_sum_canonical(v);
+                if (doc[d] < 0) continue;
+                if (abits && !jv_doc_accepted(abits, doc[d])) continue;
+                const float s = jv_finish_score(sim, v, qnorm[t], xn[d]) * mul;
+                const uint64_t key = jv_mk_key(s, doc[d]);
+                if (key > *reinterpret_cast<volatile unsigned long long *>(&thr[t])) {
+                    if (lane == 0) {
+                        while (atomicCAS(&lock[t], 0, 1) != 0) {
+                        }
+                        __threadfence_block();
+                        volatile uint64_t *lst = topk + (size_t)t * k;
+                        int c = *reinterpret_cast<volatile int *>(&cnt[t]);
+                        if (c < k) {
+                            int pos = c; // insert keeping ascending order
+                            while (pos > 0 && lst[pos - 1] > key) {
+                                lst[pos] = lst[pos - 1];
+                                pos--;
+                            }
+                            lst[pos] = key;
+                            c++;
+                            *reinterpret_cast<volatile int *>(&cnt[t]) = c;
+                            if (c == k) *reinterpret_cast<volatile unsigned long long *>(&thr[t]) = lst[0];
+                        } else if (key > lst[0]) {
+                            int pos = 0; // drop the worst, shift down
+                            while (pos + 1 < k && lst[pos + 1] < key) {
+                                lst[pos] = lst[pos + 1];
+                                pos++;
+                            }
+                            lst[pos] = key;
+                            *reinterpret_cast<volatile unsigned long long *>(&thr[t]) = lst[0];
+                        }
+                        __threadfence_block();
+                        atomicExch(&lock[t], 0);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // emit per-slice partial lists, best first
+    for (int i = tid; i < tq * k; i += kExactThreads) {
+        const int t = i / k, j = i - t * k;
+        const int c = cnt[t];
+        const int64_t o = ((int64_t)blockIdx.y * nq + (q0 + t)) * k + j;
+        if (j < c) {
+            const uint64_t key = topk[(size_t)t * k + (c - 1 - j)];
+            part_doc[o] = jv_key_id(key);
+            part_score[o] = jv_key_score(key);
+        } else {
+            part_doc[o] = -1;
+            part_score[o] = 0.f;
+        }
+    }
+}
+
+// generic fallback (dim % 4 != 0 or very large dim): one warp per (query, doc) through the shared reducer
+__global__ void __launch_bounds__(kExactThreads)
+exact_kernel_generic(const float *__restrict__ vectors, const float *__restrict__ vec_norm,
+                     const int32_t *__restrict__ ord_to_doc, int64_t n, int dim, int sim, float mul,
+                     const float *__restrict__ queries, int nq, int k, const uint64_t *__restrict__ accept,
+                     int64_t accept_stride, int64_t slice_len, int32_t *part_doc, float *part_score) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qi = blockIdx.x;
+    float *sq = reinterpret_cast<float *>(smem_raw);
+    uint64_t *topk = reinterpret_cast<uint64_t *>(smem_raw + ((((size_t)dim * 4) + 15) & ~(size_t)15));
+    __shared__ int s_cnt, s_lock;
+    __shared__ float s_qn;
+    for (int i = tid; i < dim; i += kExactThreads) sq[i] = queries[(int64_t)qi * dim + i];
+    if (tid == 0) s_cnt = 0, s_lock = 0;
+    __syncthreads();
+    if (warp == 0) {
+        float qn = jv_warp_reduce_pair<false>(sq, queries + (int64_t)qi * dim, dim, lane, false);
+        if (lane == 0) s_qn = qn;
+    }
+    __syncthreads();
+    const uint64_t *abits = accept ? accept + (int64_t)qi * accept_stride : nullptr;
+    const int64_t d_begin = (int64_t)blockIdx.y * slice_len, d_end = min(n, d_begin + slice_len);
+    for (int64_t o = d_begin + warp; o < d_end; o += kExactThreads / 32) {
+        const int32_t doc = ord_to_doc ? ord_to_doc[o] : (int32_t)o;
+        if (doc < 0 || (abits && !jv_doc_accepted(abits, doc))) continue;
+        const float *x = vectors + o * dim;
+        float raw = sim == JV_SIM_EUCLIDEAN ? jv_warp_reduce_pair<true>(sq, x, dim, lane, false)
+                                            : jv_warp_reduce_pair<false>(sq, x, dim, lane, false);
+        const float s = jv_finish_score(sim, raw, s_qn, sim == JV_SIM_COSINE ? vec_norm[o] : 0.f) * mul;
+        const uint64_t key = jv_mk_key(s, doc);
+        if (lane == 0) {
+            while (atomicCAS(&s_lock, 0, 1) != 0) {
+            }
+            __threadfence_block();
+            volatile uint64_t *lst = topk;
+            int c = *reinterpret_cast<volatile int *>(&s_cnt);
+            if (c < k) {
+                int pos = c;
+                while (pos > 0 && lst[pos - 1] > key) {
+                    lst[pos] = lst[pos - 1];
+                    pos--;
+                }
+                lst[pos] = key;
+                *reinterpret_cast<volatile int *>(&s_cnt) = c + 1;
+            } else if (key > lst[0]) {
+                int pos = 0;
+                while (pos + 1 < k && lst[pos + 1] < key) {
+                    lst[pos] = lst[pos + 1];
+                    pos++;
+                }
+                lst[pos] = key;
+            }
+            __threadfence_block();
+            atomicExch(&s_lock, 0);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int j = tid; j < k; j += kExactThreads) {
+        const int c = s_cnt;
+        const int64_t o = ((int64_t)blockIdx.y * nq + qi) * k + j;
+        if (j < c) {
+            const uint64_t key = topk[c - 1 - j];
+            part_doc[o] = jv_key_id(key);
+            part_score[o] = jv_key_score(key);
+        } else {
+            part_doc[o] = -1;
+            part_score[o] = 0.f;
+        }
+    }
+}
+
+template <int NCH, int DPW>
+static int32_t launch_exact_typed(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, const uint64_t *d_accept,
+                                  int64_t stride, int TQ, int S, int64_t slice_len, size_t smem, int32_t *pd, float *ps) {
+    auto kern = exact_kernel<NCH, DPW>;
+    JV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float mul = ix->sim == JV_SIM_MIP ? 2.0f : 1.0f; // JVectorVectorScorer.java:43-50
+    dim3 grid((nq + TQ - 1) / TQ, S);
+    kern<<<grid, kExactThreads, smem, ctx->stream>>>(ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->n,
+                                                     ix->dim, ix->sim, mul, d_queries, nq, k, TQ, d_accept, stride, slice_len, pd, ps);
+    JV_CUDA_TRY(cudaGetLastError());
+    return JV_OK;
+}
+
+int32_t launch_exact_topk(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, const uint64_t *d_accept,
+                          int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
+                          int *launches) {
+    if (nq <= 0) return JV_OK;
+    JV_REQUIRE(k >= 1 && k <= 1024, "exact_topk: 1 <= k <= 1024");
+    const int dim = ix->dim;
+    const int nch = (dim + 127) / 128;
+    const bool fast = (dim & 3) == 0 && nch <= 16 && ((reinterpret_cast<uintptr_t>(d_queries) & 15) == 0);
+    int TQ = 1;
+    size_t smem = 0;
+    if (fast) {
+        const size_t per_q = (size_t)dim * 4 + (size_t)k * 8 + 12 + 8;
+        TQ = (int)((96 * 1024) / per_q);
+        if (TQ > 32) TQ = 32;
+        if (TQ < 1) TQ = 1;
+        if (TQ > nq) TQ = nq;
+        smem = (size_t)TQ * per_q + 16;
+    } else {
+        smem = ((((size_t)dim * 4) + 15) & ~(size_t)15) + (size_t)k * 8;
+    }
+    JV_REQUIRE(smem <= ix->smem_optin - 1024, "exact_topk: k=%d dim=%d do not fit shared memory", k, dim);
+    const int qtiles = (nq + TQ - 1) / TQ;
+    // enough CTAs for ~2 waves, but keep slices >= 2048 docs so per-slice lists amortise
+    int S = (2 * ix->sm_count * 2 + qtiles - 1) / qtiles;
+    const int64_t max_s = (ix->n + 2047) / 2048;
+    if (S > max_s) S = (int)max_s;
+    if (S < 1) S = 1;
+    if (S > 65535) S = 65535;
+    const int64_t slice_len = (ix->n + S - 1) / S;
+    JV_TRY(ctx->slice_doc.ensure((size_t)S * nq * k * 4));
+    JV_TRY(ctx->slice_score.ensure((size_t)S * nq * k * 4));
+    int32_t *pd = ctx->slice_doc.as<int32_t>();
+    float *ps = ctx->slice_score.as<float>();
+    int32_t st = JV_OK;
+    if (fast) {
+#define JV_EX(N, D) st = launch_exact_typed<N, D>(ix, ctx, d_queries, nq, k, d_accept, accept_stride_words, TQ, S, slice_len, smem, pd, ps)
+        if (nch <= 1) JV_EX(1, 4);
+        else if (nch <= 2) JV_EX(2, 4);
+        else if (nch <= 4) JV_EX(4, 2);
+        else if (nch <= 6) JV_EX(6, 2);
+        else if (nch <= 8) JV_EX(8, 2);
+        else if (nch <= 12) JV_EX(12, 1);
+        else JV_EX(16, 1);
+#undef JV_EX
+    } else {
+        const float mul = ix->sim == JV_SIM_MIP ? 2.0f : 1.0f;
+        JV_CUDA_TRY(cudaFuncSetAttribute(exact_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        exact_kernel_generic<<<dim3(nq, S), kExactThreads, smem, ctx->stream>>>(
+            ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->n, dim, ix->sim, mul, d_queries, nq, k,
+            d_accept, accept_stride_words, slice_len, pd, ps);
+        JV_CUDA_TRY(cudaGetLastError());
+    }
+    JV_TRY(st);
+    JV_TRY(launch_merge_topk(ctx->stream, S, nq, k, pd, ps, d_out_doc, d_out_score, d_out_count));
+    if (launches) *launches += 2;
+    return JV_OK;
+}
+
+}  // namespace jv

@@ -1,0 +1,106 @@
+"""ctypes binding of libjvgpu.so — the same symbols the Java codec binds through Panama FFM
+(INTEGRATION.md).  Loading fails loudly when the CUDA library is missing: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libjvgpu.so"
+
+JV_OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_INTERNAL = -1, -2, -3, -4, -5
+SIM_EUCLIDEAN, SIM_DOT, SIM_COSINE, SIM_MIP = 0, 1, 2, 3
+FLAG_FUSED_LAYOUT, FLAG_LUT_F16, FLAG_NO_VECTORS_ON_DEVICE = 1, 2, 4
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("similarity", C.c_int32), ("dim", C.c_int32), ("max_degree", C.c_int32),
+        ("n", C.c_int64), ("entry_node", C.c_int32), ("max_doc", C.c_int32),
+        ("adjacency", C.c_void_p), ("vectors", C.c_void_p), ("ord_to_doc", C.c_void_p),
+        ("pq_m", C.c_int32), ("pq_k", C.c_int32),
+        ("pq_codebooks", C.c_void_p), ("pq_global_centroid", C.c_void_p), ("pq_codes", C.c_void_p),
+        ("device", C.c_int32), ("flags", C.c_uint32),
+    ]
+
+
+class QueryStats(C.Structure):
+    _fields_ = [("visited", C.c_int32), ("expanded", C.c_int32), ("expanded_base", C.c_int32), ("reranked", C.c_int32)]
+
+
+class BatchTiming(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("search_ms", C.c_float), ("rerank_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("total_ms", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("k", C.c_int32), ("rerank_k", C.c_int32), ("threshold", C.c_float),
+                ("rerank_floor", C.c_float), ("reserved", C.c_int32), ("accept_bits", C.c_void_p),
+                ("accept_stride_words", C.c_int64)]
+
+
+# every symbol include/jvgpu.h declares: (name, restype, argtypes)
+_P, _I32, _I64, _F, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
+SYMBOLS = {
+    "jv_version": (_I32, []),
+    "jv_last_error": (C.c_char_p, []),
+    "jv_device_count": (_I32, [_P]),
+    "jv_index_create": (_I32, [_P, _P]),
+    "jv_index_destroy": (_I32, [_P]),
+    "jv_index_device_bytes": (_I32, [_P, _P]),
+    "jv_index_debug_counter": (_I32, [_P, _I32, _P]),
+    "jv_search_batch": (_I32, [_P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "jv_search_batch_dev": (_I32, [_P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "jv_exact_topk": (_I32, [_P, _P, _I32, _I32, _P, _I64, _P, _P, _P]),
+    "jv_exact_topk_dev": (_I32, [_P, _P, _I32, _I32, _P, _I64, _P, _P, _P]),
+    "jv_pq_encode": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "jv_pq_encode_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "jv_pq_lut": (_I32, [_P, _P, _I32, _P]),
+    "jv_pq_adc_scores": (_I32, [_P, _P, _I32, _P, _I32, _P]),
+    "jv_merge_topk": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "jv_merge_topk_dev": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "jv_pq_train": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
+    "jv_pq_train_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
+    "jv_graph_build": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
+    "jv_graph_build_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
+}
+
+
+class JVectorNativeError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libjvgpu status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libjvgpu.so and bind every declared symbol; raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python opensearch-jvector_b200/build.py` "
+                "(the product path has no CPU fallback)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status == JV_OK:
+        return
+    msg = load().jv_last_error().decode("utf-8", "replace")
+    if status == ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)                      # Java: IllegalArgumentException
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)             # Java: UnsupportedOperationException
+    if status == ERR_OUT_OF_MEMORY:
+        raise MemoryError(msg)
+    raise JVectorNativeError(status, msg)          # Java: IOException

@@ -1,0 +1,1040 @@
+/*
+ * jv_oracle.c — CPU restatement of the opensearch-jvector query hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (opensearch-jvector_b200/) never links, imports or calls anything in oracle/.
+ *
+ * PARITY STATUS: the arithmetic of this path lives in the third-party library
+ * io.github.jbellis:jvector:4.0.0-rc.9 (reference build.gradle:362, gradle.properties:8) whose
+ * source is NOT under /root/reference and which cannot be built here (no JVM).  This file restates
+ * its published algorithm and the plugin's glue around it.  It is pinned
+ * against every known-answer test the reference holds for this path (tests/test_oracle_kat.py:
+ * KNNJVectorTests analytic top-3 ids/scores, the CommonTestUtils score formulas, seeded recall
+ * floors), but PQ codes / LUT values / traversal order have no golden vectors in the reference:
+ * for those, PARITY IS UNPINNED and claims read "vs. CPU restatement of jVector 4.0.0-rc.9".
+ *
+ * Citations: paths relative to /root/reference/src/main/java/org/opensearch/knn/index/codec/jvector/.
+ *
+ * Floating point: compiled with -ffp-contract=off; every fused multiply-add is an explicit fmaf()
+ * so the GPU kernels (which use __fmaf_rn in the same order) can match bit for bit.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/jvgpu.h" /* jv_index_desc, jv_query_stats, JV_SIM_* (types only) */
+
+#define JVO_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * java.util.Random — the reference's fixtures are `new Random(seed).nextFloat()` row-major
+ * (src/testFixtures/java/org/opensearch/knn/TestUtils.java:108-124).  Documented 48-bit LCG.
+ * ------------------------------------------------------------------------------------------ */
+JVO_EXPORT void jvo_java_random_floats(int64_t seed, int64_t count, float *out) {
+    const uint64_t mask = (1ULL << 48) - 1;
+    uint64_t state = ((uint64_t)seed ^ 0x5DEECE66DULL) & mask;
+    for (int64_t i = 0; i < count; i++) {
+        state = (state * 0x5DEECE66DULL + 0xBULL) & mask;
+        int32_t bits24 = (int32_t)(state >> (48 - 24));
+        out[i] = (float)bits24 / (float)(1 << 24);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Canonical fp32 reductions.  jVector's VectorUtil (Panama) keeps lane-wise partial sums and
+ * reduces horizontally, so its exact rounding depends on the host's SIMD width; any fixed order
+ * is within dim*eps of it (hence the 1e-5 relative gate).  We fix ONE order that CPU and GPU both
+ * implement exactly: 128 strided partial sums (element i -> partial i mod 128, fmaf), then
+ * ((p0+p1)+(p2+p3)) inside each group of 4, then a halving tree over the 32 groups.
+ * ------------------------------------------------------------------------------------------ */
+static inline float reduce128(const float *acc) {
+    float v[32];
+    for (int j = 0; j < 32; j++) v[j] = (acc[4 * j] + acc[4 * j + 1]) + (acc[4 * j + 2] + acc[4 * j + 3]);
+    for (int off = 16; off >= 1; off >>= 1)
+        for (int j = 0; j < off; j++) v[j] = v[j] + v[j + off];
+    return v[0];
+}
+
+static inline float canon_dot(const float *a, const float *b, int dim) {
+    float acc[128];
+    memset(acc, 0, sizeof(acc));
+    int i = 0;
+    for (; i + 128 <= dim; i += 128)
+        for (int c = 0; c < 128; c++) acc[c] = fmaf(a[i + c], b[i + c], acc[c]);
+    for (int c = 0; i + c < dim; c++) acc[c] = fmaf(a[i + c], b[i + c], acc[c]);
+    return reduce128(acc);
+}
+
+static inline float canon_l2sq(const float *a, const float *b, int dim) {
+    float acc[128];
+    memset(acc, 0, sizeof(acc));
+    int i = 0;
+    for (; i + 128 <= dim; i += 128)
+        for (int c = 0; c < 128; c++) {
+            float d = a[i + c] - b[i + c];
+            acc[c] = fmaf(d, d, acc[c]);
+        }
+    for (int c = 0; i + c < dim; c++) {
+        float d = a[i + c] - b[i + c];
+        acc[c] = fmaf(d, d, acc[c]);
+    }
+    return reduce128(acc);
+}
+
+/* jVector VectorSimilarityFunction.compare (pinned by CommonTestUtils.java:84-93):
+ * EUCLIDEAN 1/(1+d2), DOT (1+dot)/2, COSINE (1+cos)/2.  `qnorm` = canon_dot(q,q). */
+static inline float exact_score(int sim, const float *q, float qnorm, const float *x, int dim) {
+    switch (sim) {
+    case JV_SIM_EUCLIDEAN:
+        return 1.0f / (1.0f + canon_l2sq(q, x, dim));
+    case JV_SIM_COSINE: {
+        float d = canon_dot(q, x, dim);
+        float xn = canon_dot(x, x, dim);
+        float c = (float)((double)d / sqrt((double)qnorm * (double)xn));
+        return (1.0f + c) / 2.0f;
+    }
+    default: /* DOT, MIP */
+        return (1.0f + canon_dot(q, x, dim)) / 2.0f;
+    }
+}
+
+JVO_EXPORT float jvo_exact_score(int32_t sim, const float *q, const float *x, int32_t dim) {
+    return exact_score(sim, q, canon_dot(q, q, dim), x, dim);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * (score, node) ordering.  jVector NodeQueue packs (floatToSortableInt(score) << 32) | ~node so
+ * ties prefer the LOWER node id.  We use the unsigned-orderable transform so plain
+ * uint64 comparison works: larger key = better.
+ * ------------------------------------------------------------------------------------------ */
+static inline uint32_t f2ord(float f) {
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+static inline float ord2f(uint32_t u) {
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+static inline uint64_t mk_key(float score, int32_t node) { return ((uint64_t)f2ord(score) << 32) | (uint32_t)(~node); }
+static inline int32_t key_node(uint64_t k) { return (int32_t)(~(uint32_t)k); }
+static inline float key_score(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
+
+/* growable binary heaps over uint64 keys */
+typedef struct {
+    uint64_t *a;
+    int n, cap;
+} heap_t;
+static void heap_reserve(heap_t *h, int cap) {
+    if (cap > h->cap) {
+        h->cap = cap < 64 ? 64 : cap;
+        h->a = (uint64_t *)realloc(h->a, sizeof(uint64_t) * (size_t)h->cap);
+    }
+}
+static void maxheap_push(heap_t *h, uint64_t k) {
+    if (h->n == h->cap) heap_reserve(h, h->cap * 2 + 64);
+    int i = h->n++;
+    while (i > 0) {
+        int p = (i - 1) >> 1;
+        if (h->a[p] >= k) break;
+        h->a[i] = h->a[p];
+        i = p;
+    }
+    h->a[i] = k;
+}
+static uint64_t maxheap_pop(heap_t *h) {
+    uint64_t top = h->a[0], last = h->a[--h->n];
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1;
+        if (l >= h->n) break;
+        int c = (r < h->n && h->a[r] > h->a[l]) ? r : l;
+        if (h->a[c] <= last) break;
+        h->a[i] = h->a[c];
+        i = c;
+    }
+    if (h->n > 0) h->a[i] = last;
+    return top;
+}
+static void minheap_push(heap_t *h, uint64_t k) {
+    if (h->n == h->cap) heap_reserve(h, h->cap * 2 + 64);
+    int i = h->n++;
+    while (i > 0) {
+        int p = (i - 1) >> 1;
+        if (h->a[p] <= k) break;
+        h->a[i] = h->a[p];
+        i = p;
+    }
+    h->a[i] = k;
+}
+static void minheap_replace_top(heap_t *h, uint64_t k) {
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1;
+        if (l >= h->n) break;
+        int c = (r < h->n && h->a[r] < h->a[l]) ? r : l;
+        if (h->a[c] >= k) break;
+        h->a[i] = h->a[c];
+        i = c;
+    }
+    h->a[i] = k;
+}
+/* bounded min-heap push: keep the `bound` best keys */
+static inline void bounded_push(heap_t *h, int bound, uint64_t k) {
+    if (h->n < bound)
+        minheap_push(h, k);
+    else if (k > h->a[0])
+        minheap_replace_top(h, k);
+}
+static int cmp_u64_desc(const void *x, const void *y) {
+    uint64_t a = *(const uint64_t *)x, b = *(const uint64_t *)y;
+    return a < b ? 1 : (a > b ? -1 : 0);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Product quantisation (call sites JVectorIndexQuantization.java:114-140,
+ * JVectorWriter.java:1117-1124, JVectorReader.java:352-357).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int dim, M, K;
+    int *size, *off;     /* sub-vector sizes / offsets into the vector */
+    int64_t *cb_off;     /* offset of subspace m's codebook in the flat codebook array */
+} pq_shape;
+
+static void pq_shape_init(pq_shape *s, int dim, int M, int K) {
+    s->dim = dim;
+    s->M = M;
+    s->K = K;
+    s->size = (int *)malloc(sizeof(int) * (size_t)M);
+    s->off = (int *)malloc(sizeof(int) * (size_t)M);
+    s->cb_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)M);
+    int base = dim / M, rem = dim % M, o = 0;
+    int64_t co = 0;
+    for (int m = 0; m < M; m++) {
+        s->size[m] = base + (m < rem ? 1 : 0); /* first dim%M sub-vectors get base+1 */
+        s->off[m] = o;
+        s->cb_off[m] = co;
+        o += s->size[m];
+        co += (int64_t)K * s->size[m];
+    }
+}
+static void pq_shape_free(pq_shape *s) {
+    free(s->size);
+    free(s->off);
+    free(s->cb_off);
+}
+
+JVO_EXPORT void jvo_pq_subspaces(int32_t dim, int32_t M, int32_t *sizes, int32_t *offsets) {
+    int base = dim / M, rem = dim % M, o = 0;
+    for (int m = 0; m < M; m++) {
+        sizes[m] = base + (m < rem ? 1 : 0);
+        offsets[m] = o;
+        o += sizes[m];
+    }
+}
+
+/* JVectorIndexQuantization.PQ.defaultNumSubspaces, JVectorIndexQuantization.java:428-446 */
+JVO_EXPORT int32_t jvo_default_num_subspaces(int32_t d) {
+    if (d <= 32) return d;
+    if (d <= 64) return 32;
+    if (d <= 200) return (int32_t)(d * 0.5);
+    if (d <= 400) return 100;
+    if (d <= 768) return (int32_t)(d * 0.25);
+    if (d <= 1536) return 192;
+    return (int32_t)(d * 0.125);
+}
+
+static inline float sub_l2sq(const float *x, const float *c, int len) {
+    float acc = 0.0f;
+    for (int j = 0; j < len; j++) {
+        float d = x[j] - c[j];
+        acc = fmaf(d, d, acc);
+    }
+    return acc;
+}
+static inline float sub_dot(const float *x, const float *c, int len) {
+    float acc = 0.0f;
+    for (int j = 0; j < len; j++) acc = fmaf(x[j], c[j], acc);
+    return acc;
+}
+
+/* K6: ProductQuantization.encode — x' = x - g; code[m] = first argmin_c ||x'_m - C_m[c]||^2 (strict <). */
+JVO_EXPORT void jvo_pq_encode(const float *vectors, int64_t n, int32_t dim, int32_t M, int32_t K, const float *codebooks,
+                              const float *gcent, uint8_t *out_codes, int32_t threads) {
+    pq_shape s;
+    pq_shape_init(&s, dim, M, K);
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        float *xc = (float *)malloc(sizeof(float) * (size_t)dim);
+        const float *x = vectors + i * dim;
+        for (int d = 0; d < dim; d++) xc[d] = gcent ? x[d] - gcent[d] : x[d];
+        for (int m = 0; m < M; m++) {
+            const float *cb = codebooks + s.cb_off[m];
+            float best = INFINITY;
+            int idx = 0;
+            for (int c = 0; c < K; c++) {
+                float d2 = sub_l2sq(xc + s.off[m], cb + (int64_t)c * s.size[m], s.size[m]);
+                if (d2 < best) {
+                    best = d2;
+                    idx = c;
+                }
+            }
+            out_codes[i * M + m] = (uint8_t)idx;
+        }
+        free(xc);
+    }
+    pq_shape_free(&s);
+}
+
+/* K1: PQDecoder precomputed table.  DOT/COSINE/MIP: lut[m][c] = q_m . C_m[c];
+ * EUCLIDEAN: lut[m][c] = ||(q-g)_m - C_m[c]||^2. */
+static void pq_build_lut(const pq_shape *s, int sim, const float *codebooks, const float *gcent, const float *q, float *lut,
+                         float *qc_scratch) {
+    const float *qq = q;
+    if (sim == JV_SIM_EUCLIDEAN && gcent) {
+        for (int d = 0; d < s->dim; d++) qc_scratch[d] = q[d] - gcent[d];
+        qq = qc_scratch;
+    }
+    for (int m = 0; m < s->M; m++) {
+        const float *cb = codebooks + s->cb_off[m];
+        for (int c = 0; c < s->K; c++) {
+            const float *cv = cb + (int64_t)c * s->size[m];
+            lut[m * s->K + c] = (sim == JV_SIM_EUCLIDEAN) ? sub_l2sq(qq + s->off[m], cv, s->size[m])
+                                                          : sub_dot(qq + s->off[m], cv, s->size[m]);
+        }
+    }
+}
+
+JVO_EXPORT void jvo_pq_lut(int32_t sim, int32_t dim, int32_t M, int32_t K, const float *codebooks, const float *gcent,
+                           const float *queries, int32_t nq, float *out_lut) {
+    pq_shape s;
+    pq_shape_init(&s, dim, M, K);
+    float *scratch = (float *)malloc(sizeof(float) * (size_t)dim);
+    for (int i = 0; i < nq; i++)
+        pq_build_lut(&s, sim, codebooks, gcent, queries + (int64_t)i * dim, out_lut + (int64_t)i * M * K, scratch);
+    free(scratch);
+    pq_shape_free(&s);
+}
+
+/* ||decode(code)||^2 = sum_m ||C_m[code_m]||^2 : the cosine decoder's second table, folded per node
+ * because it does not depend on the query. */
+static float pq_node_norm(const pq_shape *s, const float *codebooks, const uint8_t *code) {
+    float acc = 0.0f;
+    for (int m = 0; m < s->M; m++) {
+        const float *cv = codebooks + s->cb_off[m] + (int64_t)code[m] * s->size[m];
+        acc += sub_dot(cv, cv, s->size[m]);
+    }
+    return acc;
+}
+
+/* a4: assembleAndSum + decoder mapping.  The order in which the M table entries are summed is not
+ * observable in the reference beyond rounding (Panama lane-wise partials, host dependent).  Two
+ * fixed orders are provided:
+ *   order 0  four interleaved sequential accumulators (scalar-loop flavour)
+ *   order 1  "warp32": 32 lane partials, lane l sums subspaces 4w..4w+3 for code words w = l, l+32, ..
+ *            in increasing m, then the halving tree of reduce128 — the order the sm_100a kernel uses,
+ *            so fp32 traversals can be compared bit for bit. */
+static inline float adc_sum(const float *lut, int M, int K, const uint8_t *code, int order) {
+    if (order == 1) {
+        float v[32];
+        const int nwords = (M + 3) >> 2;
+        for (int l = 0; l < 32; l++) {
+            float s = 0.f;
+            for (int w = l; w < nwords; w += 32)
+                for (int b = 0; b < 4; b++)
+                    if (4 * w + b < M) s += lut[(4 * w + b) * K + code[4 * w + b]];
+            v[l] = s;
+        }
+        for (int off = 16; off >= 1; off >>= 1)
+            for (int j = 0; j < off; j++) v[j] = v[j] + v[j + off];
+        return v[0];
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int m = 0;
+    for (; m + 4 <= M; m += 4) {
+        s0 += lut[(m + 0) * K + code[m + 0]];
+        s1 += lut[(m + 1) * K + code[m + 1]];
+        s2 += lut[(m + 2) * K + code[m + 2]];
+        s3 += lut[(m + 3) * K + code[m + 3]];
+    }
+    for (; m < M; m++) s0 += lut[m * K + code[m]];
+    return (s0 + s1) + (s2 + s3);
+}
+
+static inline float adc_score(int sim, const float *lut, int M, int K, const uint8_t *code, float node_norm, float qnorm,
+                              int order) {
+    float s = adc_sum(lut, M, K, code, order);
+    switch (sim) {
+    case JV_SIM_EUCLIDEAN:
+        return 1.0f / (1.0f + s);
+    case JV_SIM_COSINE:
+        return (1.0f + s / sqrtf(node_norm * qnorm)) * 0.5f;
+    default:
+        return (1.0f + s) * 0.5f;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Index view + per-thread search scratch
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    jv_index_desc d;
+    pq_shape pq;
+    int has_pq;
+    int adc_order;    /* see adc_sum */
+    float *node_norm; /* cosine + PQ only */
+} jvo_index;
+
+JVO_EXPORT jvo_index *jvo_index_create(const jv_index_desc *desc) {
+    jvo_index *ix = (jvo_index *)calloc(1, sizeof(jvo_index));
+    ix->d = *desc;
+    ix->has_pq = desc->pq_m > 0 && desc->pq_codes && desc->pq_codebooks;
+    if (ix->has_pq) {
+        pq_shape_init(&ix->pq, desc->dim, desc->pq_m, desc->pq_k);
+        if (desc->similarity == JV_SIM_COSINE) {
+            ix->node_norm = (float *)malloc(sizeof(float) * (size_t)desc->n);
+            for (int64_t i = 0; i < desc->n; i++)
+                ix->node_norm[i] = pq_node_norm(&ix->pq, desc->pq_codebooks, desc->pq_codes + i * desc->pq_m);
+        }
+    }
+    return ix;
+}
+JVO_EXPORT void jvo_index_set_adc_order(jvo_index *ix, int32_t order) { ix->adc_order = order; }
+JVO_EXPORT void jvo_index_destroy(jvo_index *ix) {
+    if (!ix) return;
+    if (ix->has_pq) pq_shape_free(&ix->pq);
+    free(ix->node_norm);
+    free(ix);
+}
+
+typedef struct {
+    heap_t cand, res;
+    uint64_t *visited; /* bitmap over ordinals */
+    int32_t *touched;
+    int ntouched, touched_cap;
+    float *lut, *qc;
+    uint64_t *sorted;
+} scratch_t;
+
+static scratch_t *scratch_new(const jvo_index *ix) {
+    scratch_t *s = (scratch_t *)calloc(1, sizeof(scratch_t));
+    s->visited = (uint64_t *)calloc((size_t)((ix->d.n + 63) / 64), 8);
+    s->touched_cap = 4096;
+    s->touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)s->touched_cap);
+    if (ix->has_pq) s->lut = (float *)malloc(sizeof(float) * (size_t)ix->d.pq_m * ix->d.pq_k);
+    s->qc = (float *)malloc(sizeof(float) * (size_t)ix->d.dim);
+    return s;
+}
+static void scratch_free(scratch_t *s) {
+    free(s->cand.a);
+    free(s->res.a);
+    free(s->visited);
+    free(s->touched);
+    free(s->lut);
+    free(s->qc);
+    free(s->sorted);
+    free(s);
+}
+static inline int visit(scratch_t *s, int32_t node) {
+    uint64_t bit = 1ULL << (node & 63);
+    uint64_t *w = &s->visited[node >> 6];
+    if (*w & bit) return 0;
+    *w |= bit;
+    if (s->ntouched == s->touched_cap) {
+        s->touched_cap *= 2;
+        s->touched = (int32_t *)realloc(s->touched, sizeof(int32_t) * (size_t)s->touched_cap);
+    }
+    s->touched[s->ntouched++] = node;
+    return 1;
+}
+static void visited_reset(scratch_t *s) {
+    for (int i = 0; i < s->ntouched; i++) s->visited[s->touched[i] >> 6] = 0;
+    s->ntouched = 0;
+}
+
+/* a9: accept-bits lambda, JVectorReader.java:157-163 + GraphNodeIdToDocMap.java:159-161 */
+static inline int accepted(const jvo_index *ix, const uint64_t *bits, int32_t ord) {
+    int32_t doc = ix->d.ord_to_doc ? ix->d.ord_to_doc[ord] : ord;
+    if (doc == -1) return 0; /* deleted / no-vector ordinals are never returned */
+    if (!bits) return 1;
+    return (int)((bits[doc >> 6] >> (doc & 63)) & 1ULL);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * GraphSearcher.search for ONE query on the flat (level-0) graph, followed by the
+ * rerank step, ordinal->doc mapping and collector ordering — i.e. JVectorReader.search,
+ * JVectorReader.java:130-210.  approx_out (nullable, [rerank_k] keys) receives the approximate
+ * result list before rerank, best first, for the graph builder and for tests.
+ * ------------------------------------------------------------------------------------------ */
+static void search_one(const jvo_index *ix, scratch_t *S, const float *q, int k, int rerank_k, float threshold,
+                       float rerank_floor, const uint64_t *bits, int32_t *out_doc, float *out_score, int32_t *out_count,
+                       jv_query_stats *st, uint64_t *approx_out, int32_t *approx_count, int entry_override,
+                       int64_t n_limit) {
+    const jv_index_desc *d = &ix->d;
+    const int sim = d->similarity, dim = d->dim, R = d->max_degree;
+    const int use_pq = ix->has_pq;
+    const float qnorm = canon_dot(q, q, dim);
+    const float mip_mul = (sim == JV_SIM_MIP && !use_pq) ? 2.0f : 1.0f; /* wrapExactScoreFunction, :220-239 */
+    if (use_pq) pq_build_lut(&ix->pq, sim, d->pq_codebooks, d->pq_global_centroid, q, S->lut, S->qc);
+
+#define APPROX(node)                                                                                                    \
+    (use_pq ? adc_score(sim, S->lut, d->pq_m, d->pq_k, d->pq_codes + (int64_t)(node) * d->pq_m,                          \
+                        ix->node_norm ? ix->node_norm[node] : 0.f, qnorm, ix->adc_order)                                 \
+            : exact_score(sim, q, qnorm, d->vectors + (int64_t)(node) * dim, dim) * mip_mul)
+
+    S->cand.n = 0;
+    S->res.n = 0;
+    int visited = 0, expanded = 0, reranked = 0;
+    int32_t entry = entry_override >= 0 ? entry_override : d->entry_node;
+    if (d->n > 0 && entry >= 0) {
+        visit(S, entry);
+        visited++;
+        maxheap_push(&S->cand, mk_key(APPROX(entry), entry));
+    }
+    while (S->cand.n > 0) {
+        uint64_t top = S->cand.a[0];
+        float sc = key_score(top);
+        if (S->res.n >= rerank_k && sc < key_score(S->res.a[0])) break;
+        maxheap_pop(&S->cand);
+        int32_t c = key_node(top);
+        if (accepted(ix, bits, c) && sc >= threshold) bounded_push(&S->res, rerank_k, top);
+        expanded++;
+        const int32_t *nb = d->adjacency + (int64_t)c * R;
+        for (int j = 0; j < R; j++) {
+            int32_t nn = nb[j];
+            if (nn < 0) break;
+            if (nn >= n_limit) continue; /* builder: nodes not inserted yet */
+            if (!visit(S, nn)) continue;
+            visited++;
+            maxheap_push(&S->cand, mk_key(APPROX(nn), nn));
+        }
+    }
+#undef APPROX
+    visited_reset(S);
+
+    /* approximate results, best first */
+    int na = S->res.n;
+    S->sorted = (uint64_t *)realloc(S->sorted, sizeof(uint64_t) * (size_t)(na > 0 ? na : 1));
+    memcpy(S->sorted, S->res.a, sizeof(uint64_t) * (size_t)na);
+    qsort(S->sorted, (size_t)na, sizeof(uint64_t), cmp_u64_desc);
+    if (approx_out) {
+        memcpy(approx_out, S->sorted, sizeof(uint64_t) * (size_t)na);
+        *approx_count = na;
+    }
+
+    /* rerank (a5) — only when a reranker exists, i.e. the PQ path (JVectorReader.java:352-356) */
+    heap_t fin = {0};
+    if (out_doc) {
+        for (int i = 0; i < na; i++) {
+            int32_t node = key_node(S->sorted[i]);
+            float s = key_score(S->sorted[i]);
+            if (use_pq) {
+                if (s < rerank_floor) continue;
+                s = exact_score(sim, q, qnorm, d->vectors + (int64_t)node * dim, dim); /* reranker is NOT x2-wrapped */
+                reranked++;
+            }
+            int32_t doc = d->ord_to_doc ? d->ord_to_doc[node] : node;
+            bounded_push(&fin, k, mk_key(s, doc)); /* collector: tie -> lower docId (a10) */
+        }
+        qsort(fin.a, (size_t)fin.n, sizeof(uint64_t), cmp_u64_desc);
+        for (int i = 0; i < k; i++) {
+            out_doc[i] = i < fin.n ? key_node(fin.a[i]) : -1;
+            out_score[i] = i < fin.n ? key_score(fin.a[i]) : 0.0f;
+        }
+        if (out_count) *out_count = fin.n;
+        free(fin.a);
+    }
+    if (st) {
+        st->visited = visited;
+        st->expanded = expanded;
+        st->expanded_base = expanded;
+        st->reranked = reranked;
+    }
+}
+
+JVO_EXPORT int32_t jvo_search_batch(const jvo_index *ix, const float *queries, int32_t nq, int32_t k, int32_t rerank_k,
+                                    float threshold, float rerank_floor, const uint64_t *accept_bits,
+                                    int64_t accept_stride_words, int32_t *out_doc, float *out_score, int32_t *out_count,
+                                    jv_query_stats *stats, int32_t threads) {
+    if (rerank_k < k) return -1; /* GraphSearcher requires rerankK >= topK */
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+#endif
+    {
+        scratch_t *S = scratch_new(ix);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int i = 0; i < nq; i++) {
+            const uint64_t *bits = accept_bits ? accept_bits + (int64_t)i * accept_stride_words : NULL;
+            search_one(ix, S, queries + (int64_t)i * ix->d.dim, k, rerank_k, threshold, rerank_floor, bits,
+                       out_doc + (int64_t)i * k, out_score + (int64_t)i * k, out_count ? out_count + i : NULL,
+                       stats ? stats + i : NULL, NULL, NULL, -1, ix->d.n);
+        }
+        scratch_free(S);
+    }
+    return 0;
+}
+
+/* approximate result lists only (before rerank): nodes/scores [nq*rerank_k], -1 padded */
+JVO_EXPORT int32_t jvo_search_approx(const jvo_index *ix, const float *queries, int32_t nq, int32_t rerank_k,
+                                     float threshold, const uint64_t *accept_bits, int64_t accept_stride_words,
+                                     int32_t *out_node, float *out_score, int32_t *out_count, jv_query_stats *stats) {
+    scratch_t *S = scratch_new(ix);
+    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)rerank_k);
+    for (int i = 0; i < nq; i++) {
+        int32_t cnt = 0;
+        const uint64_t *bits = accept_bits ? accept_bits + (int64_t)i * accept_stride_words : NULL;
+        search_one(ix, S, queries + (int64_t)i * ix->d.dim, rerank_k, rerank_k, threshold, 0.f, bits, NULL, NULL, NULL,
+                   stats ? stats + i : NULL, keys, &cnt, -1, ix->d.n);
+        for (int j = 0; j < rerank_k; j++) {
+            out_node[(int64_t)i * rerank_k + j] = j < cnt ? key_node(keys[j]) : -1;
+            out_score[(int64_t)i * rerank_k + j] = j < cnt ? key_score(keys[j]) : 0.f;
+        }
+        if (out_count) out_count[i] = cnt;
+    }
+    free(keys);
+    scratch_free(S);
+    return 0;
+}
+
+/* ADC score of explicit (query,node) pairs (a4) */
+JVO_EXPORT void jvo_pq_adc_scores(const jvo_index *ix, const float *queries, int32_t nq, const int32_t *nodes,
+                                  int32_t per_query, float *out) {
+    scratch_t *S = scratch_new(ix);
+    const jv_index_desc *d = &ix->d;
+    for (int i = 0; i < nq; i++) {
+        const float *q = queries + (int64_t)i * d->dim;
+        float qnorm = canon_dot(q, q, d->dim);
+        pq_build_lut(&ix->pq, d->similarity, d->pq_codebooks, d->pq_global_centroid, q, S->lut, S->qc);
+        for (int j = 0; j < per_query; j++) {
+            int32_t node = nodes[(int64_t)i * per_query + j];
+            out[(int64_t)i * per_query + j] =
+                adc_score(d->similarity, S->lut, d->pq_m, d->pq_k, d->pq_codes + (int64_t)node * d->pq_m,
+                          ix->node_norm ? ix->node_norm[node] : 0.f, qnorm, ix->adc_order);
+        }
+    }
+    scratch_free(S);
+}
+
+/* K5: brute-force exact top-k = Lucene exactSearch over JVectorVectorScorer.score()
+ * (JVectorVectorScorer.java:36-53): jVector score, x2 for MIP; deleted ordinals skipped; tie -> lower doc. */
+JVO_EXPORT int32_t jvo_exact_topk(const jvo_index *ix, const float *queries, int32_t nq, int32_t k,
+                                  const uint64_t *accept_bits, int64_t accept_stride_words, int32_t *out_doc,
+                                  float *out_score, int32_t *out_count, int32_t threads) {
+    const jv_index_desc *d = &ix->d;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+#endif
+    for (int i = 0; i < nq; i++) {
+        const float *q = queries + (int64_t)i * d->dim;
+        const uint64_t *bits = accept_bits ? accept_bits + (int64_t)i * accept_stride_words : NULL;
+        float qnorm = canon_dot(q, q, d->dim);
+        float mul = d->similarity == JV_SIM_MIP ? 2.0f : 1.0f;
+        heap_t h = {0};
+        for (int64_t o = 0; o < d->n; o++) {
+            int32_t doc = d->ord_to_doc ? d->ord_to_doc[o] : (int32_t)o;
+            if (doc == -1) continue;
+            if (bits && !((bits[doc >> 6] >> (doc & 63)) & 1ULL)) continue;
+            float s = exact_score(d->similarity, q, qnorm, d->vectors + o * d->dim, d->dim) * mul;
+            bounded_push(&h, k, mk_key(s, doc));
+        }
+        qsort(h.a, (size_t)h.n, sizeof(uint64_t), cmp_u64_desc);
+        for (int j = 0; j < k; j++) {
+            out_doc[(int64_t)i * k + j] = j < h.n ? key_node(h.a[j]) : -1;
+            out_score[(int64_t)i * k + j] = j < h.n ? key_score(h.a[j]) : 0.0f;
+        }
+        if (out_count) out_count[i] = h.n;
+        free(h.a);
+    }
+    return 0;
+}
+
+/* K7: merge g per-shard lists [g][nq][k] -> top-k, tie -> lower doc (Lucene TopDocs.merge analogue) */
+JVO_EXPORT void jvo_merge_topk(int32_t g, int32_t nq, int32_t k, const int32_t *docs, const float *scores, int32_t *out_doc,
+                               float *out_score, int32_t *out_count) {
+    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)g * k);
+    for (int i = 0; i < nq; i++) {
+        int n = 0;
+        for (int s = 0; s < g; s++)
+            for (int j = 0; j < k; j++) {
+                int64_t idx = ((int64_t)s * nq + i) * k + j;
+                if (docs[idx] >= 0) keys[n++] = mk_key(scores[idx], docs[idx]);
+            }
+        qsort(keys, (size_t)n, sizeof(uint64_t), cmp_u64_desc);
+        for (int j = 0; j < k; j++) {
+            out_doc[(int64_t)i * k + j] = j < n ? key_node(keys[j]) : -1;
+            out_score[(int64_t)i * k + j] = j < n ? key_score(keys[j]) : 0.f;
+        }
+        if (out_count) out_count[i] = n < k ? n : k;
+    }
+    free(keys);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FIXTURE: PQ codebook training (ProductQuantization.compute, JVectorIndexQuantization.java:123-131;
+ * SURVEY A.3 [M]): optional global centring, per-subspace k-means++ seeding + `iters` Lloyd
+ * iterations.  Upstream training is randomised, so codebooks are only comparable given the same
+ * generator; ours is splitmix64 so the device trainer (jv_pq_train) can reproduce it exactly.
+ * Accumulations are sequential in double in ordinal order.
+ * ------------------------------------------------------------------------------------------ */
+static inline uint64_t splitmix64(uint64_t *s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static inline double u01(uint64_t *s) { return (double)(splitmix64(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+JVO_EXPORT void jvo_pq_train(const float *vectors, int64_t n, int32_t dim, int32_t M, int32_t K, int32_t center,
+                             int32_t iters, uint64_t seed, float *out_codebooks, float *out_gcent) {
+    pq_shape s;
+    pq_shape_init(&s, dim, M, K);
+    float *g = NULL;
+    if (center) {
+        g = out_gcent;
+        for (int d = 0; d < dim; d++) {
+            double acc = 0.0;
+            for (int64_t i = 0; i < n; i++) acc += (double)vectors[i * dim + d];
+            g[d] = (float)(acc / (double)n);
+        }
+    }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int m = 0; m < M; m++) {
+        const int len = s.size[m], off = s.off[m];
+        float *cb = out_codebooks + s.cb_off[m];
+        float *x = (float *)malloc(sizeof(float) * (size_t)n * len); /* centred sub-vectors */
+        for (int64_t i = 0; i < n; i++)
+            for (int j = 0; j < len; j++) x[i * len + j] = g ? vectors[i * dim + off + j] - g[off + j] : vectors[i * dim + off + j];
+        float *d2 = (float *)malloc(sizeof(float) * (size_t)n);
+        int32_t *assign = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+        uint64_t rng = seed * 0x9E3779B97F4A7C15ULL + (uint64_t)m * 0xD1B54A32D192ED03ULL + 1;
+        /* k-means++ seeding */
+        int64_t first = (int64_t)(splitmix64(&rng) % (uint64_t)n);
+        memcpy(cb, x + first * len, sizeof(float) * (size_t)len);
+        for (int64_t i = 0; i < n; i++) d2[i] = sub_l2sq(x + i * len, cb, len);
+        for (int c = 1; c < K; c++) {
+            double total = 0.0;
+            for (int64_t i = 0; i < n; i++) total += (double)d2[i];
+            double r = u01(&rng) * total, run = 0.0;
+            int64_t pick = n - 1;
+            for (int64_t i = 0; i < n; i++) {
+                run += (double)d2[i];
+                if (run > r) {
+                    pick = i;
+                    break;
+                }
+            }
+            float *cc = cb + (int64_t)c * len;
+            memcpy(cc, x + pick * len, sizeof(float) * (size_t)len);
+            for (int64_t i = 0; i < n; i++) {
+                float dd = sub_l2sq(x + i * len, cc, len);
+                if (dd < d2[i]) d2[i] = dd;
+            }
+        }
+        /* Lloyd */
+        double *sum = (double *)malloc(sizeof(double) * (size_t)K * len);
+        int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)K);
+        for (int it = 0; it < iters; it++) {
+            for (int64_t i = 0; i < n; i++) {
+                float best = INFINITY;
+                int idx = 0;
+                for (int c = 0; c < K; c++) {
+                    float dd = sub_l2sq(x + i * len, cb + (int64_t)c * len, len);
+                    if (dd < best) {
+                        best = dd;
+                        idx = c;
+                    }
+                }
+                assign[i] = idx;
+            }
+            memset(sum, 0, sizeof(double) * (size_t)K * len);
+            memset(cnt, 0, sizeof(int64_t) * (size_t)K);
+            for (int64_t i = 0; i < n; i++) {
+                cnt[assign[i]]++;
+                for (int j = 0; j < len; j++) sum[(int64_t)assign[i] * len + j] += (double)x[i * len + j];
+            }
+            for (int c = 0; c < K; c++)
+                if (cnt[c] > 0) /* empty cluster keeps its previous centroid */
+                    for (int j = 0; j < len; j++) cb[(int64_t)c * len + j] = (float)(sum[(int64_t)c * len + j] / (double)cnt[c]);
+        }
+        free(sum);
+        free(cnt);
+        free(x);
+        free(d2);
+        free(assign);
+    }
+    pq_shape_free(&s);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FIXTURE: Vamana construction (GraphIndexBuilder, JVectorWriter.java:1383-1422; SURVEY A.4 [M]).
+ * Batched-insert schedule shared with the device builder (jv_graph_build) so adjacency can be
+ * compared exactly:
+ *   entry = medoid (node whose exact score against the mean vector is best)
+ *   batches: entry alone first; then, over the remaining ordinals in order, batches whose size is
+ *            min(max_batch, max(1, inserted * growth)) ("prefix doubling")
+ *   per batch, against the graph FROZEN at batch start:
+ *     1. search(q = vector[p], L = beamWidth, exact scores) -> candidates (best first, p itself excluded)
+ *     2. out[p] = retainDiverse(candidates, R, alpha)
+ *   then, in ordinal order of the batch: for nb in out[p]: append p to adj[nb];
+ *   then every node touched whose degree > R*overflow is re-pruned with retainDiverse to R.
+ *   cleanup: every node with degree > R re-pruned to R.
+ * retainDiverse (jVector ConcurrentNeighborMap.retainDiverse [M]): for a = 1.0, 1.2, .. <= alpha: walk
+ * candidates best first, select c unless some already-selected s has score(c,s) > score(c,p) * a.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t *nodes;
+    float *scores;
+    int n;
+} nlist;
+
+static int retain_diverse(const float *vecs, int dim, int sim, const int32_t *cn, const float *cs, int nc, int R,
+                          float alpha, int32_t *out_nodes, float *out_scores) {
+    int nsel = 0;
+    uint8_t *taken = (uint8_t *)calloc((size_t)(nc > 0 ? nc : 1), 1);
+    for (float a = 1.0f; a <= alpha + 1e-6f && nsel < R; a += 0.2f) {
+        for (int i = 0; i < nc && nsel < R; i++) {
+            if (taken[i]) continue;
+            const float *cv = vecs + (int64_t)cn[i] * dim;
+            float cnorm = canon_dot(cv, cv, dim);
+            int diverse = 1;
+            for (int j = 0; j < nsel; j++) {
+                float sb = exact_score(sim == JV_SIM_MIP ? JV_SIM_DOT : sim, cv, cnorm, vecs + (int64_t)out_nodes[j] * dim, dim);
+                if (sb > cs[i] * a) {
+                    diverse = 0;
+                    break;
+                }
+            }
+            if (diverse) {
+                taken[i] = 1;
+                out_nodes[nsel] = cn[i];
+                out_scores[nsel] = cs[i];
+                nsel++;
+            }
+        }
+    }
+    free(taken);
+    return nsel;
+}
+
+static void sort_by_key_desc(int32_t *nodes, float *scores, int n) {
+    uint64_t *k = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) k[i] = mk_key(scores[i], nodes[i]);
+    qsort(k, (size_t)n, sizeof(uint64_t), cmp_u64_desc);
+    for (int i = 0; i < n; i++) {
+        nodes[i] = key_node(k[i]);
+        scores[i] = key_score(k[i]);
+    }
+    free(k);
+}
+
+JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim, int32_t sim, int32_t R, int32_t beam,
+                                   float overflow, float alpha, int32_t max_batch, float growth, int32_t *out_adj,
+                                   int32_t *out_entry) {
+    const int bsim = sim == JV_SIM_MIP ? JV_SIM_DOT : sim;
+    const int cap = (int)ceilf((float)R * overflow) + 1; /* list capacity incl. one overflow slot */
+    /* medoid */
+    float *mean = (float *)calloc((size_t)dim, sizeof(float));
+    for (int d = 0; d < dim; d++) {
+        double acc = 0;
+        for (int64_t i = 0; i < n; i++) acc += vectors[i * dim + d];
+        mean[d] = (float)(acc / (double)n);
+    }
+    float mnorm = canon_dot(mean, mean, dim);
+    int32_t entry = 0;
+    uint64_t bestk = 0;
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t kk = mk_key(exact_score(bsim, mean, mnorm, vectors + i * dim, dim), (int32_t)i);
+        if (kk > bestk) {
+            bestk = kk;
+            entry = (int32_t)i;
+        }
+    }
+    free(mean);
+    *out_entry = entry;
+
+    /* insertion order: entry first, then ordinals ascending */
+    int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    order[0] = entry;
+    for (int64_t i = 0, j = 1; i < n; i++)
+        if (i != entry) order[j++] = (int32_t)i;
+
+    /* dynamic adjacency with scores (score of neighbour w.r.t. owner) */
+    int32_t **adj = (int32_t **)calloc((size_t)n, sizeof(int32_t *));
+    float **ads = (float **)calloc((size_t)n, sizeof(float *));
+    int *deg = (int *)calloc((size_t)n, sizeof(int));
+    int *acap = (int *)calloc((size_t)n, sizeof(int));
+    uint8_t *inserted = (uint8_t *)calloc((size_t)n, 1);
+    /* frozen flat view for the searcher: stride Rb = floor(R*overflow), the largest degree that
+     * survives a batch (longer lists are re-pruned to R), so searches see the overflow edges too */
+    const int Rb = (int)floorf((float)R * overflow) > R ? (int)floorf((float)R * overflow) : R;
+    int32_t *flat = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * Rb);
+    for (int64_t i = 0; i < n * Rb; i++) flat[i] = -1;
+
+    jv_index_desc d;
+    memset(&d, 0, sizeof(d));
+    d.similarity = bsim;
+    d.dim = dim;
+    d.max_degree = Rb;
+    d.n = n;
+    d.entry_node = entry;
+    d.adjacency = flat;
+    d.vectors = vectors;
+    jvo_index *ix = jvo_index_create(&d);
+
+    inserted[entry] = 1;
+    int64_t done = 1;
+    while (done < n) {
+        int64_t bs = (int64_t)((double)done * growth);
+        if (bs < 1) bs = 1;
+        if (bs > max_batch) bs = max_batch;
+        if (bs > n - done) bs = n - done;
+        /* 1+2: search + prune against the frozen graph */
+        int32_t *newn = (int32_t *)malloc(sizeof(int32_t) * (size_t)bs * R);
+        float *news = (float *)malloc(sizeof(float) * (size_t)bs * R);
+        int *newc = (int *)malloc(sizeof(int) * (size_t)bs);
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+        {
+            scratch_t *S = scratch_new(ix);
+            uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)beam);
+            int32_t *cn = (int32_t *)malloc(sizeof(int32_t) * (size_t)beam);
+            float *cs = (float *)malloc(sizeof(float) * (size_t)beam);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 8)
+#endif
+            for (int64_t b = 0; b < bs; b++) {
+                int32_t p = order[done + b];
+                int32_t cnt = 0;
+                search_one(ix, S, vectors + (int64_t)p * dim, beam, beam, 0.f, 0.f, NULL, NULL, NULL, NULL, NULL, keys,
+                           &cnt, entry, n);
+                int nc = 0;
+                for (int i = 0; i < cnt; i++) {
+                    if (key_node(keys[i]) == p) continue;
+                    cn[nc] = key_node(keys[i]);
+                    cs[nc] = key_score(keys[i]);
+                    nc++;
+                }
+                newc[b] = retain_diverse(vectors, dim, bsim, cn, cs, nc, R, alpha, newn + b * R, news + b * R);
+            }
+            free(keys);
+            free(cn);
+            free(cs);
+            scratch_free(S);
+        }
+        /* commit out-edges, then backlinks in batch order */
+        int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)bs * (R + 1));
+        int nt = 0;
+        for (int64_t b = 0; b < bs; b++) {
+            int32_t p = order[done + b];
+            inserted[p] = 1;
+            if (acap[p] < newc[b] + 1) {
+                acap[p] = cap + 8;
+                adj[p] = (int32_t *)realloc(adj[p], sizeof(int32_t) * (size_t)acap[p]);
+                ads[p] = (float *)realloc(ads[p], sizeof(float) * (size_t)acap[p]);
+            }
+            deg[p] = newc[b];
+            memcpy(adj[p], newn + b * R, sizeof(int32_t) * (size_t)newc[b]);
+            memcpy(ads[p], news + b * R, sizeof(float) * (size_t)newc[b]);
+            touched[nt++] = p;
+        }
+        for (int64_t b = 0; b < bs; b++) {
+            int32_t p = order[done + b];
+            for (int j = 0; j < newc[b]; j++) {
+                int32_t nb = newn[b * R + j];
+                int dup = 0;
+                for (int t = 0; t < deg[nb]; t++)
+                    if (adj[nb][t] == p) {
+                        dup = 1;
+                        break;
+                    }
+                if (dup) continue;
+                if (deg[nb] + 1 > acap[nb]) {
+                    acap[nb] = (deg[nb] + 1) * 2 + 8;
+                    adj[nb] = (int32_t *)realloc(adj[nb], sizeof(int32_t) * (size_t)acap[nb]);
+                    ads[nb] = (float *)realloc(ads[nb], sizeof(float) * (size_t)acap[nb]);
+                }
+                adj[nb][deg[nb]] = p;
+                ads[nb][deg[nb]] = news[b * R + j]; /* symmetric similarity */
+                deg[nb]++;
+                touched[nt++] = nb;
+            }
+        }
+        /* re-prune overflowing lists */
+        for (int t = 0; t < nt; t++) {
+            int32_t u = touched[t];
+            if ((float)deg[u] > (float)R * overflow) {
+                sort_by_key_desc(adj[u], ads[u], deg[u]);
+                int32_t *tn = (int32_t *)malloc(sizeof(int32_t) * (size_t)R);
+                float *ts = (float *)malloc(sizeof(float) * (size_t)R);
+                int c = retain_diverse(vectors, dim, bsim, adj[u], ads[u], deg[u], R, alpha, tn, ts);
+                memcpy(adj[u], tn, sizeof(int32_t) * (size_t)c);
+                memcpy(ads[u], ts, sizeof(float) * (size_t)c);
+                deg[u] = c;
+                free(tn);
+                free(ts);
+            }
+        }
+        /* refresh the frozen view */
+        for (int t = 0; t < nt; t++) {
+            int32_t u = touched[t];
+            for (int j = 0; j < Rb; j++) flat[(int64_t)u * Rb + j] = j < deg[u] ? adj[u][j] : -1;
+        }
+        free(touched);
+        free(newn);
+        free(news);
+        free(newc);
+        done += bs;
+    }
+    /* cleanup: enforce degree <= R */
+    for (int64_t u = 0; u < n; u++) {
+        if (deg[u] > R) {
+            sort_by_key_desc(adj[u], ads[u], deg[u]);
+            int32_t *tn = (int32_t *)malloc(sizeof(int32_t) * (size_t)R);
+            float *ts = (float *)malloc(sizeof(float) * (size_t)R);
+            int c = retain_diverse(vectors, dim, bsim, adj[u], ads[u], deg[u], R, alpha, tn, ts);
+            memcpy(adj[u], tn, sizeof(int32_t) * (size_t)c);
+            deg[u] = c;
+            free(tn);
+            free(ts);
+        }
+        for (int j = 0; j < R; j++) out_adj[u * R + j] = j < deg[u] ? adj[u][j] : -1;
+    }
+    for (int64_t u = 0; u < n; u++) {
+        free(adj[u]);
+        free(ads[u]);
+    }
+    free(adj);
+    free(ads);
+    free(deg);
+    free(acap);
+    free(inserted);
+    free(flat);
+    free(order);
+    jvo_index_destroy(ix);
+    return 0;
+}
+
+JVO_EXPORT int32_t jvo_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

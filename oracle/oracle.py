@@ -1,0 +1,285 @@
+"""ctypes front-end of the CPU oracle (oracle/jv_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+Parity status: "unpinned" for PQ codes / LUT / traversal order (no golden vectors exist in the
+reference and jVector 4.0.0-rc.9 itself cannot run here); pinned for the analytic known-answer tests
+the reference holds (tests/test_oracle_kat.py).  See the header of jv_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "_build" / "libjvoracle.so"
+
+SIM_EUCLIDEAN, SIM_DOT, SIM_COSINE, SIM_MIP = 0, 1, 2, 3
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    src = _HERE / "jv_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-s"], check=True)
+    return _LIB_PATH
+
+
+class IndexDesc(C.Structure):
+    """Mirror of jv_index_desc in include/jvgpu.h (the oracle consumes the same description)."""
+
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("similarity", C.c_int32),
+        ("dim", C.c_int32),
+        ("max_degree", C.c_int32),
+        ("n", C.c_int64),
+        ("entry_node", C.c_int32),
+        ("max_doc", C.c_int32),
+        ("adjacency", C.c_void_p),
+        ("vectors", C.c_void_p),
+        ("ord_to_doc", C.c_void_p),
+        ("pq_m", C.c_int32),
+        ("pq_k", C.c_int32),
+        ("pq_codebooks", C.c_void_p),
+        ("pq_global_centroid", C.c_void_p),
+        ("pq_codes", C.c_void_p),
+        ("device", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class QueryStats(C.Structure):
+    _fields_ = [("visited", C.c_int32), ("expanded", C.c_int32), ("expanded_base", C.c_int32), ("reranked", C.c_int32)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.jvo_index_create.restype = C.c_void_p
+        _lib.jvo_index_create.argtypes = [C.POINTER(IndexDesc)]
+        _lib.jvo_index_destroy.argtypes = [C.c_void_p]
+        _lib.jvo_exact_score.restype = C.c_float
+        _lib.jvo_default_num_subspaces.restype = C.c_int32
+        _lib.jvo_num_threads.restype = C.c_int32
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def java_random_floats(seed: int, count: int) -> np.ndarray:
+    """`new java.util.Random(seed)` then `count` x nextFloat() (TestUtils.java:108-124)."""
+    out = np.empty(count, dtype=np.float32)
+    lib().jvo_java_random_floats(C.c_int64(seed), C.c_int64(count), _p(out))
+    return out
+
+
+def java_random_vectors(n: int, dim: int, seed: int) -> np.ndarray:
+    return java_random_floats(seed, n * dim).reshape(n, dim)
+
+
+def exact_score(sim: int, q, x) -> float:
+    q = _f32(q)
+    x = _f32(x)
+    return float(lib().jvo_exact_score(C.c_int32(sim), _p(q), _p(x), C.c_int32(q.shape[0])))
+
+
+def default_num_subspaces(dim: int) -> int:
+    return int(lib().jvo_default_num_subspaces(C.c_int32(dim)))
+
+
+def pq_subspaces(dim: int, m: int):
+    sizes = np.empty(m, dtype=np.int32)
+    offs = np.empty(m, dtype=np.int32)
+    lib().jvo_pq_subspaces(C.c_int32(dim), C.c_int32(m), _p(sizes), _p(offs))
+    return sizes, offs
+
+
+def pq_train(vectors, m: int, k: int, center: bool, iters: int = 6, seed: int = 0):
+    v = _f32(vectors)
+    n, dim = v.shape
+    cb = np.empty(k * dim, dtype=np.float32)
+    g = np.zeros(dim, dtype=np.float32) if center else None
+    lib().jvo_pq_train(_p(v), C.c_int64(n), C.c_int32(dim), C.c_int32(m), C.c_int32(k), C.c_int32(int(center)),
+                       C.c_int32(iters), C.c_uint64(seed), _p(cb), _p(g))
+    return cb, g
+
+
+def pq_encode(vectors, m: int, k: int, codebooks, gcent=None, threads: int = 0) -> np.ndarray:
+    v = _f32(vectors)
+    n, dim = v.shape
+    cb = _f32(codebooks)
+    g = _f32(gcent)
+    out = np.empty((n, m), dtype=np.uint8)
+    lib().jvo_pq_encode(_p(v), C.c_int64(n), C.c_int32(dim), C.c_int32(m), C.c_int32(k), _p(cb), _p(g), _p(out),
+                        C.c_int32(threads))
+    return out
+
+
+def pq_lut(sim: int, dim: int, m: int, k: int, codebooks, gcent, queries) -> np.ndarray:
+    q = _f32(queries)
+    cb = _f32(codebooks)
+    g = _f32(gcent)
+    out = np.empty((q.shape[0], m, k), dtype=np.float32)
+    lib().jvo_pq_lut(C.c_int32(sim), C.c_int32(dim), C.c_int32(m), C.c_int32(k), _p(cb), _p(g), _p(q),
+                     C.c_int32(q.shape[0]), _p(out))
+    return out
+
+
+def graph_build(vectors, sim: int, max_degree: int = 32, beam_width: int = 100, overflow: float = 1.2,
+                alpha: float = 1.2, max_batch: int = 1024, growth: float = 0.02):
+    """Fixture: batched-insert Vamana with exact build scores.  Returns (adjacency[n,R], entry)."""
+    v = _f32(vectors)
+    n, dim = v.shape
+    adj = np.empty((n, max_degree), dtype=np.int32)
+    entry = C.c_int32(0)
+    lib().jvo_graph_build(_p(v), C.c_int64(n), C.c_int32(dim), C.c_int32(sim), C.c_int32(max_degree),
+                          C.c_int32(beam_width), C.c_float(overflow), C.c_float(alpha), C.c_int32(max_batch),
+                          C.c_float(growth), _p(adj), C.byref(entry))
+    return adj, int(entry.value)
+
+
+class OracleIndex:
+    """One field of one segment, as decoded arrays (what FieldEntry holds, JVectorReader.java:284-337)."""
+
+    def __init__(self, similarity: int, vectors, adjacency, entry_node: int, ord_to_doc=None, max_doc=None,
+                 pq_m: int = 0, pq_k: int = 0, pq_codebooks=None, pq_global_centroid=None, pq_codes=None,
+                 adc_order: int = 0):
+        self.vectors = _f32(vectors)
+        self.n, self.dim = self.vectors.shape
+        self.adjacency = np.ascontiguousarray(adjacency, dtype=np.int32)
+        self.ord_to_doc = None if ord_to_doc is None else np.ascontiguousarray(ord_to_doc, dtype=np.int32)
+        self.max_doc = int(max_doc) if max_doc is not None else (
+            self.n if self.ord_to_doc is None else int(self.ord_to_doc.max(initial=-1)) + 1)
+        self.codebooks = _f32(pq_codebooks)
+        self.gcent = _f32(pq_global_centroid)
+        self.codes = None if pq_codes is None else np.ascontiguousarray(pq_codes, dtype=np.uint8)
+        self.similarity = similarity
+        d = IndexDesc()
+        d.struct_size = C.sizeof(IndexDesc)
+        d.similarity = similarity
+        d.dim = self.dim
+        d.max_degree = self.adjacency.shape[1] if self.adjacency.ndim == 2 else 0
+        d.n = self.n
+        d.entry_node = entry_node
+        d.max_doc = self.max_doc
+        d.adjacency = self.adjacency.ctypes.data
+        d.vectors = self.vectors.ctypes.data
+        d.ord_to_doc = None if self.ord_to_doc is None else self.ord_to_doc.ctypes.data
+        d.pq_m = pq_m if self.codes is not None else 0
+        d.pq_k = pq_k
+        d.pq_codebooks = None if self.codebooks is None else self.codebooks.ctypes.data
+        d.pq_global_centroid = None if self.gcent is None else self.gcent.ctypes.data
+        d.pq_codes = None if self.codes is None else self.codes.ctypes.data
+        self.desc = d
+        self._h = lib().jvo_index_create(C.byref(d))
+        if adc_order:
+            lib().jvo_index_set_adc_order(C.c_void_p(self._h), C.c_int32(adc_order))
+
+    def close(self):
+        if self._h:
+            lib().jvo_index_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _bits(self, accept_bits, nq):
+        if accept_bits is None:
+            return None, 0
+        b = np.ascontiguousarray(accept_bits, dtype=np.uint64)
+        stride = 0 if b.ndim == 1 else b.shape[1]
+        return b, stride
+
+    def search(self, queries, k: int, rerank_k: int, threshold: float = 0.0, rerank_floor: float = 0.0,
+               accept_bits=None, threads: int = 0):
+        q = _f32(np.atleast_2d(queries))
+        nq = q.shape[0]
+        docs = np.empty((nq, k), dtype=np.int32)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        stats = (QueryStats * nq)()
+        b, stride = self._bits(accept_bits, nq)
+        rc = lib().jvo_search_batch(C.c_void_p(self._h), _p(q), C.c_int32(nq), C.c_int32(k), C.c_int32(rerank_k),
+                                    C.c_float(threshold), C.c_float(rerank_floor), _p(b), C.c_int64(stride), _p(docs),
+                                    _p(scores), _p(counts), stats, C.c_int32(threads))
+        if rc != 0:
+            raise ValueError("rerankK must be >= topK")
+        st = np.frombuffer(stats, dtype=np.int32).reshape(nq, 4).copy()
+        return docs, scores, counts, st
+
+    def search_approx(self, queries, rerank_k: int, threshold: float = 0.0, accept_bits=None):
+        q = _f32(np.atleast_2d(queries))
+        nq = q.shape[0]
+        nodes = np.empty((nq, rerank_k), dtype=np.int32)
+        scores = np.empty((nq, rerank_k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        stats = (QueryStats * nq)()
+        b, stride = self._bits(accept_bits, nq)
+        lib().jvo_search_approx(C.c_void_p(self._h), _p(q), C.c_int32(nq), C.c_int32(rerank_k), C.c_float(threshold),
+                                _p(b), C.c_int64(stride), _p(nodes), _p(scores), _p(counts), stats)
+        st = np.frombuffer(stats, dtype=np.int32).reshape(nq, 4).copy()
+        return nodes, scores, counts, st
+
+    def adc_scores(self, queries, nodes):
+        q = _f32(np.atleast_2d(queries))
+        nd = np.ascontiguousarray(np.atleast_2d(nodes), dtype=np.int32)
+        out = np.empty(nd.shape, dtype=np.float32)
+        lib().jvo_pq_adc_scores(C.c_void_p(self._h), _p(q), C.c_int32(q.shape[0]), _p(nd), C.c_int32(nd.shape[1]), _p(out))
+        return out
+
+    def exact_topk(self, queries, k: int, accept_bits=None, threads: int = 0):
+        q = _f32(np.atleast_2d(queries))
+        nq = q.shape[0]
+        docs = np.empty((nq, k), dtype=np.int32)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        b, stride = self._bits(accept_bits, nq)
+        lib().jvo_exact_topk(C.c_void_p(self._h), _p(q), C.c_int32(nq), C.c_int32(k), _p(b), C.c_int64(stride),
+                             _p(docs), _p(scores), _p(counts), C.c_int32(threads))
+        return docs, scores, counts
+
+
+def merge_topk(docs, scores, k: int):
+    """docs/scores [g, nq, k] -> merged top-k (tie -> lower doc)."""
+    d = np.ascontiguousarray(docs, dtype=np.int32)
+    s = _f32(scores)
+    g, nq, kk = d.shape
+    assert kk == k
+    od = np.empty((nq, k), dtype=np.int32)
+    os_ = np.empty((nq, k), dtype=np.float32)
+    oc = np.empty(nq, dtype=np.int32)
+    lib().jvo_merge_topk(C.c_int32(g), C.c_int32(nq), C.c_int32(k), _p(d), _p(s), _p(od), _p(os_), _p(oc))
+    return od, os_, oc
+
+
+def num_threads() -> int:
+    return int(lib().jvo_num_threads())
+
+
+def make_accept_bits(accept_mask) -> np.ndarray:
+    """bool[maxDoc] -> Lucene FixedBitSet words (bit d = word d>>6, bit d&63)."""
+    m = np.asarray(accept_mask, dtype=bool)
+    nwords = (m.shape[0] + 63) // 64
+    padded = np.zeros(nwords * 64, dtype=bool)
+    padded[: m.shape[0]] = m
+    return np.packbits(padded.reshape(nwords, 64), axis=1, bitorder="little").view(np.uint64).reshape(nwords)
