@@ -54,6 +54,7 @@ namespace jv {
 // K1+K2 / K4: graph traversal with ADC (PQ) or exact scoring; writes the approximate result list.
 struct SearchLaunch {
     const float *d_queries;
+    const int32_t *d_query_ids = nullptr; // builder: query i = stored vector query_ids[i]
     int nq;
     int rerank_k;
     float threshold;

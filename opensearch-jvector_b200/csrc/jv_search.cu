@@ -42,6 +42,7 @@ struct SearchParams {
     float mip_mul;
     // batch
     const float *queries;
+    const int32_t *query_ids; // optional: query i is vectors[query_ids[i]] (graph builder)
     const uint64_t *accept;
     int64_t accept_stride;
     uint64_t *approx_keys;
@@ -195,7 +196,8 @@ template <bool PQ, typename LutT> __global__ void __launch_bounds__(kThreads) se
         const int qi = s_query;
         if (qi >= p.nq) break;
 
-        const float *gq = p.queries + (int64_t)qi * p.dim;
+        // builder mode: the query is a stored vector addressed by ordinal
+        const float *gq = p.query_ids ? p.vectors + (int64_t)__ldg(p.query_ids + qi) * p.dim : p.queries + (int64_t)qi * p.dim;
         for (int i = tid; i < p.dim; i += kThreads) sq[i] = __ldg(gq + i);
         for (int i = tid; i < H; i += kThreads) hash[i] = kEmpty;
         if (tid == 0) {
@@ -417,8 +419,9 @@ static int32_t launch_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_
                   fixed_bytes, smem_limit);
         return JV_ERR_UNSUPPORTED;
     }
-    // do not take more than needed when the table is small: expected visits ~ 2 * L * R
-    const int64_t want = (int64_t)8 * p.L * (p.R > 0 ? p.R : 1);
+    // do not take more than needed: visits ~ expansions * new-neighbours ~ 0.7 * L * R without a filter;
+    // a filter multiplies the expansions by ~1/selectivity, so keep everything shared memory offers then
+    const int64_t want = p.accept ? ((int64_t)1 << 30) : (int64_t)3 * p.L * (p.R > 0 ? p.R : 1);
     while (hash_log2 > 12 && ((int64_t)1 << (hash_log2 - 1)) >= want) hash_log2--;
     p.hash_log2 = hash_log2;
     const size_t smem = fixed_bytes + ((size_t)4 << hash_log2);
@@ -448,6 +451,7 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     p.n_limit = a.n_limit > 0 ? a.n_limit : ix->n;
     if (a.entry_override >= 0) p.entry = a.entry_override;
     p.queries = a.d_queries;
+    p.query_ids = a.d_query_ids;
     p.accept = a.d_accept;
     p.accept_stride = a.accept_stride_words;
     p.approx_keys = a.d_approx_keys;

@@ -696,6 +696,7 @@ static inline uint64_t splitmix64(uint64_t *s) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
+#define JVO_KMPP_BLOCK 256
 static inline double u01(uint64_t *s) { return (double)(splitmix64(s) >> 11) * (1.0 / 9007199254740992.0); }
 
 JVO_EXPORT void jvo_pq_train(const float *vectors, int64_t n, int32_t dim, int32_t M, int32_t K, int32_t center,
@@ -727,17 +728,36 @@ JVO_EXPORT void jvo_pq_train(const float *vectors, int64_t n, int32_t dim, int32
         int64_t first = (int64_t)(splitmix64(&rng) % (uint64_t)n);
         memcpy(cb, x + first * len, sizeof(float) * (size_t)len);
         for (int64_t i = 0; i < n; i++) d2[i] = sub_l2sq(x + i * len, cb, len);
+        const int64_t nblk = (n + JVO_KMPP_BLOCK - 1) / JVO_KMPP_BLOCK;
+        double *bsum = (double *)malloc(sizeof(double) * (size_t)nblk);
         for (int c = 1; c < K; c++) {
+            /* D^2 sampling over a two-level sum (blocks of 256 in ordinal order) so that the device trainer,
+             * which sums blocks in parallel, reproduces the same pick */
             double total = 0.0;
-            for (int64_t i = 0; i < n; i++) total += (double)d2[i];
-            double r = u01(&rng) * total, run = 0.0;
+            for (int64_t b = 0; b < nblk; b++) {
+                double acc = 0.0;
+                const int64_t e = (b + 1) * JVO_KMPP_BLOCK < n ? (b + 1) * JVO_KMPP_BLOCK : n;
+                for (int64_t i = b * JVO_KMPP_BLOCK; i < e; i++) acc += (double)d2[i];
+                bsum[b] = acc;
+                total += acc;
+            }
+            const double r = u01(&rng) * total;
+            double run = 0.0;
             int64_t pick = n - 1;
-            for (int64_t i = 0; i < n; i++) {
-                run += (double)d2[i];
-                if (run > r) {
-                    pick = i;
+            for (int64_t b = 0; b < nblk; b++) {
+                if (run + bsum[b] > r || b == nblk - 1) {
+                    const int64_t e = (b + 1) * JVO_KMPP_BLOCK < n ? (b + 1) * JVO_KMPP_BLOCK : n;
+                    pick = e - 1;
+                    for (int64_t i = b * JVO_KMPP_BLOCK; i < e; i++) {
+                        run += (double)d2[i];
+                        if (run > r) {
+                            pick = i;
+                            break;
+                        }
+                    }
                     break;
                 }
+                run += bsum[b];
             }
             float *cc = cb + (int64_t)c * len;
             memcpy(cc, x + pick * len, sizeof(float) * (size_t)len);
@@ -776,6 +796,7 @@ JVO_EXPORT void jvo_pq_train(const float *vectors, int64_t n, int32_t dim, int32
         free(cnt);
         free(x);
         free(d2);
+        free(bsum);
         free(assign);
     }
     pq_shape_free(&s);
@@ -786,22 +807,20 @@ JVO_EXPORT void jvo_pq_train(const float *vectors, int64_t n, int32_t dim, int32
  * Batched-insert schedule shared with the device builder (jv_graph_build) so adjacency can be
  * compared exactly:
  *   entry = medoid (node whose exact score against the mean vector is best)
- *   batches: entry alone first; then, over the remaining ordinals in order, batches whose size is
- *            min(max_batch, max(1, inserted * growth)) ("prefix doubling")
+ *   batches: entry alone first; then, over the remaining ordinals in order, batches of size
+ *            min(inserted, max(1, min(max_batch, frac * n)))  ("prefix doubling", ParlayANN style)
  *   per batch, against the graph FROZEN at batch start:
  *     1. search(q = vector[p], L = beamWidth, exact scores) -> candidates (best first, p itself excluded)
  *     2. out[p] = retainDiverse(candidates, R, alpha)
  *   then, in ordinal order of the batch: for nb in out[p]: append p to adj[nb];
- *   then every node touched whose degree > R*overflow is re-pruned with retainDiverse to R.
+ *   then every node touched whose degree > R*overflow is sorted best first, cut to the best 1024 and
+ *   re-pruned with retainDiverse to R.
  *   cleanup: every node with degree > R re-pruned to R.
  * retainDiverse (jVector ConcurrentNeighborMap.retainDiverse [M]): for a = 1.0, 1.2, .. <= alpha: walk
  * candidates best first, select c unless some already-selected s has score(c,s) > score(c,p) * a.
  * ------------------------------------------------------------------------------------------ */
-typedef struct {
-    int32_t *nodes;
-    float *scores;
-    int n;
-} nlist;
+#define JVO_PRUNE_MAX_CANDS 1024
+#define JVO_APPEND_CAP 2048
 
 static int retain_diverse(const float *vecs, int dim, int sim, const int32_t *cn, const float *cs, int nc, int R,
                           float alpha, int32_t *out_nodes, float *out_scores) {
@@ -844,7 +863,7 @@ static void sort_by_key_desc(int32_t *nodes, float *scores, int n) {
 }
 
 JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim, int32_t sim, int32_t R, int32_t beam,
-                                   float overflow, float alpha, int32_t max_batch, float growth, int32_t *out_adj,
+                                   float overflow, float alpha, int32_t max_batch, float frac, int32_t *out_adj,
                                    int32_t *out_entry) {
     const int bsim = sim == JV_SIM_MIP ? JV_SIM_DOT : sim;
     const int cap = (int)ceilf((float)R * overflow) + 1; /* list capacity incl. one overflow slot */
@@ -899,10 +918,11 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
 
     inserted[entry] = 1;
     int64_t done = 1;
+    int64_t bcap = (int64_t)((double)n * (double)frac); /* prefix doubling, capped at frac*n and max_batch */
+    if (bcap > max_batch) bcap = max_batch;
+    if (bcap < 1) bcap = 1;
     while (done < n) {
-        int64_t bs = (int64_t)((double)done * growth);
-        if (bs < 1) bs = 1;
-        if (bs > max_batch) bs = max_batch;
+        int64_t bs = done < bcap ? done : bcap;
         if (bs > n - done) bs = n - done;
         /* 1+2: search + prune against the frozen graph */
         int32_t *newn = (int32_t *)malloc(sizeof(int32_t) * (size_t)bs * R);
@@ -965,6 +985,7 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
                         break;
                     }
                 if (dup) continue;
+                if (deg[nb] >= JVO_APPEND_CAP) continue; /* old ++ incoming is cut at 2048 entries (device scratch size) */
                 if (deg[nb] + 1 > acap[nb]) {
                     acap[nb] = (deg[nb] + 1) * 2 + 8;
                     adj[nb] = (int32_t *)realloc(adj[nb], sizeof(int32_t) * (size_t)acap[nb]);
@@ -981,6 +1002,7 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
             int32_t u = touched[t];
             if ((float)deg[u] > (float)R * overflow) {
                 sort_by_key_desc(adj[u], ads[u], deg[u]);
+                if (deg[u] > JVO_PRUNE_MAX_CANDS) deg[u] = JVO_PRUNE_MAX_CANDS; /* keep the best; same cap on the device */
                 int32_t *tn = (int32_t *)malloc(sizeof(int32_t) * (size_t)R);
                 float *ts = (float *)malloc(sizeof(float) * (size_t)R);
                 int c = retain_diverse(vectors, dim, bsim, adj[u], ads[u], deg[u], R, alpha, tn, ts);
@@ -1006,6 +1028,7 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
     for (int64_t u = 0; u < n; u++) {
         if (deg[u] > R) {
             sort_by_key_desc(adj[u], ads[u], deg[u]);
+            if (deg[u] > JVO_PRUNE_MAX_CANDS) deg[u] = JVO_PRUNE_MAX_CANDS;
             int32_t *tn = (int32_t *)malloc(sizeof(int32_t) * (size_t)R);
             float *ts = (float *)malloc(sizeof(float) * (size_t)R);
             int c = retain_diverse(vectors, dim, bsim, adj[u], ads[u], deg[u], R, alpha, tn, ts);

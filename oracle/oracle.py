@@ -143,7 +143,7 @@ def pq_lut(sim: int, dim: int, m: int, k: int, codebooks, gcent, queries) -> np.
 
 
 def graph_build(vectors, sim: int, max_degree: int = 32, beam_width: int = 100, overflow: float = 1.2,
-                alpha: float = 1.2, max_batch: int = 1024, growth: float = 0.02):
+                alpha: float = 1.2, max_batch: int = 8192, frac: float = 0.02):
     """Fixture: batched-insert Vamana with exact build scores.  Returns (adjacency[n,R], entry)."""
     v = _f32(vectors)
     n, dim = v.shape
@@ -151,7 +151,7 @@ def graph_build(vectors, sim: int, max_degree: int = 32, beam_width: int = 100, 
     entry = C.c_int32(0)
     lib().jvo_graph_build(_p(v), C.c_int64(n), C.c_int32(dim), C.c_int32(sim), C.c_int32(max_degree),
                           C.c_int32(beam_width), C.c_float(overflow), C.c_float(alpha), C.c_int32(max_batch),
-                          C.c_float(growth), _p(adj), C.byref(entry))
+                          C.c_float(frac), _p(adj), C.byref(entry))
     return adj, int(entry.value)
 
 
