@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Headline benchmark: QPS at recall@10 >= 0.95 on 1M x 768 PQ (BASELINE.json configs[1]) + ADC / rerank
+HBM GB/s against the measured roofline.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on all host cores
+
+One "step" = one pass of the hot path (LUT build + beam search with ADC + exact rerank) over one batch of
+10 000 queries.  `value` is measured with the query batch already resident in HBM (jv_search_batch_dev);
+`e2e` goes through the host-pointer entry point the Java codec would call (jv_search_batch): pinned host
+queries in, (doc, score) lists out, copies inside the timed region.
+
+Multi-GPU (torchrun): "replicas" layout (default) — every rank holds the whole 1M index and searches its own
+10 000-query batch, no data-path collective (weak scaling: per-GPU work fixed).  `--layout shards` partitions
+the index across ranks instead, broadcasts the queries and merges per-GPU top-k lists on device after an NCCL
+all-gather (BASELINE.json configs[2] flavour).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: n, dim, sim, pq_m, R, k, overquery, nq
+    "cfg2-1Mx768-dot-pq192": dict(n=1_000_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=128),
+    "cfg2-small-100kx768": dict(n=100_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=128),
+    "tiny-20kx128": dict(n=20_000, dim=128, sim=1, pq_m=32, R=16, k=10, over=5, nq=2_000, latent=32),
+}
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.samples, self._stop, self._t = device, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def gen_data(torch, w, device, seed, n, nq):
+    """Embedding-shaped synthetic data: 1024-cluster Gaussian mixture in a `latent`-d space, embedded into `dim`
+    dimensions by a fixed random map plus small isotropic noise, L2-normalised (SURVEY 8d "Cohere-shaped")."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    dim, L, C = w["dim"], w["latent"], 1024
+    W = torch.randn(L, dim, generator=g, device=device) / (L ** 0.5)
+    cent = torch.randn(C, L, generator=g, device=device)
+
+    def draw(m, gen):
+        out = torch.empty(m, dim, device=device)
+        for s in range(0, m, 131072):
+            e = min(m, s + 131072)
+            z = cent[torch.randint(0, C, (e - s,), generator=gen, device=device)] + 0.6 * torch.randn(e - s, L, generator=gen, device=device)
+            x = z @ W + 0.02 * torch.randn(e - s, dim, generator=gen, device=device)
+            out[s:e] = x / x.norm(dim=1, keepdim=True)
+        return out
+
+    base = draw(n, g)
+    gq = torch.Generator(device=device)
+    gq.manual_seed(seed + 1)
+    queries = draw(nq, gq)
+    return base.contiguous(), queries.contiguous()
+
+
+def build_fixture(torch, jv, w, device, seed, n, log):
+    """Synthetic segment built on the GPU: PQ codebooks (jv_pq_train_dev), codes (K6), Vamana graph (jv_graph_build_dev)."""
+    N = jv.native
+    lib = N.load()
+    dev_t = torch.device("cuda", device)
+    t0 = time.time()
+    base, queries = gen_data(torch, w, dev_t, seed, n, w["nq"])
+    torch.cuda.synchronize(device)
+    log(f"data {n}x{w['dim']} generated in {time.time() - t0:.1f}s")
+    dim, m, K = w["dim"], w["pq_m"], 256
+    t0 = time.time()
+    sample = base
+    if n > 128_000:  # ProductQuantization trains on <= 128k sampled vectors
+        gs = torch.Generator(device=dev_t)
+        gs.manual_seed(seed + 2)
+        sample = base[torch.randperm(n, generator=gs, device=dev_t)[:128_000].sort().values].contiguous()
+    cb = torch.empty(K * dim, device=dev_t)
+    N.check(lib.jv_pq_train_dev(device, sample.data_ptr(), sample.shape[0], dim, m, K, 0, 6, seed, cb.data_ptr(), None))
+    del sample
+    log(f"PQ trained ({m}x{K}) in {time.time() - t0:.1f}s")
+    codes = torch.empty(n, m, dtype=torch.uint8, device=dev_t)
+    enc_ms = C.c_float(0)
+    N.check(lib.jv_pq_encode_dev(device, base.data_ptr(), n, dim, m, K, cb.data_ptr(), None, codes.data_ptr(), C.addressof(enc_ms)))
+    log(f"PQ encode kernel {enc_ms.value:.2f} ms ({n / enc_ms.value / 1e3:.2f} M vectors/s)")
+    t0 = time.time()
+    adj = torch.empty(n, w["R"], dtype=torch.int32, device=dev_t)
+    entry = C.c_int32(0)
+    N.check(lib.jv_graph_build_dev(device, base.data_ptr(), n, dim, w["sim"], w["R"], 100, 1.2, 1.2, adj.data_ptr(), C.addressof(entry)))
+    log(f"Vamana graph (R={w['R']}, beamWidth=100) built in {time.time() - t0:.1f}s, mean degree {(adj >= 0).sum(1).float().mean().item():.1f}")
+    host = dict(base=base.cpu().numpy(), queries=queries.cpu().numpy(), cb=cb.cpu().numpy(), codes=codes.cpu().numpy(),
+                adj=adj.cpu().numpy(), entry=int(entry.value), enc_ms=float(enc_ms.value))
+    del base, codes, adj, cb
+    torch.cuda.empty_cache()
+    return host, queries
+
+
+def recall_at_k(found, truth):
+    k = truth.shape[1]
+    return float(np.mean([len(set(f[f >= 0].tolist()) & set(t.tolist())) / k for f, t in zip(found, truth)]))
+
+
+def algorithmic_bytes(stats, m, R, dim):
+    """ADC = visited*M + expanded*4*(1+R) per query; rerank = reranked*dim*4."""
+    visited, expanded, reranked = stats[:, 0].astype(np.int64), stats[:, 1].astype(np.int64), stats[:, 3].astype(np.int64)
+    return int((visited * m + expanded * 4 * (1 + R)).sum()), int((reranked * dim * 4).sum())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("JV_BENCH_WORKLOAD", "cfg2-1Mx768-dot-pq192"), choices=list(WORKLOADS))
+    ap.add_argument("--layout", default="replicas", choices=["replicas", "shards"])
+    ap.add_argument("--adc-table", default="fp16", choices=["fp16", "fp32"],
+                    help="precision of the per-query ADC table in shared memory (steering scores only; final scores are exact)")
+    ap.add_argument("--expand-width", type=int, default=0, help="0 = library default (4); 1..8; -1 = strict reference-order kernel")
+    ap.add_argument("--quiet", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def log(msg):
+        if not args.quiet and rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    if args.impl == "reference" and rank != 0:
+        return 0  # the CPU arm runs on rank 0 alone
+
+    import torch
+    import jvpkg
+    jv = jvpkg.load()
+    N = jv.native
+    lib = N.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = dict(WORKLOADS[args.workload])
+    k, rk, nq, dim, m, R = w["k"], w["k"] * w["over"], w["nq"], w["dim"], w["pq_m"], w["R"]
+    shards = args.layout == "shards" and world > 1
+    n_local = w["n"] // world if shards else w["n"]
+    seed = 1234 + (rank * 17 if shards else 0)  # replicas share one index; shards hold disjoint data
+    host, d_queries = build_fixture(torch, jv, w, local_rank, seed, n_local, log)
+    if shards and dist is not None:  # every shard answers the same query batch
+        dist.broadcast(d_queries, src=0)
+        host["queries"] = d_queries.cpu().numpy()
+    elif world > 1:  # replicas: each rank searches its own batch
+        _, d_queries = gen_data(torch, w, torch.device("cuda", local_rank), 999 + rank, 8, nq)
+        host["queries"] = d_queries.cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------ CPU arm
+    if args.impl == "reference":
+        from oracle import oracle as O
+        ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
+                            pq_codes=host["codes"])
+        cores = O.num_threads()
+        t0 = time.time()
+        ora.search(host["queries"][:256], k, rk)
+        per_q = (time.time() - t0) / 256
+        sample = int(min(nq, max(256, 1.5 / per_q)))  # ~1.5 s of CPU work per step
+        for _ in range(args.warmup):
+            ora.search(host["queries"][:sample], k, rk)
+        t0 = time.time()
+        for _ in range(args.steps):
+            docs, _, _, _ = ora.search(host["queries"][:sample], k, rk)
+        el = time.time() - t0
+        qps = sample * args.steps / el
+        line = {"impl": "reference", "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "n": n_local, "dim": dim, "similarity": "dot", "pq": f"{m}x256", "k": k,
+                           "rerank_k": rk, "graph": f"Vamana R={R} beamWidth=100 (fixture built on the GPU, shared with our arm)"},
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                 "sample": f"{sample} queries per step, OpenMP one query per thread (CPU restatement of jVector 4.0.0-rc.9, not the JVM)"},
+                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------------------------------ our arm
+    flags = N.FLAG_LUT_F16 if args.adc_table == "fp16" else 0
+    t0 = time.time()
+    gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"], pq_codes=host["codes"],
+                     device=local_rank, flags=flags)
+    log(f"index resident in HBM: {gi.device_bytes() / 2**30:.2f} GiB ({time.time() - t0:.1f}s)")
+    dev_t = torch.device("cuda", local_rank)
+    base_doc = rank * n_local if shards else 0
+    out_doc = torch.empty(nq, k, dtype=torch.int32, device=dev_t)
+    out_score = torch.empty(nq, k, dtype=torch.float32, device=dev_t)
+    out_count = torch.empty(nq, dtype=torch.int32, device=dev_t)
+    stats = torch.empty(nq, 4, dtype=torch.int32, device=dev_t)
+    gt_doc = torch.empty(nq, k, dtype=torch.int32, device=dev_t)
+    gt_score = torch.empty(nq, k, dtype=torch.float32, device=dev_t)
+    gt_cnt = torch.empty(nq, dtype=torch.int32, device=dev_t)
+    t0 = time.time()
+    gi.exact_topk_dev(d_queries.data_ptr(), nq, k, gt_doc.data_ptr(), gt_score.data_ptr(), gt_cnt.data_ptr())  # ground truth (K5)
+    log(f"exact ground truth for {nq} queries in {time.time() - t0:.2f}s")
+
+    def merge_shards(docs_t, scores_t):
+        """K7: all-gather the per-GPU lists over NCCL and merge them on the device."""
+        gd = torch.empty(world, nq, k, dtype=torch.int32, device=dev_t)
+        gs = torch.empty(world, nq, k, dtype=torch.float32, device=dev_t)
+        dist.all_gather_into_tensor(gd, torch.where(docs_t >= 0, docs_t + base_doc, docs_t))
+        dist.all_gather_into_tensor(gs, scores_t)
+        md = torch.empty(nq, k, dtype=torch.int32, device=dev_t)
+        ms = torch.empty(nq, k, dtype=torch.float32, device=dev_t)
+        mc = torch.empty(nq, dtype=torch.int32, device=dev_t)
+        kms = C.c_float(0)
+        N.check(lib.jv_merge_topk_dev(local_rank, world, nq, k, gd.data_ptr(), gs.data_ptr(), md.data_ptr(), ms.data_ptr(), mc.data_ptr(),
+                                      C.addressof(kms)))
+        return md, ms, kms.value
+
+    def step_dev():
+        t = gi.search_dev(d_queries.data_ptr(), nq, k, rk, out_doc.data_ptr(), out_score.data_ptr(), out_count.data_ptr(), stats.data_ptr(),
+                          expand_width=args.expand_width)
+        if shards:
+            _, _, kms = merge_shards(out_doc, out_score)
+            t["merge_ms"] = kms
+        return t
+
+    def barrier():
+        torch.cuda.synchronize(local_rank)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local_rank)
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    timings = []
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            timings.append(step_dev())
+        barrier()
+        wall = time.perf_counter() - wall0
+    dev_ms = sum(t["total_ms"] + t.get("merge_ms", 0.0) for t in timings)
+    search_ms = sum(t["search_ms"] for t in timings) / args.steps
+    rerank_ms = sum(t["rerank_ms"] for t in timings) / args.steps
+    launches = sum(t["launches"] for t in timings) + (args.steps if shards else 0)
+
+    # recall against exact ground truth (per shard merged when sharded)
+    if shards:
+        found, _, _ = merge_shards(out_doc, out_score)
+        truth, _, _ = merge_shards(gt_doc, gt_score)
+        found, truth = found.cpu().numpy(), truth.cpu().numpy()
+    else:
+        found, truth = out_doc.cpu().numpy(), gt_doc.cpu().numpy()
+    rec = recall_at_k(found, truth)
+    st = stats.cpu().numpy()
+    adc_bytes, rr_bytes = algorithmic_bytes(st, m, R, dim)
+
+    # ---- e2e through the host-pointer entry point (what the Java codec calls): pinned host queries, host results
+    hq = torch.from_numpy(host["queries"]).pin_memory()
+    h_doc = torch.empty(nq, k, dtype=torch.int32).pin_memory()
+    h_score = torch.empty(nq, k, dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
+    h_stats = torch.empty(nq, 4, dtype=torch.int32).pin_memory()
+    p = gi._params(k, rk, 0.0, 0.0, None, 0, args.expand_width)
+
+    def step_e2e():
+        N.check(lib.jv_search_batch(gi.handle, hq.data_ptr(), nq, C.addressof(p), h_doc.data_ptr(), h_score.data_ptr(), h_cnt.data_ptr(),
+                                    h_stats.data_ptr(), None))
+        if shards:
+            md, _, _ = merge_shards(h_doc.to(dev_t, non_blocking=True), h_score.to(dev_t, non_blocking=True))
+            md.cpu()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_wall = time.perf_counter() - e0
+
+    # max over ranks
+    t_dev, t_wall, t_e2e = dev_ms / 1e3, wall, e2e_wall
+    if dist is not None:
+        tt = torch.tensor([t_dev, t_wall, t_e2e], dtype=torch.float64, device=dev_t)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_wall, t_e2e = tt.tolist()
+        rr = torch.tensor([rec], dtype=torch.float64, device=dev_t)
+        dist.all_reduce(rr, op=dist.ReduceOp.MIN)
+        rec = float(rr.item())
+    units = nq * args.steps * (1 if shards else world)  # queries answered by the whole job
+    value = units / t_dev
+    peak, peak_src = measured_peak()
+
+    line = {
+        "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "n": w["n"], "dim": dim, "similarity": "dot", "pq": f"{m}x256", "k": k, "rerank_k": rk,
+                   "graph": f"Vamana R={R} beamWidth=100", "query_batch": nq, "layout": args.layout if world > 1 else "single",
+                   "adc_table": args.adc_table, "expand_width": args.expand_width or 4,
+                   "l2": f"index working set {gi.device_bytes() / 2**30:.2f} GiB >> 126 MB L2, no flush needed"},
+        "recall_at_10": rec, "wall_ms_per_step": t_wall / args.steps * 1e3,
+        "visited_per_query": float(st[:, 0].mean()), "expanded_per_query": float(st[:, 1].mean()),
+        "visited_set_overflows": gi.visited_overflows(),
+        "roofline": {"bound": "hbm", "kernel": "search_kernel (K1 LUT + K2 beam search + ADC)",
+                     "achieved": adc_bytes / (search_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": adc_bytes / (search_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": adc_bytes, "kernel_ms": search_ms,
+                     "rerank": {"achieved": rr_bytes / (rerank_ms * 1e-3) / 1e9, "frac": rr_bytes / (rerank_ms * 1e-3) / 1e9 / peak,
+                                "algorithmic_bytes_per_launch": rr_bytes, "kernel_ms": rerank_ms}},
+        "pq_encode": {"kernel_ms": host["enc_ms"], "vectors_per_s": n_local / (host["enc_ms"] * 1e-3)},
+        "e2e": {"value": units / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+                "d2h_bytes_per_step": nq * k * 8 + nq * 4 + nq * 16},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+    }
+    # CPU baseline on rank 0, N=1 only: the oracle port on a bounded sample of the same workload
+    if rank == 0 and world == 1:
+        from oracle import oracle as O
+        ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
+                            pq_codes=host["codes"])
+        cores = O.num_threads()
+        t0 = time.time()
+        ora.search(host["queries"][:256], k, rk)
+        per_q = (time.time() - t0) / 256
+        sample = int(min(nq, max(512, 12.0 / per_q)))
+        t0 = time.time()
+        cd, _, _, cst = ora.search(host["queries"][:sample], k, rk)
+        el = time.time() - t0
+        line["cpu_baseline"] = {"value": sample / el, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} of the {nq} queries, one query per OpenMP thread, same index (CPU restatement, not the JVM)",
+                                "recall_at_10": recall_at_k(cd, truth[:sample]),
+                                "visited_per_query": float(cst[:, 0].mean())}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    gi.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

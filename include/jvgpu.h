@@ -134,7 +134,11 @@ typedef struct jv_search_params {
     int32_t rerank_k;      /* k * overQueryFactor, JVectorReader.java:168-169; must be >= k      */
     float threshold;       /* JVectorKnnCollector.getThreshold(), default 0                      */
     float rerank_floor;    /* JVectorKnnCollector.getRerankFloor(), default 0                    */
-    int32_t reserved;
+    int32_t expand_width;  /* traversal schedule (GPU-side knob, not part of the reference API):
+                            *   0  default: the fast kernel expands the 4 best unexpanded candidates per step
+                            *   1..8 explicit width; 1 = the reference's best-first order (up to exact score ties)
+                            *  -1  strict kernel: candidate heap + result heap exactly as GraphSearcher;
+                            *      always used when accept_bits or threshold > 0 are given                      */
     /* AcceptDocs by Lucene docId (FixedBitSet words: bit d = word d>>6, bit d&63), NULL = accept all.
      * accept_stride_words == 0: one bitset shared by the batch; else query i uses
      * accept_bits + i*accept_stride_words.  An ordinal is accepted iff ord_to_doc[ord] != -1 and its

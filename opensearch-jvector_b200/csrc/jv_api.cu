@@ -106,6 +106,7 @@ int32_t validate_params(const jv_index *ix, int32_t nq, const jv_search_params *
     JV_REQUIRE(p->rerank_k >= p->k, "rerankK must be >= topK (GraphSearcher contract)");
     JV_REQUIRE(p->rerank_k <= 4096, "rerank_k > 4096 not supported");
     JV_REQUIRE(p->accept_stride_words >= 0, "accept_stride_words must be >= 0");
+    JV_REQUIRE(p->expand_width >= -1 && p->expand_width <= 8, "expand_width must be in [-1, 8]");
     return JV_OK;
 }
 
@@ -287,6 +288,7 @@ static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, i
     a.d_stats = d_stats;
     a.entry_override = -1;
     a.n_limit = ix->n;
+    a.expand_width = p->expand_width;
     JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     JV_TRY(launch_search(ix, c, a, launches));
     JV_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));

@@ -582,6 +582,7 @@ static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t 
         a.d_stats = nullptr;
         a.entry_override = entry;
         a.n_limit = n;
+        a.expand_width = -1; // reference order exactly: the oracle's builder must reproduce this graph bit for bit
         JV_TRY(launch_search(&ix, &ctx, a, &launches));
         // 2. out-edges of the new nodes + edge keys
         int64_t ne_pad = 1;

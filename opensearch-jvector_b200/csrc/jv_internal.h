@@ -63,6 +63,7 @@ struct SearchLaunch {
     uint64_t *d_approx_keys; // [nq * rerank_k]
     int32_t *d_approx_count; // [nq]
     jv_query_stats *d_stats; // [nq]
+    int expand_width = 0;    // 0 = default (4), >= 1 explicit width (fast kernel); -1 = strict reference-order kernel
     int entry_override;      // -1 = index entry
     int64_t n_limit;         // nodes >= n_limit are ignored (graph builder); n for queries
 };

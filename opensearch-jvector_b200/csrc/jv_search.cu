@@ -17,143 +17,10 @@
 // (M bytes, coalesced 4-byte-per-lane loads) per NEW neighbour — the algorithmic bytes of SURVEY 8(d).
 #include "jv_internal.h"
 
-#include <cuda_fp16.h>
+#include "jv_search_common.cuh"
 
 namespace jv {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kMaxR = 128; // max graph degree supported by the per-step scratch
-constexpr uint32_t kEmpty = 0xffffffffu;
-
-struct SearchParams {
-    // index
-    const int32_t *adjacency;
-    const float *vectors;
-    const float *vec_norm;
-    const int32_t *ord_to_doc;
-    const uint8_t *codes;
-    const float *codebooks;
-    const float *gcent;
-    const int32_t *pq_size, *pq_off, *pq_cboff;
-    const float *node_norm;
-    int64_t n, n_limit;
-    int R, entry, sim, dim, M, K, code_stride, sub_uniform;
-    float mip_mul;
-    // batch
-    const float *queries;
-    const int32_t *query_ids; // optional: query i is vectors[query_ids[i]] (graph builder)
-    const uint64_t *accept;
-    int64_t accept_stride;
-    uint64_t *approx_keys;
-    int32_t *approx_count;
-    jv_query_stats *stats;
-    int *work_counter;
-    int *dbg;
-    int nq, L;
-    float threshold;
-    // shared-memory geometry
-    int cand_cap, hash_log2;
-};
-
-template <typename T> __device__ __forceinline__ float lut_get(const T *lut, int i);
-template <> __device__ __forceinline__ float lut_get<float>(const float *lut, int i) { return lut[i]; }
-template <> __device__ __forceinline__ float lut_get<__half>(const __half *lut, int i) { return __half2float(lut[i]); }
-template <typename T> __device__ __forceinline__ void lut_put(T *lut, int i, float v);
-template <> __device__ __forceinline__ void lut_put<float>(float *lut, int i, float v) { lut[i] = v; }
-template <> __device__ __forceinline__ void lut_put<__half>(__half *lut, int i, float v) { lut[i] = __float2half_rn(v); }
-
-// K1: lut[m][c] = q_m . C_m[c]  (DOT/COSINE/MIP)  or  ||(q-g)_m - C_m[c]||^2 (EUCLIDEAN); sequential fmaf over
-// the sub-vector, identical to oracle pq_build_lut (PQVectors.precomputedScoreFunctionFor, JVectorReader.java:354).
-template <typename LutT>
-__device__ __forceinline__ void build_lut(const SearchParams &p, const float *sq, LutT *lut, int tid, int nthreads) {
-    const int total = p.M * p.K;
-    const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
-    if (p.sub_uniform && (p.dim / p.M) == 4) {
-        // fast path (sub-dim 4: 768-d/192, the headline config): one float4 centroid per table entry, coalesced
-        const float4 *cb4 = reinterpret_cast<const float4 *>(p.codebooks);
-        for (int idx = tid; idx < total; idx += nthreads) {
-            const int m = idx / p.K;
-            float4 c = __ldg(cb4 + idx);
-            float q0 = sq[4 * m], q1 = sq[4 * m + 1], q2 = sq[4 * m + 2], q3 = sq[4 * m + 3];
-            float acc = 0.f;
-            if (l2) {
-                if (p.gcent) {
-                    q0 -= __ldg(p.gcent + 4 * m), q1 -= __ldg(p.gcent + 4 * m + 1);
-                    q2 -= __ldg(p.gcent + 4 * m + 2), q3 -= __ldg(p.gcent + 4 * m + 3);
-                }
-                float d0 = q0 - c.x, d1 = q1 - c.y, d2 = q2 - c.z, d3 = q3 - c.w;
-                acc = __fmaf_rn(d0, d0, acc);
-                acc = __fmaf_rn(d1, d1, acc);
-                acc = __fmaf_rn(d2, d2, acc);
-                acc = __fmaf_rn(d3, d3, acc);
-            } else {
-                acc = __fmaf_rn(q0, c.x, acc);
-                acc = __fmaf_rn(q1, c.y, acc);
-                acc = __fmaf_rn(q2, c.z, acc);
-                acc = __fmaf_rn(q3, c.w, acc);
-            }
-            lut_put(lut, idx, acc);
-        }
-        return;
-    }
-    for (int idx = tid; idx < total; idx += nthreads) {
-        const int m = idx / p.K, c = idx - m * p.K;
-        const int len = __ldg(p.pq_size + m), off = __ldg(p.pq_off + m);
-        const float *cv = p.codebooks + __ldg(p.pq_cboff + m) + (int64_t)c * len;
-        float acc = 0.f;
-        for (int j = 0; j < len; j++) {
-            float qv = sq[off + j];
-            if (l2) {
-                if (p.gcent) qv -= __ldg(p.gcent + off + j);
-                float d = qv - __ldg(cv + j);
-                acc = __fmaf_rn(d, d, acc);
-            } else {
-                acc = __fmaf_rn(qv, __ldg(cv + j), acc);
-            }
-        }
-        lut_put(lut, idx, acc);
-    }
-}
-
-// a4: decoder mapping of the summed partials (PQDecoder.*Decoder)
-__device__ __forceinline__ float adc_finish(int sim, float s, float node_norm, float qnorm) {
-    if (sim == JV_SIM_EUCLIDEAN) return __fdiv_rn(1.0f, __fadd_rn(1.0f, s));
-    if (sim == JV_SIM_COSINE) return __fmul_rn(__fadd_rn(1.0f, __fdiv_rn(s, __fsqrt_rn(__fmul_rn(node_norm, qnorm)))), 0.5f);
-    return __fmul_rn(__fadd_rn(1.0f, s), 0.5f);
-}
-
-// one warp sums the table entries selected by one code row (assembleAndSum).  Lane l owns the 4-byte code
-// words l, l+32, .. and adds their subspaces in increasing m; the 32 lane partials go through the halving
-// tree.  This is "order 1 / warp32" of oracle adc_sum, so fp32 traversals match the oracle bit for bit.
-template <typename LutT>
-__device__ __forceinline__ float adc_warp_sum(const LutT *lut, int K, int M, const uint8_t *row, int lane) {
-    const uint32_t *row32 = reinterpret_cast<const uint32_t *>(row);
-    const int nwords = (M + 3) >> 2;
-    float s = 0.f;
-    for (int w = lane; w < nwords; w += 32) {
-        const uint32_t cw = __ldg(row32 + w);
-        const int m0 = w * 4;
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-            if (m0 + b < M) s = __fadd_rn(s, lut_get(lut, (m0 + b) * K + (int)((cw >> (8 * b)) & 0xffu)));
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(JV_FULL_MASK, s, off));
-    return s;
-}
-
-__device__ __forceinline__ int lower_bound_u64(const uint64_t *a, int n, uint64_t key) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (a[mid] < key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
 
 template <bool PQ, typename LutT> __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -385,29 +252,6 @@ template <bool PQ, typename LutT> __global__ void __launch_bounds__(kThreads) se
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static void fill_params(const jv_index *ix, SearchParams &p) {
-    p.adjacency = ix->adjacency.as<int32_t>();
-    p.vectors = ix->vectors_dev;
-    p.vec_norm = ix->vec_norm.as<float>();
-    p.ord_to_doc = ix->ord_to_doc.as<int32_t>();
-    p.codes = ix->codes.as<uint8_t>();
-    p.codebooks = ix->codebooks.as<float>();
-    p.gcent = ix->gcent.as<float>();
-    p.pq_size = ix->pq_size.as<int32_t>();
-    p.pq_off = ix->pq_off.as<int32_t>();
-    p.pq_cboff = ix->pq_cboff.as<int32_t>();
-    p.node_norm = ix->node_norm.as<float>();
-    p.n = ix->n;
-    p.R = ix->R;
-    p.entry = ix->entry;
-    p.sim = ix->sim;
-    p.dim = ix->dim;
-    p.M = ix->pq.M;
-    p.K = ix->pq.K;
-    p.code_stride = ix->code_stride;
-    p.sub_uniform = ix->pq.uniform ? 1 : 0;
-    p.mip_mul = (ix->sim == JV_SIM_MIP && !ix->has_pq) ? 2.0f : 1.0f; // wrapExactScoreFunction, JVectorReader.java:220-239
-}
 
 template <bool PQ, typename LutT>
 static int32_t launch_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_t fixed_bytes, size_t smem_limit) {
@@ -469,6 +313,13 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     if (a.d_accept) C = C * 8 > 4096 ? (C > 4096 ? C : 4096) : C * 8;
     p.cand_cap = C;
     const bool f16 = (ix->flags & JV_INDEX_FLAG_LUT_F16) != 0;
+    // production path: unfiltered, threshold-free queries go to the fast kernel (jv_search_fast.cu); filters and
+    // range thresholds need the reference's two-queue semantics and stay on the strict kernel below.
+    if (a.expand_width >= 0 && a.d_accept == nullptr && !(a.threshold > 0.f)) {
+        const int32_t fs = launch_search_fast(ix, ctx, p, a.expand_width == 0 ? 4 : a.expand_width, f16);
+        if (fs == JV_OK && launches) *launches += 1;
+        return fs;
+    }
     size_t fixed = 0;
     if (ix->has_pq) fixed += (((size_t)p.M * p.K * (f16 ? 2 : 4)) + 15) & ~(size_t)15;
     fixed += (((size_t)p.dim * 4) + 15) & ~(size_t)15;

@@ -158,16 +158,17 @@ class GpuIndex:
         N.check(N.load().jv_index_debug_counter(self.handle, 0, C.addressof(b)))
         return int(b.value)
 
-    def _params(self, k, rerank_k, threshold, rerank_floor, accept_ptr, stride):
+    def _params(self, k, rerank_k, threshold, rerank_floor, accept_ptr, stride, expand_width=0):
         p = N.SearchParams()
         p.struct_size = C.sizeof(N.SearchParams)
         p.k, p.rerank_k, p.threshold, p.rerank_floor = k, rerank_k, threshold, rerank_floor
+        p.expand_width = expand_width
         p.accept_bits, p.accept_stride_words = accept_ptr, stride
         return p
 
     # -- K1+K2(+K4)+K3
     def search(self, queries, k: int, rerank_k: int, threshold: float = 0.0, rerank_floor: float = 0.0,
-               accept_bits=None) -> SearchResult:
+               accept_bits=None, expand_width: int = 0) -> SearchResult:
         q = _f32(np.atleast_2d(queries))
         if q.shape[1] != self.dim:
             raise ValueError(f"query dimension {q.shape[1]} != index dimension {self.dim}")
@@ -180,7 +181,7 @@ class GpuIndex:
         if accept_bits is not None:
             bits = np.ascontiguousarray(accept_bits, dtype=np.uint64)
             stride = 0 if bits.ndim == 1 else bits.shape[1]
-        p = self._params(k, rerank_k, threshold, rerank_floor, _ptr(bits), stride)
+        p = self._params(k, rerank_k, threshold, rerank_floor, _ptr(bits), stride, expand_width)
         t = N.BatchTiming()
         N.check(N.load().jv_search_batch(self.handle, _ptr(q), nq, C.addressof(p), _ptr(docs), _ptr(scores), _ptr(counts),
                                          _ptr(stats), C.addressof(t)))
@@ -189,9 +190,9 @@ class GpuIndex:
 
     def search_dev(self, d_queries_ptr: int, nq: int, k: int, rerank_k: int, d_out_doc: int, d_out_score: int,
                    d_out_count: int, d_stats: int = None, threshold: float = 0.0, rerank_floor: float = 0.0,
-                   d_accept_bits: int = None, accept_stride_words: int = 0) -> dict:
+                   d_accept_bits: int = None, accept_stride_words: int = 0, expand_width: int = 0) -> dict:
         """Device-pointer variant (inputs resident in HBM): returns the device-side timing."""
-        p = self._params(k, rerank_k, threshold, rerank_floor, d_accept_bits, accept_stride_words)
+        p = self._params(k, rerank_k, threshold, rerank_floor, d_accept_bits, accept_stride_words, expand_width)
         t = N.BatchTiming()
         N.check(N.load().jv_search_batch_dev(self.handle, d_queries_ptr, nq, C.addressof(p), d_out_doc, d_out_score,
                                              d_out_count, d_stats, C.addressof(t)))

@@ -36,7 +36,7 @@ class BatchTiming(C.Structure):
 
 class SearchParams(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("k", C.c_int32), ("rerank_k", C.c_int32), ("threshold", C.c_float),
-                ("rerank_floor", C.c_float), ("reserved", C.c_int32), ("accept_bits", C.c_void_p),
+                ("rerank_floor", C.c_float), ("expand_width", C.c_int32), ("accept_bits", C.c_void_p),
                 ("accept_stride_words", C.c_int64)]
 
 
