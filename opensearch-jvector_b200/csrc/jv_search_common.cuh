@@ -40,7 +40,7 @@ struct SearchParams {
     // shared-memory geometry
     int cand_cap, hash_log2;
     // fast kernel
-    int expand_width, list_cap;
+    int expand_width, list_cap, adc_lanes_log2;
 };
 
 template <typename T> __device__ __forceinline__ float lut_get(const T *lut, int i);
@@ -101,10 +101,64 @@ __device__ __forceinline__ void build_lut_uniform(const SearchParams &p, const f
     }
 }
 
+// K == 256 with a 256-thread CTA (every production config: K = min(256, n)): thread c owns centroid c of every
+// subspace, so there is no index arithmetic at all — per entry one coalesced vector load (16 B * 32 lanes), one
+// broadcast read of q_m from shared memory, S FMAs and one store.  Same fmaf order as build_lut_uniform.
+template <typename LutT, int S>
+__device__ __forceinline__ void build_lut_k256(const SearchParams &p, const float *sq, LutT *lut, int tid) {
+    const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
+    constexpr int U = S <= 4 ? 8 : 4;
+    constexpr int V = S == 2 ? 2 : 4;
+    constexpr int NV = S / V;
+    const int M = p.M;
+    for (int m0 = 0; m0 < M; m0 += U) {
+        float cc[U][S];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u;
+            const size_t e = ((size_t)m * 256 + tid) * NV;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                if (V == 2) {
+                    const float2 t = m < M ? __ldg(reinterpret_cast<const float2 *>(p.codebooks) + e + v) : make_float2(0.f, 0.f);
+                    cc[u][v * V] = t.x, cc[u][v * V + 1] = t.y;
+                } else {
+                    const float4 t = m < M ? __ldg(reinterpret_cast<const float4 *>(p.codebooks) + e + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cc[u][v * V] = t.x, cc[u][v * V + 1] = t.y, cc[u][v * V + 2] = t.z, cc[u][v * V + 3] = t.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u;
+            if (m >= M) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                float qv = sq[S * m + j]; // warp-wide broadcast
+                if (l2) {
+                    if (p.gcent) qv -= __ldg(p.gcent + S * m + j);
+                    const float d = qv - cc[u][j];
+                    acc = __fmaf_rn(d, d, acc);
+                } else {
+                    acc = __fmaf_rn(qv, cc[u][j], acc);
+                }
+            }
+            lut_put(lut, m * 256 + tid, acc);
+        }
+    }
+}
+
 template <typename LutT>
 __device__ __forceinline__ void build_lut(const SearchParams &p, const float *sq, LutT *lut, int tid, int nthreads) {
     const int total = p.M * p.K;
     const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
+    if (p.sub_uniform && p.K == 256 && nthreads == 256) {
+        const int S = p.dim / p.M;
+        if (S == 4) return build_lut_k256<LutT, 4>(p, sq, lut, tid);
+        if (S == 2) return build_lut_k256<LutT, 2>(p, sq, lut, tid);
+        if (S == 8) return build_lut_k256<LutT, 8>(p, sq, lut, tid);
+    }
     if (p.sub_uniform) {
         const int S = p.dim / p.M;
         if (S == 4) return build_lut_uniform<LutT, 4>(p, sq, lut, tid, nthreads);

@@ -7,12 +7,15 @@
 //     list explores exactly the same nodes for expand_width = 1 (up to exact score ties).
 //   * expand_width E > 1 expands the E best unexpanded entries per step (a superset exploration: recall >= the
 //     strict order's, fewer dependent round trips to HBM, E*R neighbour rows in flight at once).
-//   * the visited set is a small direct-mapped filter in shared memory: it only avoids re-scoring.  Correctness does
-//     not depend on it — a re-scored node is either already in the list (dropped as a duplicate at merge time) or
-//     scores below the list's worst entry (dropped again) — so it never overflows and needs no atomics.
+//   * the visited set is a small 2-way set-associative filter of 15-bit tags in shared memory.  It only avoids
+//     re-scoring: a re-scored node is either already in the list (dropped as a duplicate at merge time) or scores
+//     below the list's worst entry (dropped again), so evictions cost work, never correctness, and it cannot
+//     overflow.  (set, tag) is a bijection of the ordinal, so there are no false positives.
 //   * the ADC table may be held in fp16 (JV_INDEX_FLAG_LUT_F16): 96 KB instead of 192 KB at M=192,K=256, which lets two
 //     CTAs share an SM.  ADC scores only steer the traversal; returned scores come from the exact rerank (K3).
-// Shared memory per CTA: lut[M*K] | q[dim] | list[2][L] | surv[256] | flags | ids[256] | sel[8] | filter[H].
+//   * ADC sums use `adc_lanes` lanes per code row (<= 4 code words per lane) so small-M configurations keep all 32
+//     lanes busy; the summation order is "order = adc_lanes" of oracle adc_sum.
+// Shared memory per CTA: lut[M*K] | q[dim] | list[2][L] | surv[256] | ids[256] | filter[H] | flags[256].
 #include "jv_search_common.cuh"
 
 namespace jv {
@@ -42,11 +45,30 @@ __device__ __forceinline__ int count_better(const uint64_t *list, int n, uint64_
     return lo;
 }
 
-template <bool PQ, typename LutT>
+// visited filter: returns true when `nb` was NOT present (and records it).  2 tags of 15 bits + valid bit per word.
+__device__ __forceinline__ bool filter_insert(uint32_t *filter, int set_bits, bool tagged, int32_t nb) {
+    if (tagged) {
+        const uint32_t x = ((uint32_t)nb * 0x9E3779B1u) & ((1u << (set_bits + 15)) - 1u); // bijection on set_bits+15 bit ordinals
+        const uint32_t set = x >> 15, tag = (x & 0x7fffu) | 0x8000u;
+        uint32_t old = filter[set];
+        for (;;) {
+            if ((old & 0xffffu) == tag || (old >> 16) == tag) return false;
+            const uint32_t seen = atomicCAS(&filter[set], old, (old << 16) | tag);
+            if (seen == old) return true;
+            old = seen;
+        }
+    } else { // huge shards (ordinal does not fit set+tag): direct-mapped full ordinals
+        const uint32_t h = ((uint32_t)nb * 2654435761u) >> (32 - set_bits);
+        return atomicExch(&filter[h], (uint32_t)nb) != (uint32_t)nb;
+    }
+}
+
+template <bool PQ, typename LutT, bool K256>
 __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.L, E = p.expand_width, H = 1 << p.hash_log2;
+    const int K = K256 ? 256 : p.K;
 
     unsigned char *sp = smem_raw;
     LutT *lut = reinterpret_cast<LutT *>(sp);
@@ -65,11 +87,15 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     sp += (size_t)H * 4;
     uint8_t *sflag = reinterpret_cast<uint8_t *>(sp);
 
-    __shared__ int s_query, s_nn, s_ns, s_warp_cnt[kFWarps], s_sel[kMaxE];
+    __shared__ int s_query, s_nn, s_ns, s_nsel, s_sel[kMaxE];
     __shared__ float s_qnorm;
 
     const bool vec4 = (p.dim & 3) == 0 && (p.query_ids != nullptr || (reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
-    const int hshift = 32 - p.hash_log2;
+    const bool tagged = p.n_limit <= ((int64_t)1 << (p.hash_log2 + 15));
+    // ADC lane geometry
+    const int lpn_log2 = p.adc_lanes_log2, LPN = 1 << lpn_log2, G = 32 >> lpn_log2;
+    const int sub = lane >> lpn_log2, sl = lane & (LPN - 1);
+    const int nwords = p.M >> 2;
 
     for (;;) {
         __syncthreads();
@@ -83,7 +109,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         if (qi >= p.nq) break;
         const float *gq = p.query_ids ? p.vectors + (int64_t)__ldg(p.query_ids + qi) * p.dim : p.queries + (int64_t)qi * p.dim;
         for (int i = tid; i < p.dim; i += kFThreads) sq[i] = __ldg(gq + i);
-        for (int i = tid; i < H; i += kFThreads) filter[i] = kEmpty;
+        for (int i = tid; i < H; i += kFThreads) filter[i] = tagged ? 0u : kEmpty;
         __syncthreads();
         if (PQ) build_lut<LutT>(p, sq, lut, tid, kFThreads);
         if (warp == 0) {
@@ -93,27 +119,61 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         __syncthreads();
         const float qnorm = s_qnorm;
 
-        auto score_node = [&](int32_t node) -> float { // one warp; result valid in all lanes
-            if (PQ) {
-                const float s = adc_warp_sum<LutT>(lut, p.K, p.M, p.codes + (int64_t)node * p.code_stride, lane);
-                const float nn = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + node) : 0.f;
-                return adc_finish(p.sim, s, nn, qnorm);
-            } else {
-                const float *x = p.vectors + (int64_t)node * p.dim;
-                const float raw = p.sim == JV_SIM_EUCLIDEAN ? jv_warp_reduce_pair<true>(sq, x, p.dim, lane, vec4)
-                                                            : jv_warp_reduce_pair<false>(sq, x, p.dim, lane, vec4);
-                const float xn = p.sim == JV_SIM_COSINE ? __ldg(p.vec_norm + node) : 0.f;
-                return jv_finish_score(p.sim, raw, qnorm, xn) * p.mip_mul;
+        // ADC sum of one code row by a group of LPN lanes (valid in the group's lane 0 after the reduction)
+        auto adc_group = [&](int32_t nb) -> float {
+            float s = 0.f;
+            uint32_t cw[4] = {0u, 0u, 0u, 0u};
+            if (nb >= 0) {
+                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nb * p.code_stride);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int w = sl + (t << lpn_log2);
+                    if (w < nwords) cw[t] = __ldg(row32 + w);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int w = sl + (t << lpn_log2);
+                    if (w < nwords) {
+                        const LutT *lw = lut + (size_t)w * 4 * K;
+                        s = __fadd_rn(s, lut_get(lw, (int)(cw[t] & 0xffu)));
+                        s = __fadd_rn(s, lut_get(lw, K + (int)((cw[t] >> 8) & 0xffu)));
+                        s = __fadd_rn(s, lut_get(lw, 2 * K + (int)((cw[t] >> 16) & 0xffu)));
+                        s = __fadd_rn(s, lut_get(lw, 3 * K + (int)(cw[t] >> 24)));
+                    }
+                }
+                for (int w = sl + (4 << lpn_log2); w < nwords; w += LPN) { // M > 512 only
+                    const uint32_t c = __ldg(row32 + w);
+                    const LutT *lw = lut + (size_t)w * 4 * K;
+                    s = __fadd_rn(s, lut_get(lw, (int)(c & 0xffu)));
+                    s = __fadd_rn(s, lut_get(lw, K + (int)((c >> 8) & 0xffu)));
+                    s = __fadd_rn(s, lut_get(lw, 2 * K + (int)((c >> 16) & 0xffu)));
+                    s = __fadd_rn(s, lut_get(lw, 3 * K + (int)(c >> 24)));
+                }
             }
+            for (int off = LPN >> 1; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(JV_FULL_MASK, s, off));
+            return s;
+        };
+        auto exact_warp = [&](int32_t node) -> float { // one warp; result valid in all lanes
+            const float *x = p.vectors + (int64_t)node * p.dim;
+            const float raw = p.sim == JV_SIM_EUCLIDEAN ? jv_warp_reduce_pair<true>(sq, x, p.dim, lane, vec4)
+                                                        : jv_warp_reduce_pair<false>(sq, x, p.dim, lane, vec4);
+            const float xn = p.sim == JV_SIM_COSINE ? __ldg(p.vec_norm + node) : 0.f;
+            return jv_finish_score(p.sim, raw, qnorm, xn) * p.mip_mul;
         };
 
         int n = 0, cur = 0, visited = 0, expanded = 0;
         if (p.entry >= 0 && p.entry < p.n_limit) {
             if (warp == 0) {
-                const float s = score_node(p.entry);
+                float s;
+                if (PQ) {
+                    s = adc_group(sub == 0 ? p.entry : -1);
+                    s = adc_finish(p.sim, s, p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + p.entry) : 0.f, qnorm);
+                } else {
+                    s = exact_warp(p.entry);
+                }
                 if (lane == 0) {
                     list0[0] = fkey_make(s, p.entry);
-                    filter[((uint32_t)p.entry * 2654435761u) >> hshift] = (uint32_t)p.entry;
+                    filter_insert(filter, p.hash_log2, tagged, p.entry);
                 }
             }
             n = 1;
@@ -123,47 +183,35 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
 
         while (n > 0) {
             uint64_t *list = cur ? list1 : list0, *out = cur ? list0 : list1;
-            // ---- (a) pick the E best unexpanded entries (list order = best first) and mark them expanded
-            int nsel = 0;
-            for (int c0 = 0; c0 < n && nsel < E; c0 += kFThreads) {
-                const int i = c0 + tid;
-                const bool un = i < n && (list[i] & 1ull);
-                const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
-                if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
-                __syncthreads();
-                int before = nsel, total = nsel;
-                for (int w = 0; w < kFWarps; w++) {
-                    const int c = s_warp_cnt[w];
-                    if (w < warp) before += c;
-                    total += c;
+            // ---- (a) warp 0 picks the E best unexpanded entries (list order = best first) and marks them expanded
+            if (warp == 0) {
+                int found = 0;
+                for (int c0 = 0; c0 < n && found < E; c0 += 32) {
+                    const int i = c0 + lane;
+                    const bool un = i < n && (list[i] & 1ull);
+                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                    if (un && rank < E) {
+                        s_sel[rank] = fkey_node(list[i]);
+                        list[i] &= ~1ull;
+                    }
+                    found += __popc(ballot);
                 }
-                const int rank = before + __popc(ballot & ((1u << lane) - 1u));
-                if (un && rank < E) {
-                    s_sel[rank] = fkey_node(list[i]);
-                    list[i] &= ~1ull;
-                }
-                nsel = total < E ? total : E;
-                __syncthreads();
+                if (lane == 0) s_nsel = found < E ? found : E;
             }
+            __syncthreads();
+            const int nsel = s_nsel;
             if (nsel == 0) break;
 
             // ---- (b) neighbour rows of the selected nodes -> visited filter -> compacted id list
             {
                 const int R = p.R;
-                const int t = tid;
                 int32_t nb = -1;
-                if (t < nsel * R) {
-                    const int ci = t / R, j = t - ci * R;
+                if (tid < nsel * R) {
+                    const int ci = tid / R, j = tid - ci * R;
                     nb = __ldg(p.adjacency + (int64_t)s_sel[ci] * R + j);
                 }
-                bool fresh = false;
-                if (nb >= 0 && nb < p.n_limit) {
-                    const uint32_t h = ((uint32_t)nb * 2654435761u) >> hshift;
-                    if (filter[h] != (uint32_t)nb) {
-                        filter[h] = (uint32_t)nb;
-                        fresh = true;
-                    }
-                }
+                const bool fresh = nb >= 0 && nb < p.n_limit && filter_insert(filter, p.hash_log2, tagged, nb);
                 const uint32_t ballot = __ballot_sync(JV_FULL_MASK, fresh);
                 int base = 0;
                 if (lane == 0 && ballot) base = atomicAdd(&s_nn, __popc(ballot));
@@ -175,59 +223,24 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             expanded += nsel;
             visited += nn;
 
-            // ---- (c) score the gathered neighbours, one warp each; keep those that can enter the list
+            // ---- (c) score the gathered neighbours; keep those that can enter the list
             {
                 const uint64_t worst = n >= L ? (list[L - 1] >> 1) : 0ull;
                 if (PQ) {
-                    // 4 code rows per warp in flight: all loads are issued before the first table lookup
-                    const int nwords = (p.M + 3) >> 2;
-                    for (int i0 = warp; i0 < nn; i0 += kFWarps * 4) {
-                        uint32_t cw[4][2];
-                        int32_t nbs[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int i = i0 + u * kFWarps;
-                            nbs[u] = i < nn ? nb_ids[i] : -1;
-                            cw[u][0] = cw[u][1] = 0u;
-                            if (nbs[u] >= 0) {
-                                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nbs[u] * p.code_stride);
-                                if (lane < nwords) cw[u][0] = __ldg(row32 + lane);
-                                if (lane + 32 < nwords) cw[u][1] = __ldg(row32 + lane + 32);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            if (nbs[u] < 0) continue; // warp-uniform
-                            float s = 0.f;
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                const int m0 = (lane + 32 * h) * 4;
-#pragma unroll
-                                for (int b = 0; b < 4; b++)
-                                    if (m0 + b < p.M)
-                                        s = __fadd_rn(s, lut_get(lut, (m0 + b) * p.K + (int)((cw[u][h] >> (8 * b)) & 0xffu)));
-                            }
-                            if (nwords > 64) { // very wide codes (M > 256): remaining words straight from global
-                                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nbs[u] * p.code_stride);
-                                for (int w = lane + 64; w < nwords; w += 32) {
-                                    const uint32_t c = __ldg(row32 + w);
-                                    for (int b = 0; b < 4; b++)
-                                        if (w * 4 + b < p.M) s = __fadd_rn(s, lut_get(lut, (w * 4 + b) * p.K + (int)((c >> (8 * b)) & 0xffu)));
-                                }
-                            }
-#pragma unroll
-                            for (int off = 16; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(JV_FULL_MASK, s, off));
-                            if (lane == 0) {
-                                const float nnorm = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + nbs[u]) : 0.f;
-                                const uint64_t k = fkey_make(adc_finish(p.sim, s, nnorm, qnorm), nbs[u]);
-                                if ((k >> 1) > worst) surv[atomicAdd(&s_ns, 1)] = k;
-                            }
+                    for (int i0 = warp * G; i0 < nn; i0 += kFWarps * G) {
+                        const int i = i0 + sub;
+                        const int32_t nb = i < nn ? nb_ids[i] : -1;
+                        const float s = adc_group(nb);
+                        if (sl == 0 && nb >= 0) {
+                            const float nnorm = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + nb) : 0.f;
+                            const uint64_t k = fkey_make(adc_finish(p.sim, s, nnorm, qnorm), nb);
+                            if ((k >> 1) > worst) surv[atomicAdd(&s_ns, 1)] = k;
                         }
                     }
                 } else {
                     for (int i = warp; i < nn; i += kFWarps) {
                         const int32_t nb = nb_ids[i];
-                        const float s = score_node(nb);
+                        const float s = exact_warp(nb);
                         if (lane == 0) {
                             const uint64_t k = fkey_make(s, nb);
                             if ((k >> 1) > worst) surv[atomicAdd(&s_ns, 1)] = k;
@@ -238,15 +251,16 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             __syncthreads();
             const int ns = s_ns;
 
-            // ---- (d) merge survivors into the list (dedupe against the list and among themselves)
+            // ---- (d) merge survivors into the list (dedupe against the list; survivors are distinct: the filter
+            //          insertion is atomic, so a node enters nb_ids at most once per step)
             bool valid = false;
             uint64_t mine = 0ull;
+            int mypos = 0;
             if (tid < ns) {
                 mine = surv[tid];
                 const uint64_t a = mine >> 1;
-                const int pos = count_better(list, n, a);
-                valid = !(pos < n && (list[pos] >> 1) == a);
-                for (int j = 0; j < tid && valid; j++) valid = (surv[j] >> 1) != a;
+                mypos = count_better(list, n, a);
+                valid = !(mypos < n && (list[mypos] >> 1) == a);
                 sflag[tid] = valid ? 1 : 0;
             }
             __syncthreads();
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             }
             if (valid) {
                 const uint64_t a = mine >> 1;
-                int pos = count_better(list, n, a);
+                int pos = mypos;
                 for (int j = 0; j < ns; j++) pos += (sflag[j] && (surv[j] >> 1) > a) ? 1 : 0;
                 if (pos < L) out[pos] = mine;
             }
@@ -292,21 +306,21 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     }
 }
 
-template <bool PQ, typename LutT>
+template <bool PQ, typename LutT, bool K256>
 static int32_t launch_fast_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_t fixed) {
-    auto kern = fast_search_kernel<PQ, LutT>;
+    auto kern = fast_search_kernel<PQ, LutT, K256>;
     // shared memory per SM is 228 KB; every resident CTA also reserves 1 KB.  Take the highest occupancy that still
-    // leaves a >= 2048-slot visited filter, then give the filter what is left (capped: it only has to cover ~2x the
-    // nodes a query touches).
+    // leaves a >= 2048-word visited filter (4096 tags), then give the filter what is left, capped at ~2x the nodes a
+    // query touches.
     const size_t sm_total = 228 * 1024;
-    int64_t want = (int64_t)2 * p.L * p.R;
+    int64_t want = (int64_t)p.L * p.R; // words; 2 tags each
     if (want < 2048) want = 2048;
     int best_occ = 0, best_log2 = 0;
     for (int occ = 8; occ >= 1; occ--) {
         const int64_t per = (int64_t)(sm_total / occ) - 1024 - 256 - (int64_t)fixed;
         if (per < 2048 * 4) continue;
         int lg = 11;
-        while (lg < 16 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
+        while (lg < 15 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
         best_occ = occ;
         best_log2 = lg;
         break;
@@ -332,18 +346,37 @@ static int32_t launch_fast_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, 
     return JV_OK;
 }
 
+// lanes per code row: the smallest power of two that leaves <= 4 code words (16 subspaces) per lane
+int adc_lanes_for(int M) {
+    const int nwords = (M + 3) / 4;
+    int lanes = 1;
+    while (lanes < 32 && lanes * 4 < nwords) lanes <<= 1;
+    return lanes;
+}
+
 int32_t launch_search_fast(jv_index *ix, SearchCtx *ctx, SearchParams &p, int expand_width, bool f16) {
     int E = expand_width < 1 ? 1 : (expand_width > kMaxE ? kMaxE : expand_width);
     if (E * p.R > kMaxNew) E = kMaxNew / p.R;
     if (E < 1) E = 1;
     p.expand_width = E;
     p.list_cap = p.L;
+    int lanes = ix->has_pq ? adc_lanes_for(p.M) : 32, lg = 0;
+    while ((1 << lg) < lanes) lg++;
+    p.adc_lanes_log2 = lg;
     size_t fixed = 0;
     if (ix->has_pq) fixed += (((size_t)p.M * p.K * (f16 ? 2 : 4)) + 15) & ~(size_t)15;
     fixed += (((size_t)p.dim * 4) + 15) & ~(size_t)15;
     fixed += (size_t)p.L * 16 + (size_t)kMaxNew * (8 + 4 + 1);
-    if (ix->has_pq) return f16 ? launch_fast_typed<true, __half>(ix, ctx, p, fixed) : launch_fast_typed<true, float>(ix, ctx, p, fixed);
-    return launch_fast_typed<false, float>(ix, ctx, p, fixed);
+    if (ix->has_pq) {
+        if ((p.M & 3) != 0) {
+            set_error("fast search kernel needs M %% 4 == 0 (M=%d)", p.M);
+            return JV_ERR_UNSUPPORTED;
+        }
+        const bool k256 = p.K == 256;
+        if (f16) return k256 ? launch_fast_typed<true, __half, true>(ix, ctx, p, fixed) : launch_fast_typed<true, __half, false>(ix, ctx, p, fixed);
+        return k256 ? launch_fast_typed<true, float, true>(ix, ctx, p, fixed) : launch_fast_typed<true, float, false>(ix, ctx, p, fixed);
+    }
+    return launch_fast_typed<false, float, false>(ix, ctx, p, fixed);
 }
 
 }  // namespace jv

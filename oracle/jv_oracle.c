@@ -341,21 +341,23 @@ static float pq_node_norm(const pq_shape *s, const float *codebooks, const uint8
  * observable in the reference beyond rounding (Panama lane-wise partials, host dependent).  Two
  * fixed orders are provided:
  *   order 0  four interleaved sequential accumulators (scalar-loop flavour)
- *   order 1  "warp32": 32 lane partials, lane l sums subspaces 4w..4w+3 for code words w = l, l+32, ..
- *            in increasing m, then the halving tree of reduce128 — the order the sm_100a kernel uses,
+ *   order N  (N = 1,2,4,..,32 lanes): lane l sums subspaces 4w..4w+3 for code words w = l, l+N, ..
+ *            in increasing m, then a halving tree over the N lanes.  N = 32 is the strict sm_100a kernel,
+ *            N = adc_lanes(M) the fast kernel (<= 4 code words per lane),
  *            so fp32 traversals can be compared bit for bit. */
 static inline float adc_sum(const float *lut, int M, int K, const uint8_t *code, int order) {
-    if (order == 1) {
+    if (order >= 1) { /* order = number of lanes (power of two <= 32) sharing one code row */
         float v[32];
+        const int lanes = order > 32 ? 32 : order;
         const int nwords = (M + 3) >> 2;
-        for (int l = 0; l < 32; l++) {
+        for (int l = 0; l < lanes; l++) {
             float s = 0.f;
-            for (int w = l; w < nwords; w += 32)
+            for (int w = l; w < nwords; w += lanes)
                 for (int b = 0; b < 4; b++)
                     if (4 * w + b < M) s += lut[(4 * w + b) * K + code[4 * w + b]];
             v[l] = s;
         }
-        for (int off = 16; off >= 1; off >>= 1)
+        for (int off = lanes >> 1; off >= 1; off >>= 1)
             for (int j = 0; j < off; j++) v[j] = v[j] + v[j + off];
         return v[0];
     }

@@ -35,10 +35,18 @@ def fx_exact():
     return make_fixture(O.SIM_COSINE, base, q, max_degree=16)
 
 
+def adc_lanes(m: int) -> int:
+    """lanes per code row in the fast kernel (jv_search_fast.cu adc_lanes_for): <= 4 code words per lane."""
+    nwords, lanes = (m + 3) // 4, 1
+    while lanes < 32 and lanes * 4 < nwords:
+        lanes *= 2
+    return lanes
+
+
 @pytest.mark.parametrize("name", ["fx_dot", "fx_l2", "fx_cos8", "fx_exact"])
 def test_width1_is_reference_order(jv, request, name):
     fx = request.getfixturevalue(name)
-    ora = fx.oracle_index(adc_order=1)
+    ora = fx.oracle_index(adc_order=adc_lanes(fx.pq_m) if fx.pq_m else 0)
     with fx.gpu_index(jv) as gi:
         for k, rk in ((10, 50), (1, 1), (20, 200)):
             r = gi.search(fx.queries, k, rk, expand_width=1)
@@ -49,7 +57,7 @@ def test_width1_is_reference_order(jv, request, name):
             np.testing.assert_array_equal(r.stats[:, 1], wst[:, 1])   # expansions
             np.testing.assert_array_equal(r.stats[:, 3], wst[:, 3])   # reranked
             assert (r.stats[:, 0] >= wst[:, 0]).all()                 # re-scored nodes count as visits
-            assert r.stats[:, 0].mean() <= 1.3 * wst[:, 0].mean()
+            assert r.stats[:, 0].mean() <= 1.15 * wst[:, 0].mean() + 4  # the 2-way tagged filter rarely evicts
 
 
 @pytest.mark.parametrize("name", ["fx_dot", "fx_l2", "fx_cos8", "fx_exact"])
@@ -108,7 +116,7 @@ def test_large_rerank_k_and_small_graph(jv, fx_l2):
 
 def test_filtered_and_threshold_queries_use_strict_kernel(jv, fx_l2):
     fx = fx_l2
-    ora = fx.oracle_index(adc_order=1)
+    ora = fx.oracle_index(adc_order=32)
     rng = np.random.default_rng(1)
     bits = O.make_accept_bits(rng.random(fx.base.shape[0]) < 0.3)
     with fx.gpu_index(jv) as gi:

@@ -95,7 +95,7 @@ def test_lut_and_adc_bit_exact(jv, request, name):
         np.testing.assert_array_equal(lut, want)
         nodes = np.tile(np.arange(0, 400, dtype=np.int32), (8, 1))
         got = gi.adc_scores(q, nodes)
-        ora = fx.oracle_index(adc_order=1).adc_scores(q, nodes)
+        ora = fx.oracle_index(adc_order=32).adc_scores(q, nodes)
         np.testing.assert_array_equal(got, ora)
         np.testing.assert_allclose(got, fx.oracle_index(adc_order=0).adc_scores(q, nodes), rtol=SCORE_RTOL)
 
@@ -192,7 +192,7 @@ def test_search_exact_other_similarities(jv, sim):
 @pytest.mark.parametrize("name", ["fx_pq_dot", "fx_pq_l2", "fx_pq_cos"])
 def test_search_pq_identical_to_oracle(jv, request, name):
     fx = request.getfixturevalue(name)
-    ora = fx.oracle_index(adc_order=1)
+    ora = fx.oracle_index(adc_order=32)
     with fx.gpu_index(jv) as gi:
         for k, rk in ((10, 50), (5, 5), (20, 200)):
             r = gi.search(fx.queries, k, rk, expand_width=STRICT)
@@ -226,7 +226,7 @@ def test_search_pq_fp16_table_recall_parity(jv, request, name):
 
 def test_search_pq_filter_threshold_floor(jv, fx_pq_l2):
     fx = fx_pq_l2
-    ora = fx.oracle_index(adc_order=1)
+    ora = fx.oracle_index(adc_order=32)
     rng = np.random.default_rng(77)
     mask = rng.random(fx.base.shape[0]) < 0.10  # 10 % selectivity (config 4 flavour)
     bits = O.make_accept_bits(mask)
@@ -256,7 +256,7 @@ def test_search_ordinal_map_deleted_and_batch_of_one(jv):
     o2d = rng.permutation(4000)[:2500].astype(np.int32)
     o2d[rng.random(2500) < 0.05] = -1
     fx = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=16, pq_m=16, ord_to_doc=o2d, max_doc=4000)
-    ora = fx.oracle_index(adc_order=1)
+    ora = fx.oracle_index(adc_order=32)
     with fx.gpu_index(jv) as gi:
         r = gi.search(q, 10, 50, expand_width=STRICT)
         wd, ws, wc, wst = ora.search(q, 10, 50)
@@ -303,7 +303,7 @@ def test_concurrent_queries_share_one_index(jv, fx_pq_dot):
     """KNNJVectorTests.java:982-1028: 10 threads x 100 queries on one reader."""
     import threading
     fx = fx_pq_dot
-    want = fx.oracle_index(adc_order=1).search(fx.queries, 10, 50)[0]
+    want = fx.oracle_index(adc_order=32).search(fx.queries, 10, 50)[0]
     errors = []
     with fx.gpu_index(jv) as gi:
         def worker(t):

@@ -212,7 +212,7 @@ def test_pq_lut_and_adc_consistent():
         ix = fx.oracle_index()
         nodes = np.tile(np.arange(50, dtype=np.int32), (3, 1))
         adc = ix.adc_scores(q, nodes)
-        adc1 = fx.oracle_index(adc_order=1).adc_scores(q, nodes)
+        adc1 = fx.oracle_index(adc_order=32).adc_scores(q, nodes)
         np.testing.assert_allclose(adc, adc1, rtol=1e-5)
         # ADC score == exact score against the decoded vector
         sizes, offs = O.pq_subspaces(24, 6)
