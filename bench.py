@@ -34,8 +34,9 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
     # name: n, dim, sim, pq_m, R, k, overquery, nq
-    "cfg2-1Mx768-dot-pq192": dict(n=1_000_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=128),
-    "cfg2-small-100kx768": dict(n=100_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=128),
+    # latent = intrinsic dimension of the synthetic embeddings (text-embedding models measure ~30-60)
+    "cfg2-1Mx768-dot-pq192": dict(n=1_000_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64),
+    "cfg2-small-100kx768": dict(n=100_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64),
     "tiny-20kx128": dict(n=20_000, dim=128, sim=1, pq_m=32, R=16, k=10, over=5, nq=2_000, latent=32),
 }
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -173,6 +174,8 @@ def main():
     ap.add_argument("--adc-table", default="fp16", choices=["fp16", "fp32"],
                     help="precision of the per-query ADC table in shared memory (steering scores only; final scores are exact)")
     ap.add_argument("--expand-width", type=int, default=0, help="0 = library default (4); 1..8; -1 = strict reference-order kernel")
+    ap.add_argument("--overquery", type=int, default=0, help="override the workload's overquery factor (rerankK = k * overquery)")
+    ap.add_argument("--latent", type=int, default=0, help="override the intrinsic dimension of the synthetic data")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
@@ -202,6 +205,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = dict(WORKLOADS[args.workload])
+    if args.overquery:
+        w["over"] = args.overquery
+    if args.latent:
+        w["latent"] = args.latent
     k, rk, nq, dim, m, R = w["k"], w["k"] * w["over"], w["nq"], w["dim"], w["pq_m"], w["R"]
     shards = args.layout == "shards" and world > 1
     n_local = w["n"] // world if shards else w["n"]

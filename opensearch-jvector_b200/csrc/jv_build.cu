@@ -398,6 +398,10 @@ backlink_kernel(const BuildParams p, int mode, int64_t done, const uint64_t *__r
             u = (int32_t)item;
         }
         const int d0 = p.deg[u];
+        // every thread must have read the old degree before thread 0 publishes the new one at the end of the
+        // (barrier-free) append path below — without this a late warp sees the updated degree, computes a larger
+        // total and takes the prune branch on its own (found by compute-sanitizer synccheck)
+        __syncthreads();
         if (mode == 1 && d0 <= p.R) continue;
         int total = d0 + m;
         if (total > kAppendCap) total = kAppendCap;

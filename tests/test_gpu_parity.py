@@ -335,7 +335,9 @@ def test_pq_train_matches_oracle(jv, n, dim, m, k, center):
 
 
 @pytest.mark.parametrize("sim,n,dim,R", [(O.SIM_EUCLIDEAN, 3000, 32, 16), (O.SIM_COSINE, 2000, 48, 32), (O.SIM_DOT, 2500, 64, 16),
-                                         (O.SIM_EUCLIDEAN, 300, 128, 32), (O.SIM_EUCLIDEAN, 1, 8, 4), (O.SIM_EUCLIDEAN, 2, 8, 4)])
+                                         (O.SIM_EUCLIDEAN, 300, 128, 32), (O.SIM_EUCLIDEAN, 1, 8, 4), (O.SIM_EUCLIDEAN, 2, 8, 4),
+                                         # batches of 400 nodes: multi-chunk edge sort + contended back-link targets
+                                         (O.SIM_EUCLIDEAN, 20000, 16, 16), (O.SIM_DOT, 12000, 24, 32)])
 def test_graph_build_matches_oracle(jv, sim, n, dim, R):
     base, _ = clustered(n, dim, 1, seed=100 + n, normalize=(sim != O.SIM_EUCLIDEAN))
     adj, entry = jv.graph_build(base, sim, R, 100, 1.2, 1.2)
