@@ -35,8 +35,9 @@ sys.path.insert(0, str(ROOT))
 WORKLOADS = {
     # name: n, dim, sim, pq_m, R, k, overquery, nq
     # latent = intrinsic dimension of the synthetic embeddings (text-embedding models measure ~30-60)
-    "cfg2-1Mx768-dot-pq192": dict(n=1_000_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64),
-    "cfg2-small-100kx768": dict(n=100_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64),
+    # clusters = mixture components (~250 points per component at 1M keeps recall@10 near the 0.95 operating point)
+    "cfg2-1Mx768-dot-pq192": dict(n=1_000_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=4096),
+    "cfg2-small-100kx768": dict(n=100_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=512),
     "tiny-20kx128": dict(n=20_000, dim=128, sim=1, pq_m=32, R=16, k=10, over=5, nq=2_000, latent=32),
 }
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -96,7 +97,7 @@ def gen_data(torch, w, device, seed, n, nq):
     dimensions by a fixed random map plus small isotropic noise, L2-normalised (SURVEY 8d "Cohere-shaped")."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    dim, L, C = w["dim"], w["latent"], 1024
+    dim, L, C = w["dim"], w["latent"], w.get("clusters", 1024)
     W = torch.randn(L, dim, generator=g, device=device) / (L ** 0.5)
     cent = torch.randn(C, L, generator=g, device=device)
 
@@ -176,6 +177,7 @@ def main():
     ap.add_argument("--expand-width", type=int, default=0, help="0 = library default (4); 1..8; -1 = strict reference-order kernel")
     ap.add_argument("--overquery", type=int, default=0, help="override the workload's overquery factor (rerankK = k * overquery)")
     ap.add_argument("--latent", type=int, default=0, help="override the intrinsic dimension of the synthetic data")
+    ap.add_argument("--clusters", type=int, default=0, help="override the number of mixture components of the synthetic data")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
@@ -209,6 +211,8 @@ def main():
         w["over"] = args.overquery
     if args.latent:
         w["latent"] = args.latent
+    if args.clusters:
+        w["clusters"] = args.clusters
     k, rk, nq, dim, m, R = w["k"], w["k"] * w["over"], w["nq"], w["dim"], w["pq_m"], w["R"]
     shards = args.layout == "shards" and world > 1
     n_local = w["n"] // world if shards else w["n"]
@@ -272,8 +276,8 @@ def main():
         """K7: all-gather the per-GPU lists over NCCL and merge them on the device."""
         gd = torch.empty(world, nq, k, dtype=torch.int32, device=dev_t)
         gs = torch.empty(world, nq, k, dtype=torch.float32, device=dev_t)
-        dist.all_gather_into_tensor(gd, torch.where(docs_t >= 0, docs_t + base_doc, docs_t))
-        dist.all_gather_into_tensor(gs, scores_t)
+        dist.all_gather_into_tensor(gd.view(world * nq, k), torch.where(docs_t >= 0, docs_t + base_doc, docs_t).contiguous())
+        dist.all_gather_into_tensor(gs.view(world * nq, k), scores_t.contiguous())
         md = torch.empty(nq, k, dtype=torch.int32, device=dev_t)
         ms = torch.empty(nq, k, dtype=torch.float32, device=dev_t)
         mc = torch.empty(nq, dtype=torch.int32, device=dev_t)

@@ -6,13 +6,17 @@ import torch, jvpkg, bench
 jv = jvpkg.load()
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2-1Mx768-dot-pq192"
 w = dict(bench.WORKLOADS[wl])
+for kv in sys.argv[2:]:
+    k_, v_ = kv.split("=")
+    w[k_] = int(v_)
+print("workload", w, flush=True)
 host, dq = bench.build_fixture(torch, jv, w, 0, 1234, w["n"], lambda m: print("[diag]", m, flush=True))
 nq = 1000
 q = host["queries"][:nq]
 rec = lambda f, t: float(np.mean([len(set(a.tolist()) & set(b.tolist())) / t.shape[1] for a, b in zip(f, t)]))
 gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=w["pq_m"], pq_k=256, pq_codebooks=host["cb"], pq_codes=host["codes"])
 gt, _, _ = gi.exact_topk(q, 10)
-for L in (50, 100, 200):
+for L in (50, 100):
     for E in (1, 4):
         r = gi.search(q, 10, L, expand_width=E)
         print(f"PQ   L={L} E={E} recall@10={rec(r.docs, gt):.4f} visited={r.stats[:,0].mean():.0f} expanded={r.stats[:,1].mean():.0f}", flush=True)
