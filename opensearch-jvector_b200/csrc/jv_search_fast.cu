@@ -85,9 +85,8 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     sp += (size_t)kMaxNew * 4;
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
     sp += (size_t)H * 4;
-    uint8_t *sflag = reinterpret_cast<uint8_t *>(sp);
 
-    __shared__ int s_query, s_nn, s_ns, s_nsel, s_sel[kMaxE];
+    __shared__ int s_query, s_nn[2], s_ns[2];
     __shared__ float s_qnorm;
 
     const bool vec4 = (p.dim & 3) == 0 && (p.query_ids != nullptr || (reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
@@ -101,8 +100,8 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         __syncthreads();
         if (tid == 0) {
             s_query = atomicAdd(p.work_counter, 1);
-            s_nn = 0;
-            s_ns = 0;
+            s_nn[0] = 0;
+            s_ns[0] = 0;
         }
         __syncthreads();
         const int qi = s_query;
@@ -161,7 +160,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             return jv_finish_score(p.sim, raw, qnorm, xn) * p.mip_mul;
         };
 
-        int n = 0, cur = 0, visited = 0, expanded = 0;
+        int n = 0, cur = 0, visited = 0, expanded = 0, step = 0;
         if (p.entry >= 0 && p.entry < p.n_limit) {
             if (warp == 0) {
                 float s;
@@ -183,25 +182,29 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
 
         while (n > 0) {
             uint64_t *list = cur ? list1 : list0, *out = cur ? list0 : list1;
-            // ---- (a) warp 0 picks the E best unexpanded entries (list order = best first) and marks them expanded
-            if (warp == 0) {
-                int found = 0;
-                for (int c0 = 0; c0 < n && found < E; c0 += 32) {
-                    const int i = c0 + lane;
-                    const bool un = i < n && (list[i] & 1ull);
-                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
-                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
-                    if (un && rank < E) {
-                        s_sel[rank] = fkey_node(list[i]);
-                        list[i] &= ~1ull;
-                    }
-                    found += __popc(ballot);
+            const int par = step & 1; // the two step counters are double buffered: no reset race
+            // ---- (a) every warp picks the E best unexpanded entries by itself (the list is read-only until (d), so
+            //          all warps agree and no barrier / serial section is needed); lane r keeps the r-th pick
+            int nsel = 0;
+            int32_t my_sel = -1;
+            for (int c0 = 0; c0 < n && nsel < E; c0 += 32) {
+                const int i = c0 + lane;
+                const uint64_t k = i < n ? list[i] : 0ull;
+                const bool un = (k & 1ull) != 0ull;
+                const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                const int32_t node_i = fkey_node(k);
+                const int cnt = __popc(ballot);
+                for (int r = nsel; r < E && r - nsel < cnt; r++) {
+                    const int src = __fns(ballot, 0, r - nsel + 1);
+                    const int32_t v = __shfl_sync(JV_FULL_MASK, node_i, src);
+                    if (lane == r) my_sel = v;
                 }
-                if (lane == 0) s_nsel = found < E ? found : E;
+                nsel = nsel + cnt < E ? nsel + cnt : E;
             }
-            __syncthreads();
-            const int nsel = s_nsel;
             if (nsel == 0) break;
+            int32_t selr[kMaxE];
+#pragma unroll
+            for (int r = 0; r < kMaxE; r++) selr[r] = __shfl_sync(JV_FULL_MASK, my_sel, r);
 
             // ---- (b) neighbour rows of the selected nodes -> visited filter -> compacted id list
             {
@@ -209,81 +212,133 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 int32_t nb = -1;
                 if (tid < nsel * R) {
                     const int ci = tid / R, j = tid - ci * R;
-                    nb = __ldg(p.adjacency + (int64_t)s_sel[ci] * R + j);
+                    int32_t sn = selr[0];
+#pragma unroll
+                    for (int r = 1; r < kMaxE; r++) sn = ci == r ? selr[r] : sn;
+                    nb = __ldg(p.adjacency + (int64_t)sn * R + j);
                 }
                 const bool fresh = nb >= 0 && nb < p.n_limit && filter_insert(filter, p.hash_log2, tagged, nb);
                 const uint32_t ballot = __ballot_sync(JV_FULL_MASK, fresh);
                 int base = 0;
-                if (lane == 0 && ballot) base = atomicAdd(&s_nn, __popc(ballot));
+                if (lane == 0 && ballot) base = atomicAdd(&s_nn[par], __popc(ballot));
                 base = __shfl_sync(JV_FULL_MASK, base, 0);
                 if (fresh) nb_ids[base + __popc(ballot & ((1u << lane) - 1u))] = nb;
             }
             __syncthreads();
-            const int nn = s_nn;
+            const int nn = s_nn[par];
+            if (tid == 0) { // next step's counters
+                s_nn[par ^ 1] = 0;
+                s_ns[par ^ 1] = 0;
+            }
             expanded += nsel;
             visited += nn;
 
-            // ---- (c) score the gathered neighbours; keep those that can enter the list
+            // ---- (c) score the gathered neighbours; keep those that can enter the list and are not already in it
             {
                 const uint64_t worst = n >= L ? (list[L - 1] >> 1) : 0ull;
+                auto offer = [&](float score, int32_t nb) {
+                    const uint64_t k = fkey_make(score, nb);
+                    const uint64_t a = k >> 1;
+                    if (a > worst) {
+                        const int pos = count_better(list, n, a);
+                        if (!(pos < n && (list[pos] >> 1) == a)) surv[atomicAdd(&s_ns[par], 1)] = k; // drop re-scored list members
+                    }
+                };
                 if (PQ) {
-                    for (int i0 = warp * G; i0 < nn; i0 += kFWarps * G) {
-                        const int i = i0 + sub;
-                        const int32_t nb = i < nn ? nb_ids[i] : -1;
-                        const float s = adc_group(nb);
-                        if (sl == 0 && nb >= 0) {
-                            const float nnorm = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + nb) : 0.f;
-                            const uint64_t k = fkey_make(adc_finish(p.sim, s, nnorm, qnorm), nb);
-                            if ((k >> 1) > worst) surv[atomicAdd(&s_ns, 1)] = k;
+                    // 4 groups of code rows per warp in flight: every load is issued before the first table lookup
+                    constexpr int U = 4;
+                    for (int i0 = warp * G; i0 < nn; i0 += kFWarps * G * U) {
+                        uint32_t cw[U][4];
+                        int32_t nbv[U];
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const int i = i0 + u * kFWarps * G + sub;
+                            nbv[u] = i < nn ? nb_ids[i] : -1;
+#pragma unroll
+                            for (int t = 0; t < 4; t++) cw[u][t] = 0u;
+                            if (nbv[u] >= 0) {
+                                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nbv[u] * p.code_stride);
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    const int w = sl + (t << lpn_log2);
+                                    if (w < nwords) cw[u][t] = __ldg(row32 + w);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            if (i0 + u * kFWarps * G >= nn) break; // warp-uniform
+                            float s = 0.f;
+                            if (nbv[u] >= 0) {
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    const int w = sl + (t << lpn_log2);
+                                    if (w < nwords) {
+                                        const LutT *lw = lut + (size_t)w * 4 * K;
+                                        s = __fadd_rn(s, lut_get(lw, (int)(cw[u][t] & 0xffu)));
+                                        s = __fadd_rn(s, lut_get(lw, K + (int)((cw[u][t] >> 8) & 0xffu)));
+                                        s = __fadd_rn(s, lut_get(lw, 2 * K + (int)((cw[u][t] >> 16) & 0xffu)));
+                                        s = __fadd_rn(s, lut_get(lw, 3 * K + (int)(cw[u][t] >> 24)));
+                                    }
+                                }
+                                if (nwords > (4 << lpn_log2)) { // M > 512 only
+                                    const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nbv[u] * p.code_stride);
+                                    for (int w = sl + (4 << lpn_log2); w < nwords; w += LPN) {
+                                        const uint32_t c = __ldg(row32 + w);
+                                        const LutT *lw = lut + (size_t)w * 4 * K;
+                                        s = __fadd_rn(s, lut_get(lw, (int)(c & 0xffu)));
+                                        s = __fadd_rn(s, lut_get(lw, K + (int)((c >> 8) & 0xffu)));
+                                        s = __fadd_rn(s, lut_get(lw, 2 * K + (int)((c >> 16) & 0xffu)));
+                                        s = __fadd_rn(s, lut_get(lw, 3 * K + (int)(c >> 24)));
+                                    }
+                                }
+                            }
+                            for (int off = LPN >> 1; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(JV_FULL_MASK, s, off));
+                            if (sl == 0 && nbv[u] >= 0) {
+                                const float nnorm = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + nbv[u]) : 0.f;
+                                offer(adc_finish(p.sim, s, nnorm, qnorm), nbv[u]);
+                            }
                         }
                     }
                 } else {
                     for (int i = warp; i < nn; i += kFWarps) {
                         const int32_t nb = nb_ids[i];
                         const float s = exact_warp(nb);
-                        if (lane == 0) {
-                            const uint64_t k = fkey_make(s, nb);
-                            if ((k >> 1) > worst) surv[atomicAdd(&s_ns, 1)] = k;
-                        }
+                        if (lane == 0) offer(s, nb);
                     }
                 }
             }
             __syncthreads();
-            const int ns = s_ns;
+            const int ns = s_ns[par];
 
-            // ---- (d) merge survivors into the list (dedupe against the list; survivors are distinct: the filter
-            //          insertion is atomic, so a node enters nb_ids at most once per step)
-            bool valid = false;
-            uint64_t mine = 0ull;
-            int mypos = 0;
+            // ---- (d) single-pass merge: survivors are distinct (atomic filter insertion) and not in the list
+            //          (checked in (c)); list entries picked in (a) are marked expanded while they move
             if (tid < ns) {
-                mine = surv[tid];
+                const uint64_t mine = surv[tid];
                 const uint64_t a = mine >> 1;
-                mypos = count_better(list, n, a);
-                valid = !(mypos < n && (list[mypos] >> 1) == a);
-                sflag[tid] = valid ? 1 : 0;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                s_nn = 0;
-                s_ns = 0;
-            }
-            if (valid) {
-                const uint64_t a = mine >> 1;
-                int pos = mypos;
-                for (int j = 0; j < ns; j++) pos += (sflag[j] && (surv[j] >> 1) > a) ? 1 : 0;
+                int pos = count_better(list, n, a);
+                for (int j = 0; j < ns; j++) pos += ((surv[j] >> 1) > a) ? 1 : 0;
                 if (pos < L) out[pos] = mine;
             }
             for (int t = tid; t < n; t += kFThreads) {
-                const uint64_t k = list[t];
+                uint64_t k = list[t];
                 const uint64_t a = k >> 1;
                 int pos = t;
-                for (int j = 0; j < ns; j++) pos += (sflag[j] && (surv[j] >> 1) > a) ? 1 : 0;
-                if (pos < L) out[pos] = k;
+                for (int j = 0; j < ns; j++) pos += ((surv[j] >> 1) > a) ? 1 : 0;
+                if (pos < L) {
+                    if (k & 1ull) {
+                        const int32_t node = fkey_node(k);
+#pragma unroll
+                        for (int r = 0; r < kMaxE; r++)
+                            if (r < nsel && node == selr[r]) k &= ~1ull;
+                    }
+                    out[pos] = k;
+                }
             }
-            const int nvalid = __syncthreads_count(valid ? 1 : 0);
-            n = n + nvalid < L ? n + nvalid : L;
+            __syncthreads();
+            n = n + ns < L ? n + ns : L;
             cur ^= 1;
+            step++;
         }
 
         // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank kernel
