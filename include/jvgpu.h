@@ -156,8 +156,10 @@ JV_API int32_t jv_device_count(int32_t *out_count);
 JV_API int32_t jv_index_create(const jv_index_desc *desc, jv_index **out_index);
 JV_API int32_t jv_index_destroy(jv_index *index);
 JV_API int32_t jv_index_device_bytes(const jv_index *index, int64_t *out_bytes);
-/* diagnostics since index creation: which = 0 -> queries whose shared-memory visited set filled up
- * (those searches stop admitting new nodes early; results stay valid but recall may drop) */
+/* diagnostics since index creation: which = 0 -> queries whose shared-memory visited set filled up in the strict
+ * kernel (those searches stop admitting new nodes early; results stay valid but recall may drop);
+ * which = 8..15 -> SM cycles the fast kernel spent per phase (setup, table build, select, neighbour rows, scoring,
+ * merge, emit, steps), summed over CTAs; which = 100 resets all counters */
 JV_API int32_t jv_index_debug_counter(jv_index *index, int32_t which, int64_t *out_value);
 
 /* ---- K1+K2(+K4)+K3: replaces the body of JVectorReader.search, JVectorReader.java:130-210 ----

@@ -489,8 +489,8 @@ static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t 
     JV_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ix.sm_count = prop.multiProcessorCount;
     ix.smem_optin = prop.sharedMemPerBlockOptin;
-    JV_TRY(ix.dbg.alloc(16));
-    JV_CUDA_TRY(cudaMemset(ix.dbg.p, 0, 16));
+    JV_TRY(ix.dbg.alloc(128));
+    JV_CUDA_TRY(cudaMemset(ix.dbg.p, 0, 128));
     JV_TRY(ix.adjacency.alloc((size_t)n * Rb * 4));
     SearchCtx ctx;
     struct CtxGuard {

@@ -106,16 +106,26 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         __syncthreads();
         const int qi = s_query;
         if (qi >= p.nq) break;
+        long long ck[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // per-phase cycles (thread 0), see jv_index_debug_counter
+        long long t_prev = clock64();
+#define JV_PHASE(i)                      \
+    {                                    \
+        const long long t_now = clock64(); \
+        ck[i] += t_now - t_prev;         \
+        t_prev = t_now;                  \
+    }
         const float *gq = p.query_ids ? p.vectors + (int64_t)__ldg(p.query_ids + qi) * p.dim : p.queries + (int64_t)qi * p.dim;
         for (int i = tid; i < p.dim; i += kFThreads) sq[i] = __ldg(gq + i);
         for (int i = tid; i < H; i += kFThreads) filter[i] = tagged ? 0u : kEmpty;
         __syncthreads();
+        JV_PHASE(0)
         if (PQ) build_lut<LutT>(p, sq, lut, tid, kFThreads);
         if (warp == 0) {
             const float qn = jv_warp_reduce_pair<false>(sq, gq, p.dim, lane, vec4);
             if (lane == 0) s_qnorm = qn;
         }
         __syncthreads();
+        JV_PHASE(1)
         const float qnorm = s_qnorm;
 
         // ADC sum of one code row by a group of LPN lanes (valid in the group's lane 0 after the reduction)
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 nsel = nsel + cnt < E ? nsel + cnt : E;
             }
             if (nsel == 0) break;
+            JV_PHASE(2)
             int32_t selr[kMaxE];
 #pragma unroll
             for (int r = 0; r < kMaxE; r++) selr[r] = __shfl_sync(JV_FULL_MASK, my_sel, r);
@@ -225,6 +236,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 if (fresh) nb_ids[base + __popc(ballot & ((1u << lane) - 1u))] = nb;
             }
             __syncthreads();
+            JV_PHASE(3)
             const int nn = s_nn[par];
             if (tid == 0) { // next step's counters
                 s_nn[par ^ 1] = 0;
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 }
             }
             __syncthreads();
+            JV_PHASE(4)
             const int ns = s_ns[par];
 
             // ---- (d) single-pass merge: survivors are distinct (atomic filter insertion) and not in the list
@@ -336,6 +349,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 }
             }
             __syncthreads();
+            JV_PHASE(5)
             n = n + ns < L ? n + ns : L;
             cur ^= 1;
             step++;
@@ -358,6 +372,13 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 }
             }
         }
+        JV_PHASE(6)
+        if (tid == 0 && p.dbg) {
+            unsigned long long *ph = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p.dbg) + 64);
+            for (int i = 0; i < 7; i++) atomicAdd(ph + i, (unsigned long long)ck[i]);
+            atomicAdd(ph + 7, (unsigned long long)step);
+        }
+#undef JV_PHASE
     }
 }
 

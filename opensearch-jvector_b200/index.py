@@ -158,6 +158,19 @@ class GpuIndex:
         N.check(N.load().jv_index_debug_counter(self.handle, 0, C.addressof(b)))
         return int(b.value)
 
+    PHASES = ("setup", "table_build", "select", "neighbour_rows", "scoring", "merge", "emit", "steps")
+
+    def phase_cycles(self, reset: bool = False) -> dict:
+        """Per-phase SM cycles of the fast traversal kernel (thread 0 of each CTA, summed) + step count."""
+        out = {}
+        b = C.c_int64(0)
+        for i, name in enumerate(self.PHASES):
+            N.check(N.load().jv_index_debug_counter(self.handle, 8 + i, C.addressof(b)))
+            out[name] = int(b.value)
+        if reset:
+            N.check(N.load().jv_index_debug_counter(self.handle, 100, C.addressof(b)))
+        return out
+
     def _params(self, k, rerank_k, threshold, rerank_floor, accept_ptr, stride, expand_width=0):
         p = N.SearchParams()
         p.struct_size = C.sizeof(N.SearchParams)
