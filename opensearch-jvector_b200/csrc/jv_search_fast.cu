@@ -45,6 +45,14 @@ __device__ __forceinline__ int count_better(const uint64_t *list, int n, uint64_
     return lo;
 }
 
+// 4-byte read-only global load the compiler may not sink towards its use: the scoring loop issues the code words of
+// several rows back to back and only then starts the table lookups (one DRAM round trip instead of one per row).
+__device__ __forceinline__ uint32_t ldg_u32_pinned(const uint32_t *ptr) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(ptr));
+    return v;
+}
+
 // visited filter: returns true when `nb` was NOT present (and records it).  2 tags of 15 bits + valid bit per word.
 __device__ __forceinline__ bool filter_insert(uint32_t *filter, int set_bits, bool tagged, int32_t nb) {
     if (tagged) {
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
     sp += (size_t)H * 4;
 
-    __shared__ int s_query, s_nn[2], s_ns[2];
+    __shared__ int s_query, s_nn[2], s_ns[2], s_nsel, s_sel[kMaxE];
     __shared__ float s_qnorm;
 
     const bool vec4 = (p.dim & 3) == 0 && (p.query_ids != nullptr || (reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
@@ -193,29 +201,26 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         while (n > 0) {
             uint64_t *list = cur ? list1 : list0, *out = cur ? list0 : list1;
             const int par = step & 1; // the two step counters are double buffered: no reset race
-            // ---- (a) every warp picks the E best unexpanded entries by itself (the list is read-only until (d), so
-            //          all warps agree and no barrier / serial section is needed); lane r keeps the r-th pick
-            int nsel = 0;
-            int32_t my_sel = -1;
-            for (int c0 = 0; c0 < n && nsel < E; c0 += 32) {
-                const int i = c0 + lane;
-                const uint64_t k = i < n ? list[i] : 0ull;
-                const bool un = (k & 1ull) != 0ull;
-                const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
-                const int32_t node_i = fkey_node(k);
-                const int cnt = __popc(ballot);
-                for (int r = nsel; r < E && r - nsel < cnt; r++) {
-                    const int src = __fns(ballot, 0, r - nsel + 1);
-                    const int32_t v = __shfl_sync(JV_FULL_MASK, node_i, src);
-                    if (lane == r) my_sel = v;
+            // ---- (a) warp 0 picks the E best unexpanded entries (list order = best first) and marks them expanded
+            if (warp == 0) {
+                int found = 0;
+                for (int c0 = 0; c0 < n && found < E; c0 += 32) {
+                    const int i = c0 + lane;
+                    const bool un = i < n && (list[i] & 1ull);
+                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                    if (un && rank < E) {
+                        s_sel[rank] = fkey_node(list[i]);
+                        list[i] &= ~1ull;
+                    }
+                    found += __popc(ballot);
                 }
-                nsel = nsel + cnt < E ? nsel + cnt : E;
+                if (lane == 0) s_nsel = found < E ? found : E;
             }
+            __syncthreads();
+            const int nsel = s_nsel;
             if (nsel == 0) break;
             JV_PHASE(2)
-            int32_t selr[kMaxE];
-#pragma unroll
-            for (int r = 0; r < kMaxE; r++) selr[r] = __shfl_sync(JV_FULL_MASK, my_sel, r);
 
             // ---- (b) neighbour rows of the selected nodes -> visited filter -> compacted id list
             {
@@ -223,10 +228,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 int32_t nb = -1;
                 if (tid < nsel * R) {
                     const int ci = tid / R, j = tid - ci * R;
-                    int32_t sn = selr[0];
-#pragma unroll
-                    for (int r = 1; r < kMaxE; r++) sn = ci == r ? selr[r] : sn;
-                    nb = __ldg(p.adjacency + (int64_t)sn * R + j);
+                    nb = __ldg(p.adjacency + (int64_t)s_sel[ci] * R + j);
                 }
                 const bool fresh = nb >= 0 && nb < p.n_limit && filter_insert(filter, p.hash_log2, tagged, nb);
                 const uint32_t ballot = __ballot_sync(JV_FULL_MASK, fresh);
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
 #pragma unroll
                                 for (int t = 0; t < 4; t++) {
                                     const int w = sl + (t << lpn_log2);
-                                    if (w < nwords) cw[u][t] = __ldg(row32 + w);
+                                    if (w < nwords) cw[u][t] = ldg_u32_pinned(row32 + w);
                                 }
                             }
                         }
@@ -325,28 +327,28 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             const int ns = s_ns[par];
 
             // ---- (d) single-pass merge: survivors are distinct (atomic filter insertion) and not in the list
-            //          (checked in (c)); list entries picked in (a) are marked expanded while they move
+            //          (checked in (c)); position = own rank + number of better keys on the other side
+            auto count_surv_better = [&](uint64_t a) -> int {
+                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = 0;
+                for (; j + 4 <= ns; j += 4) { // 4 independent shared-memory reads in flight
+                    c0 += ((surv[j] >> 1) > a) ? 1 : 0;
+                    c1 += ((surv[j + 1] >> 1) > a) ? 1 : 0;
+                    c2 += ((surv[j + 2] >> 1) > a) ? 1 : 0;
+                    c3 += ((surv[j + 3] >> 1) > a) ? 1 : 0;
+                }
+                for (; j < ns; j++) c0 += ((surv[j] >> 1) > a) ? 1 : 0;
+                return (c0 + c1) + (c2 + c3);
+            };
             if (tid < ns) {
                 const uint64_t mine = surv[tid];
                 const uint64_t a = mine >> 1;
-                int pos = count_better(list, n, a);
-                for (int j = 0; j < ns; j++) pos += ((surv[j] >> 1) > a) ? 1 : 0;
+                const int pos = count_better(list, n, a) + count_surv_better(a);
                 if (pos < L) out[pos] = mine;
             }
-            for (int t = tid; t < n; t += kFThreads) {
-                uint64_t k = list[t];
-                const uint64_t a = k >> 1;
-                int pos = t;
-                for (int j = 0; j < ns; j++) pos += ((surv[j] >> 1) > a) ? 1 : 0;
-                if (pos < L) {
-                    if (k & 1ull) {
-                        const int32_t node = fkey_node(k);
-#pragma unroll
-                        for (int r = 0; r < kMaxE; r++)
-                            if (r < nsel && node == selr[r]) k &= ~1ull;
-                    }
-                    out[pos] = k;
-                }
+            for (int t = kFThreads - 1 - tid; t < n; t += kFThreads) { // list entries on the high warps: survivors use the low ones
+                const uint64_t k = list[t];
+                const int pos = t + count_surv_better(k >> 1);
+                if (pos < L) out[pos] = k;
             }
             __syncthreads();
             JV_PHASE(5)
