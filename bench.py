@@ -43,6 +43,16 @@ WORKLOADS = {
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def ncu_traffic(workload: str, adc_table: str, width: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the search kernel on this exact workload, taken from
+    the committed `ncu --set full` capture (profiles/search_kernel_traffic.json); None when no capture matches."""
+    p = ROOT / "profiles" / "search_kernel_traffic.json"
+    try:
+        return json.loads(p.read_text()).get(f"{workload}|{adc_table}|E{width}", {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -54,42 +64,60 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one streaming nvidia-smi process at a
+    20 ms period, started before the warm-up so its start-up cost stays outside; only samples whose timestamp falls
+    inside the timed window are used)."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device: int):
-        self.device, self.samples, self._stop, self._t = device, [], threading.Event(), None
+        self.device, self.samples, self._proc, self._t = device, [], None, None
+        self.t_begin = self.t_end = None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+    def _reader(self):
+        for line in self._proc.stdout:
+            self.samples.append((time.time(), [x.strip() for x in line.strip().split(",")]))
+
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._reader, daemon=True)
+            self._t.start()
+        except Exception:
+            self._proc = None
+        return self
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self._proc is None:
+            self.start()
+        self.t_begin = time.time()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        self.t_end = time.time()
+
+    def stop(self):
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=3)
+            except Exception:
+                self._proc.kill()
+            self._proc = None
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        inside = [s for t, s in self.samples if self.t_begin is not None and self.t_begin <= t <= (self.t_end or 1e30) and len(s) >= 7]
+        used = inside or [s for _, s in self.samples if len(s) >= 7]
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        sm = sorted(float(s[0]) for s in used if s[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in used)]
+        pw = [float(s[2]) for s in used if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(used[0][1]), "reasons": reasons,
+                "samples": len(inside), "power_w_max": max(pw) if pw else None}
 
 
 def gen_data(torch, w, device, seed, n, nq):
@@ -167,7 +195,7 @@ def algorithmic_bytes(stats, m, R, dim):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("JV_BENCH_WORKLOAD", "cfg2-1Mx768-dot-pq192"), choices=list(WORKLOADS))
@@ -300,16 +328,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(local_rank)
 
+    clocks = ClockSampler(local_rank).start()
     for _ in range(args.warmup):
         step_dev()
     barrier()
     timings = []
-    with ClockSampler(local_rank) as clocks:
+    with clocks:
         wall0 = time.perf_counter()
         for _ in range(args.steps):
             timings.append(step_dev())
         barrier()
         wall = time.perf_counter() - wall0
+    clocks.stop()
     dev_ms = sum(t["total_ms"] + t.get("merge_ms", 0.0) for t in timings)
     search_ms = sum(t["search_ms"] for t in timings) / args.steps
     rerank_ms = sum(t["rerank_ms"] for t in timings) / args.steps
@@ -376,7 +406,8 @@ def main():
         "visited_set_overflows": gi.visited_overflows(),
         "roofline": {"bound": "hbm", "kernel": "search_kernel (K1 LUT + K2 beam search + ADC)",
                      "achieved": adc_bytes / (search_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": adc_bytes / (search_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": adc_bytes / (search_ms * 1e-3) / 1e9 / peak,
+                     "traffic": ncu_traffic(args.workload, args.adc_table, args.expand_width or 4), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": adc_bytes, "kernel_ms": search_ms,
                      "rerank": {"achieved": rr_bytes / (rerank_ms * 1e-3) / 1e9, "frac": rr_bytes / (rerank_ms * 1e-3) / 1e9 / peak,
                                 "algorithmic_bytes_per_launch": rr_bytes, "kernel_ms": rerank_ms}},
