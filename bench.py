@@ -120,7 +120,7 @@ class ClockSampler:
                 "samples": len(inside), "power_w_max": max(pw) if pw else None}
 
 
-def gen_data(torch, w, device, seed, n, nq):
+def gen_data(torch, w, device, seed, n, nq, query_seed=None):
     """Embedding-shaped synthetic data: 1024-cluster Gaussian mixture in a `latent`-d space, embedded into `dim`
     dimensions by a fixed random map plus small isotropic noise, L2-normalised (SURVEY 8d "Cohere-shaped")."""
     g = torch.Generator(device=device)
@@ -140,18 +140,18 @@ def gen_data(torch, w, device, seed, n, nq):
 
     base = draw(n, g)
     gq = torch.Generator(device=device)
-    gq.manual_seed(seed + 1)
+    gq.manual_seed(seed + 1 if query_seed is None else query_seed)  # same mixture, different draws
     queries = draw(nq, gq)
     return base.contiguous(), queries.contiguous()
 
 
-def build_fixture(torch, jv, w, device, seed, n, log):
+def build_fixture(torch, jv, w, device, seed, n, log, query_seed=None):
     """Synthetic segment built on the GPU: PQ codebooks (jv_pq_train_dev), codes (K6), Vamana graph (jv_graph_build_dev)."""
     N = jv.native
     lib = N.load()
     dev_t = torch.device("cuda", device)
     t0 = time.time()
-    base, queries = gen_data(torch, w, dev_t, seed, n, w["nq"])
+    base, queries = gen_data(torch, w, dev_t, seed, n, w["nq"], query_seed)
     torch.cuda.synchronize(device)
     log(f"data {n}x{w['dim']} generated in {time.time() - t0:.1f}s")
     dim, m, K = w["dim"], w["pq_m"], 256
@@ -245,12 +245,11 @@ def main():
     shards = args.layout == "shards" and world > 1
     n_local = w["n"] // world if shards else w["n"]
     seed = 1234 + (rank * 17 if shards else 0)  # replicas share one index; shards hold disjoint data
-    host, d_queries = build_fixture(torch, jv, w, local_rank, seed, n_local, log)
+    # replicas: one index, each rank answers its own query batch (same distribution, rank-specific draws)
+    host, d_queries = build_fixture(torch, jv, w, local_rank, seed, n_local, log,
+                                    query_seed=None if (shards or world == 1) else 77_000 + rank)
     if shards and dist is not None:  # every shard answers the same query batch
         dist.broadcast(d_queries, src=0)
-        host["queries"] = d_queries.cpu().numpy()
-    elif world > 1:  # replicas: each rank searches its own batch
-        _, d_queries = gen_data(torch, w, torch.device("cuda", local_rank), 999 + rank, 8, nq)
         host["queries"] = d_queries.cpu().numpy()
 
     # ------------------------------------------------------------------------------------------ CPU arm

@@ -71,8 +71,11 @@ __device__ __forceinline__ bool filter_insert(uint32_t *filter, int set_bits, bo
     }
 }
 
-template <bool PQ, typename LutT, bool K256>
+// WPL > 0: every lane of a code-row group owns exactly WPL code words (M/4 == WPL * adc_lanes): no per-word predicates
+template <bool PQ, typename LutT, bool K256, int WPL>
 __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchParams p) {
+    constexpr bool EX = WPL > 0;
+    constexpr int NT = EX ? WPL : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.L, E = p.expand_width, H = 1 << p.hash_log2;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
     sp += (size_t)H * 4;
 
-    __shared__ int s_query, s_nn[2], s_ns[2], s_nsel, s_sel[kMaxE];
+    __shared__ int s_query, s_nn[2], s_ns[2], s_nsel, s_npref, s_sel[2 * kMaxE];
     __shared__ float s_qnorm;
 
     const bool vec4 = (p.dim & 3) == 0 && (p.query_ids != nullptr || (reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             // ---- (a) warp 0 picks the E best unexpanded entries (list order = best first) and marks them expanded
             if (warp == 0) {
                 int found = 0;
-                for (int c0 = 0; c0 < n && found < E; c0 += 32) {
+                for (int c0 = 0; c0 < n; c0 += 32) {
                     const int i = c0 + lane;
                     const bool un = i < n && (list[i] & 1ull);
                     const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
@@ -212,10 +215,16 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                     if (un && rank < E) {
                         s_sel[rank] = fkey_node(list[i]);
                         list[i] &= ~1ull;
+                    } else if (un && rank < 2 * E) {
+                        s_sel[rank] = fkey_node(list[i]); // runners-up: their neighbour rows are prefetched into L2 below
                     }
                     found += __popc(ballot);
+                    if (found >= 2 * E) break;
                 }
-                if (lane == 0) s_nsel = found < E ? found : E;
+                if (lane == 0) {
+                    s_nsel = found < E ? found : E;
+                    s_npref = found < 2 * E ? (found > E ? found - E : 0) : E;
+                }
             }
             __syncthreads();
             const int nsel = s_nsel;
@@ -229,6 +238,15 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 if (tid < nsel * R) {
                     const int ci = tid / R, j = tid - ci * R;
                     nb = __ldg(p.adjacency + (int64_t)s_sel[ci] * R + j);
+                }
+                else if (tid >= kFThreads - 32) {
+                    // speculative: the next step most likely expands the runners-up; pull their rows into L2 now so that
+                    // step's dependent row read is an L2 hit instead of a DRAM round trip
+                    const int lines = (R * 4 + 127) >> 7, t = tid - (kFThreads - 32);
+                    if (t < s_npref * lines) {
+                        const char *row = reinterpret_cast<const char *>(p.adjacency + (int64_t)s_sel[nsel + t / lines] * R) + (t % lines) * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                    }
                 }
                 const bool fresh = nb >= 0 && nb < p.n_limit && filter_insert(filter, p.hash_log2, tagged, nb);
                 const uint32_t ballot = __ballot_sync(JV_FULL_MASK, fresh);
@@ -262,20 +280,20 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                     // 4 groups of code rows per warp in flight: every load is issued before the first table lookup
                     constexpr int U = 4;
                     for (int i0 = warp * G; i0 < nn; i0 += kFWarps * G * U) {
-                        uint32_t cw[U][4];
+                        uint32_t cw[U][NT];
                         int32_t nbv[U];
 #pragma unroll
                         for (int u = 0; u < U; u++) {
                             const int i = i0 + u * kFWarps * G + sub;
                             nbv[u] = i < nn ? nb_ids[i] : -1;
 #pragma unroll
-                            for (int t = 0; t < 4; t++) cw[u][t] = 0u;
+                            for (int t = 0; t < NT; t++) cw[u][t] = 0u;
                             if (nbv[u] >= 0) {
                                 const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nbv[u] * p.code_stride);
 #pragma unroll
-                                for (int t = 0; t < 4; t++) {
+                                for (int t = 0; t < NT; t++) {
                                     const int w = sl + (t << lpn_log2);
-                                    if (w < nwords) cw[u][t] = ldg_u32_pinned(row32 + w);
+                                    if (EX || w < nwords) cw[u][t] = ldg_u32_pinned(row32 + w);
                                 }
                             }
                         }
@@ -285,9 +303,9 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                             float s = 0.f;
                             if (nbv[u] >= 0) {
 #pragma unroll
-                                for (int t = 0; t < 4; t++) {
+                                for (int t = 0; t < NT; t++) {
                                     const int w = sl + (t << lpn_log2);
-                                    if (w < nwords) {
+                                    if (EX || w < nwords) {
                                         const LutT *lw = lut + (size_t)w * 4 * K;
                                         s = __fadd_rn(s, lut_get(lw, (int)(cw[u][t] & 0xffu)));
                                         s = __fadd_rn(s, lut_get(lw, K + (int)((cw[u][t] >> 8) & 0xffu)));
@@ -295,7 +313,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                                         s = __fadd_rn(s, lut_get(lw, 3 * K + (int)(cw[u][t] >> 24)));
                                     }
                                 }
-                                if (nwords > (4 << lpn_log2)) { // M > 512 only
+                                if (!EX && nwords > (4 << lpn_log2)) { // M > 512 only
                                     const uint32_t *row32 = reinterpret_cast<const uint32_t *>(p.codes + (int64_t)nbv[u] * p.code_stride);
                                     for (int w = sl + (4 << lpn_log2); w < nwords; w += LPN) {
                                         const uint32_t c = __ldg(row32 + w);
@@ -384,9 +402,9 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     }
 }
 
-template <bool PQ, typename LutT, bool K256>
+template <bool PQ, typename LutT, bool K256, int WPL>
 static int32_t launch_fast_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_t fixed) {
-    auto kern = fast_search_kernel<PQ, LutT, K256>;
+    auto kern = fast_search_kernel<PQ, LutT, K256, WPL>;
     // shared memory per SM is 228 KB; every resident CTA also reserves 1 KB.  Take the highest occupancy that still
     // leaves a >= 2048-word visited filter (4096 tags), then give the filter what is left, capped at ~2x the nodes a
     // query touches.
@@ -451,10 +469,16 @@ int32_t launch_search_fast(jv_index *ix, SearchCtx *ctx, SearchParams &p, int ex
             return JV_ERR_UNSUPPORTED;
         }
         const bool k256 = p.K == 256;
-        if (f16) return k256 ? launch_fast_typed<true, __half, true>(ix, ctx, p, fixed) : launch_fast_typed<true, __half, false>(ix, ctx, p, fixed);
-        return k256 ? launch_fast_typed<true, float, true>(ix, ctx, p, fixed) : launch_fast_typed<true, float, false>(ix, ctx, p, fixed);
+        const int nwords = p.M >> 2;
+        const int wpl = (nwords % lanes == 0 && (nwords / lanes == 3 || nwords / lanes == 4)) ? nwords / lanes : 0;
+        if (k256 && wpl == 3)
+            return f16 ? launch_fast_typed<true, __half, true, 3>(ix, ctx, p, fixed) : launch_fast_typed<true, float, true, 3>(ix, ctx, p, fixed);
+        if (k256 && wpl == 4)
+            return f16 ? launch_fast_typed<true, __half, true, 4>(ix, ctx, p, fixed) : launch_fast_typed<true, float, true, 4>(ix, ctx, p, fixed);
+        if (f16) return k256 ? launch_fast_typed<true, __half, true, 0>(ix, ctx, p, fixed) : launch_fast_typed<true, __half, false, 0>(ix, ctx, p, fixed);
+        return k256 ? launch_fast_typed<true, float, true, 0>(ix, ctx, p, fixed) : launch_fast_typed<true, float, false, 0>(ix, ctx, p, fixed);
     }
-    return launch_fast_typed<false, float, false>(ix, ctx, p, fixed);
+    return launch_fast_typed<false, float, false, 0>(ix, ctx, p, fixed);
 }
 
 }  // namespace jv
