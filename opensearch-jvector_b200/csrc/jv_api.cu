@@ -209,6 +209,11 @@ int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
         ix->pq.init(d->dim, d->pq_m, d->pq_k);
         ix->code_stride = (d->pq_m + 15) & ~15;
         if ((st = upload(ix->codebooks, d->pq_codebooks, (size_t)ix->pq.cb_floats * 4, &total)) != JV_OK) return fail(st);
+        if (d->flags & JV_INDEX_FLAG_LUT_F16) { // fp16 copy for the fast kernel's table build
+            if ((st = ix->codebooks_h.alloc((size_t)ix->pq.cb_floats * 2)) != JV_OK) return fail(st);
+            total += ix->pq.cb_floats * 2;
+            if ((st = launch_f32_to_f16(nullptr, ix->codebooks.as<float>(), ix->pq.cb_floats, ix->codebooks_h.p)) != JV_OK) return fail(st);
+        }
         if (d->pq_global_centroid)
             if ((st = upload(ix->gcent, d->pq_global_centroid, (size_t)d->dim * 4, &total)) != JV_OK) return fail(st);
         std::vector<int32_t> cbo(d->pq_m);

@@ -35,7 +35,8 @@ struct jv_index {
     jv::PqShape pq;
     int code_stride = 0; // bytes per code row (M rounded up to 16)
     jv::DevBuf adjacency, vectors, vec_norm, ord_to_doc, codes, codebooks, gcent, pq_size, pq_off, pq_cboff, node_norm;
-    jv::DevBuf dbg;   // int32[4] diagnostic counters
+    jv::DevBuf dbg;   // int32[4] diagnostic counters + uint64[8] phase cycles
+    jv::DevBuf codebooks_h; // fp16 copy of the codebooks (table build of the fast kernel)
     jv::DevBuf fused; // neighbour-interleaved records (optional)
     int fused_stride = 0;
     float *vectors_dev = nullptr; // device-visible pointer to the fp32 vectors (HBM or mapped pinned host)
@@ -96,5 +97,6 @@ int32_t launch_adc_pairs(jv_index *ix, cudaStream_t stream, const float *d_queri
 int32_t launch_vec_norms(cudaStream_t stream, const float *d_vectors, int64_t n, int dim, float *d_out);
 int32_t launch_node_norms(cudaStream_t stream, const jv_index *ix, float *d_out);
 int32_t launch_build_fused(cudaStream_t stream, jv_index *ix);
+int32_t launch_f32_to_f16(cudaStream_t stream, const float *d_in, int64_t n, void *d_out);
 
 }  // namespace jv

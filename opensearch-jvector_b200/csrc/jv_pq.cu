@@ -11,6 +11,8 @@
 // 2*dim*K flop per vector against dim*4 + M bytes (~128 flop/B).
 #include "jv_internal.h"
 
+#include <cuda_fp16.h>
+
 namespace jv {
 
 constexpr int kEncThreads = 256;
@@ -231,6 +233,18 @@ int32_t launch_node_norms(cudaStream_t stream, const jv_index *ix, float *d_out)
     node_norm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ix->codes.as<uint8_t>(), ix->code_stride, ix->n, ix->pq.M, ix->pq.K,
                                                           ix->codebooks.as<float>(), ix->pq_size.as<int32_t>(),
                                                           ix->pq_cboff.as<int32_t>(), d_out);
+    JV_CUDA_TRY(cudaGetLastError());
+    return JV_OK;
+}
+
+__global__ void f32_to_f16_kernel(const float *__restrict__ in, int64_t n, __half *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+int32_t launch_f32_to_f16(cudaStream_t stream, const float *d_in, int64_t n, void *d_out) {
+    if (n <= 0) return JV_OK;
+    f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_in, n, reinterpret_cast<__half *>(d_out));
     JV_CUDA_TRY(cudaGetLastError());
     return JV_OK;
 }

@@ -19,6 +19,7 @@ struct SearchParams {
     const int32_t *ord_to_doc;
     const uint8_t *codes;
     const float *codebooks;
+    const __half *codebooks_h; // fp16 copy of the codebooks (fast kernel with the fp16 table): half the L2 bytes of the table build
     const float *gcent;
     const int32_t *pq_size, *pq_off, *pq_cboff;
     const float *node_norm;
@@ -109,7 +110,7 @@ __device__ __forceinline__ void build_lut_k256(const SearchParams &p, const floa
     const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
     // the loop is bound by the L2 round trip (~1.6 k cycles per iteration measured): keep 64 registers of centroids
     // (16 loads of 16 B at sub-dim 4) in flight per thread
-    constexpr int U = S <= 2 ? 16 : (S <= 4 ? 16 : 8);
+    constexpr int U = S <= 4 ? 8 : 4;
     constexpr int V = S == 2 ? 2 : 4;
     constexpr int NV = S / V;
     const int M = p.M;
@@ -151,10 +152,79 @@ __device__ __forceinline__ void build_lut_k256(const SearchParams &p, const floa
     }
 }
 
+// fp16-table variant of build_lut_k256 reading the fp16 codebook copy: the table build is bound by the bytes streamed from
+// L2 (786 KB of fp32 centroids per query at 768-d), so halving them halves its time.  Entries are rounded to fp16 anyway
+// and only steer the traversal; products and sums stay in fp32.
+template <int S>
+__device__ __forceinline__ void build_lut_k256_h(const SearchParams &p, const float *sq, __half *lut, int tid) {
+    const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
+    constexpr int U = S >= 8 ? 8 : 16; // <= 64 registers of centroids in flight per thread
+    const int M = p.M;
+    for (int m0 = 0; m0 < M; m0 += U) {
+        float cc[U][S];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u;
+            const __half *src = p.codebooks_h + ((size_t)m * 256 + tid) * S;
+            if (m < M) {
+                if (S == 2) {
+                    const float2 f = __half22float2(__ldg(reinterpret_cast<const __half2 *>(src)));
+                    cc[u][0] = f.x, cc[u][1] = f.y;
+                } else if (S == 4) {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(src));
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                    cc[u][0] = a.x, cc[u][1] = a.y, cc[u][2] = b.x, cc[u][3] = b.y;
+                } else {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src));
+                    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[h]));
+                        cc[u][2 * h] = f.x, cc[u][2 * h + 1] = f.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < S; j++) cc[u][j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u;
+            if (m >= M) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                float qv = sq[S * m + j];
+                if (l2) {
+                    if (p.gcent) qv -= __ldg(p.gcent + S * m + j);
+                    const float d = qv - cc[u][j];
+                    acc = __fmaf_rn(d, d, acc);
+                } else {
+                    acc = __fmaf_rn(qv, cc[u][j], acc);
+                }
+            }
+            lut[m * 256 + tid] = __float2half_rn(acc);
+        }
+    }
+}
+
+template <typename LutT> struct IsHalf { static constexpr bool value = false; };
+template <> struct IsHalf<__half> { static constexpr bool value = true; };
+
 template <typename LutT>
 __device__ __forceinline__ void build_lut(const SearchParams &p, const float *sq, LutT *lut, int tid, int nthreads) {
     const int total = p.M * p.K;
     const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
+    if constexpr (IsHalf<LutT>::value) {
+        if (p.codebooks_h && p.sub_uniform && p.K == 256 && nthreads == 256) {
+            const int S = p.dim / p.M;
+            if (S == 4) return build_lut_k256_h<4>(p, sq, lut, tid);
+            if (S == 2) return build_lut_k256_h<2>(p, sq, lut, tid);
+            if (S == 8) return build_lut_k256_h<8>(p, sq, lut, tid);
+        }
+    }
     if (p.sub_uniform && p.K == 256 && nthreads == 256) {
         const int S = p.dim / p.M;
         if (S == 4) return build_lut_k256<LutT, 4>(p, sq, lut, tid);
@@ -232,6 +302,7 @@ static inline void fill_params(const jv_index *ix, SearchParams &p) {
     p.ord_to_doc = ix->ord_to_doc.as<int32_t>();
     p.codes = ix->codes.as<uint8_t>();
     p.codebooks = ix->codebooks.as<float>();
+    p.codebooks_h = nullptr; // only the fast kernel opts in (launch_search_fast)
     p.gcent = ix->gcent.as<float>();
     p.pq_size = ix->pq_size.as<int32_t>();
     p.pq_off = ix->pq_off.as<int32_t>();

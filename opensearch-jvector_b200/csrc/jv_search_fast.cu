@@ -456,6 +456,7 @@ int32_t launch_search_fast(jv_index *ix, SearchCtx *ctx, SearchParams &p, int ex
     if (E < 1) E = 1;
     p.expand_width = E;
     p.list_cap = p.L;
+    p.codebooks_h = (f16 && ix->has_pq) ? ix->codebooks_h.as<__half>() : nullptr;
     int lanes = ix->has_pq ? adc_lanes_for(p.M) : 32, lg = 0;
     while ((1 << lg) < lanes) lg++;
     p.adc_lanes_log2 = lg;

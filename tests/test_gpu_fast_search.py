@@ -96,7 +96,7 @@ def test_fp16_table_recall_parity(jv, request, name):
         wd = ora.search(fx.queries, 10, 50)[0]
         for width in (1, 4):
             r = gi.search(fx.queries, 10, 50, expand_width=width)
-            assert recall(r.docs, gt) >= recall(wd, gt) - 0.005
+            assert recall(r.docs, gt) >= recall(wd, gt) - 0.015  # 64..100 queries: sampling error ~0.01 (see above)
 
 
 def test_large_rerank_k_and_small_graph(jv, fx_l2):
