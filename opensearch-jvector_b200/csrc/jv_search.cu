@@ -265,7 +265,7 @@ static int32_t launch_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_
     }
     // do not take more than needed: visits ~ expansions * new-neighbours ~ 0.7 * L * R without a filter;
     // a filter multiplies the expansions by ~1/selectivity, so keep everything shared memory offers then
-    const int64_t want = p.accept ? ((int64_t)1 << 30) : (int64_t)3 * p.L * (p.R > 0 ? p.R : 1);
+    const int64_t want = (p.accept || p.threshold > 0.f) ? ((int64_t)1 << 30) : (int64_t)3 * p.L * (p.R > 0 ? p.R : 1);
     while (hash_log2 > 12 && ((int64_t)1 << (hash_log2 - 1)) >= want) hash_log2--;
     p.hash_log2 = hash_log2;
     const size_t smem = fixed_bytes + ((size_t)4 << hash_log2);
@@ -310,7 +310,7 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     // candidate capacity: without a filter only the best L unexpanded candidates can ever be popped
     // (DESIGN.md "bounded candidate list"); with a filter rejected nodes do not fill the results, keep more.
     int C = a.rerank_k < 64 ? 64 : a.rerank_k;
-    if (a.d_accept) C = C * 8 > 4096 ? (C > 4096 ? C : 4096) : C * 8;
+    if (a.d_accept || a.threshold > 0.f) C = C * 8 > 4096 ? (C > 4096 ? C : 4096) : C * 8; // results may never fill up
     p.cand_cap = C;
     const bool f16 = (ix->flags & JV_INDEX_FLAG_LUT_F16) != 0;
     // production path: unfiltered, threshold-free queries go to the fast kernel (jv_search_fast.cu); filters and
