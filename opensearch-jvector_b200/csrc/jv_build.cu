@@ -545,7 +545,7 @@ static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t 
     bp.deg = deg.as<int32_t>();
     bp.order = order.as<int32_t>();
 
-    int64_t bcap = (int64_t)((double)n * 0.02); // prefix doubling, capped at 2 % of n and 8192 (oracle defaults)
+    int64_t bcap = n / 50; // prefix doubling, capped at 2 % of n (integer, as in the oracle) and 8192
     if (bcap > 8192) bcap = 8192;
     if (bcap < 1) bcap = 1;
     int64_t epad = 1;

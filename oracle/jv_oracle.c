@@ -920,7 +920,9 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
 
     inserted[entry] = 1;
     int64_t done = 1;
-    int64_t bcap = (int64_t)((double)n * (double)frac); /* prefix doubling, capped at frac*n and max_batch */
+    /* prefix doubling, capped at n/divisor (integer: the device builder must compute the same cap) and max_batch */
+    const int64_t divisor = frac > 0.f ? (int64_t)(1.0f / frac + 0.5f) : 50;
+    int64_t bcap = n / (divisor > 0 ? divisor : 50);
     if (bcap > max_batch) bcap = max_batch;
     if (bcap < 1) bcap = 1;
     while (done < n) {
