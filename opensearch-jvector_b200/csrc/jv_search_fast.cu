@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
     sp += (size_t)H * 4;
 
-    __shared__ int s_query, s_nn[2], s_ns[2], s_nsel, s_npref, s_sel[2 * kMaxE];
+    __shared__ int s_query, s_nn[2], s_ns[2], w_sel[kFWarps][2 * kMaxE], w_pos[kFWarps][2 * kMaxE];
     __shared__ float s_qnorm;
 
     const bool vec4 = (p.dim & 3) == 0 && (p.query_ids != nullptr || (reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
@@ -204,30 +204,24 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         while (n > 0) {
             uint64_t *list = cur ? list1 : list0, *out = cur ? list0 : list1;
             const int par = step & 1; // the two step counters are double buffered: no reset race
-            // ---- (a) warp 0 picks the E best unexpanded entries (list order = best first) and marks them expanded
-            if (warp == 0) {
-                int found = 0;
-                for (int c0 = 0; c0 < n; c0 += 32) {
-                    const int i = c0 + lane;
-                    const bool un = i < n && (list[i] & 1ull);
-                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
-                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
-                    if (un && rank < E) {
-                        s_sel[rank] = fkey_node(list[i]);
-                        list[i] &= ~1ull;
-                    } else if (un && rank < 2 * E) {
-                        s_sel[rank] = fkey_node(list[i]); // runners-up: their neighbour rows are prefetched into L2 below
-                    }
-                    found += __popc(ballot);
-                    if (found >= 2 * E) break;
+            // ---- (a) every warp scans the list flags itself (two ballots at L = 50; the list is not written until after
+            //          the barrier below), so the selection needs neither a serial section nor a barrier of its own
+            int found = 0;
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                const int i = c0 + lane;
+                const bool un = i < n && (list[i] & 1ull);
+                const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                if (un && rank < 2 * E) { // ranks E..2E-1 are runners-up: their rows are prefetched into L2 below
+                    w_sel[warp][rank] = fkey_node(list[i]);
+                    w_pos[warp][rank] = i;
                 }
-                if (lane == 0) {
-                    s_nsel = found < E ? found : E;
-                    s_npref = found < 2 * E ? (found > E ? found - E : 0) : E;
-                }
+                found += __popc(ballot);
+                if (found >= 2 * E) break;
             }
-            __syncthreads();
-            const int nsel = s_nsel;
+            __syncwarp();
+            const int nsel = found < E ? found : E;
+            const int npref = found < 2 * E ? (found > E ? found - E : 0) : E;
             if (nsel == 0) break;
             JV_PHASE(2)
 
@@ -237,14 +231,13 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 int32_t nb = -1;
                 if (tid < nsel * R) {
                     const int ci = tid / R, j = tid - ci * R;
-                    nb = __ldg(p.adjacency + (int64_t)s_sel[ci] * R + j);
-                }
-                else if (tid >= kFThreads - 32) {
+                    nb = __ldg(p.adjacency + (int64_t)w_sel[warp][ci] * R + j);
+                } else if (tid >= kFThreads - 32) {
                     // speculative: the next step most likely expands the runners-up; pull their rows into L2 now so that
                     // step's dependent row read is an L2 hit instead of a DRAM round trip
                     const int lines = (R * 4 + 127) >> 7, t = tid - (kFThreads - 32);
-                    if (t < s_npref * lines) {
-                        const char *row = reinterpret_cast<const char *>(p.adjacency + (int64_t)s_sel[nsel + t / lines] * R) + (t % lines) * 128;
+                    if (t < npref * lines) {
+                        const char *row = reinterpret_cast<const char *>(p.adjacency + (int64_t)w_sel[warp][nsel + t / lines] * R) + (t % lines) * 128;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
                     }
                 }
@@ -256,6 +249,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
                 if (fresh) nb_ids[base + __popc(ballot & ((1u << lane) - 1u))] = nb;
             }
             __syncthreads();
+            if (warp == 0 && lane < nsel) list[w_pos[0][lane]] &= ~1ull; // mark expanded: flags are next read in (d), two barriers away
             JV_PHASE(3)
             const int nn = s_nn[par];
             if (tid == 0) { // next step's counters
@@ -413,7 +407,7 @@ static int32_t launch_fast_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, 
     if (want < 2048) want = 2048;
     int best_occ = 0, best_log2 = 0;
     for (int occ = 8; occ >= 1; occ--) {
-        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 256 - (int64_t)fixed;
+        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 1152 - (int64_t)fixed; // 1 KB system + static __shared__
         if (per < 2048 * 4) continue;
         int lg = 11;
         while (lg < 15 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
