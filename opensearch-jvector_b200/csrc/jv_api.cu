@@ -383,11 +383,29 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
         JV_TRY(c->accept.ensure(abytes));
         d_accept = c->accept.as<uint64_t>();
     }
+    // Queries in pinned (page-locked, UVA-mapped) host memory — the FFM shim's registered buffer, cudaHostAlloc, torch
+    // pin_memory — are read by the kernels in place over PCIe: each CTA pulls its 3 KB query when it starts on it, which
+    // overlaps with the other CTAs' work instead of a serial nq*dim*4-byte copy in front of the batch.  Pageable memory
+    // takes the staged copy.
+    const float *d_q = c->queries.as<float>();
+    bool zero_copy = false;
+    {
+        cudaPointerAttributes at;
+        void *dp = nullptr;
+        if (cudaPointerGetAttributes(&at, queries) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&dp, const_cast<float *>(queries), 0) == cudaSuccess && dp != nullptr &&
+            (reinterpret_cast<uintptr_t>(dp) & 15) == 0) {
+            d_q = static_cast<const float *>(dp);
+            zero_copy = true;
+        } else {
+            cudaGetLastError(); // pageable memory: clear the sticky "invalid value" of the attribute query
+        }
+    }
     JV_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+    if (!zero_copy) JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
     if (abytes) JV_CUDA_TRY(cudaMemcpyAsync(c->accept.p, p->accept_bits, abytes, cudaMemcpyHostToDevice, c->stream));
     int launches = 0;
-    JV_TRY(search_core(ix, c, c->queries.as<float>(), nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
+    JV_TRY(search_core(ix, c, d_q, nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
                        c->out_count.as<int32_t>(), c->stats.as<jv_query_stats>(), &launches));
     JV_CUDA_TRY(cudaMemcpyAsync(out_doc, c->out_doc.p, kb, cudaMemcpyDeviceToHost, c->stream));
     JV_CUDA_TRY(cudaMemcpyAsync(out_score, c->out_score.p, kb, cudaMemcpyDeviceToHost, c->stream));

@@ -151,7 +151,9 @@ __device__ __forceinline__ float jv_warp_sum_canonical(float v) {
 // Canonical fp32 reductions, one warp per (a, b) pair: element i goes to partial (i mod 128) with fmaf,
 // lane j owns partials 4j..4j+3; bit-identical to oracle/jv_oracle.c canon_dot / canon_l2sq.
 // `a` may live in shared memory, `b` in global; `vec4` = both are 16-byte aligned and dim % 4 == 0.
-template <bool L2>
+// BG = `b` lives in global memory (read through the read-only path); BG = false lets `b` be shared memory too
+// (e.g. the norm of a query that was staged from pinned host memory: no second trip over PCIe).
+template <bool L2, bool BG = true>
 __device__ __forceinline__ float jv_warp_reduce_pair(const float *__restrict__ a, const float *__restrict__ b, int dim,
                                                      int lane, bool vec4) {
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
@@ -162,7 +164,7 @@ __device__ __forceinline__ float jv_warp_reduce_pair(const float *__restrict__ a
 #pragma unroll 4
         for (int i = lane; i < n4; i += 32) {
             float4 x = a4[i];
-            float4 y = __ldg(b4 + i);
+            float4 y = BG ? __ldg(b4 + i) : b4[i];
             if (L2) {
                 float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
                 p0 = __fmaf_rn(d0, d0, p0);
@@ -183,7 +185,7 @@ __device__ __forceinline__ float jv_warp_reduce_pair(const float *__restrict__ a
             for (int c = 0; c < 4; c++) {
                 const bool in = base + c < dim;
                 x[c] = in ? a[base + c] : 0.f;
-                y[c] = in ? __ldg(b + base + c) : 0.f; // (0,0) contributes exactly +0 to dot and to L2
+                y[c] = in ? (BG ? __ldg(b + base + c) : b[base + c]) : 0.f; // (0,0) contributes exactly +0 to dot and to L2
             }
             if (L2) {
                 float d0 = x[0] - y[0], d1 = x[1] - y[1], d2 = x[2] - y[2], d3 = x[3] - y[3];

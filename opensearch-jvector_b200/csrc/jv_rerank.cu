@@ -35,7 +35,7 @@ rerank_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_n
         for (int i = tid; i < dim; i += kRerankThreads) sq[i] = __ldg(gq + i);
         __syncthreads();
         if (warp == 0) {
-            float qn = jv_warp_reduce_pair<false>(sq, gq, dim, lane, vec4); // second operand must be global (__ldg)
+            float qn = jv_warp_reduce_pair<false, false>(sq, sq, dim, lane, (dim & 3) == 0);
             if (lane == 0) s_qnorm = qn;
         }
         __syncthreads();

@@ -74,7 +74,7 @@ template <bool PQ, typename LutT> __global__ void __launch_bounds__(kThreads) se
         __syncthreads();
         if (PQ) build_lut<LutT>(p, sq, lut, tid, kThreads);
         if (warp == 0) {
-            float qn = jv_warp_reduce_pair<false>(sq, gq, p.dim, lane, vec4);
+            float qn = jv_warp_reduce_pair<false, false>(sq, sq, p.dim, lane, (p.dim & 3) == 0);
             if (lane == 0) s_qnorm = qn;
         }
         __syncthreads();

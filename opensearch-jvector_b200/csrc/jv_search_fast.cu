@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         JV_PHASE(0)
         if (PQ) build_lut<LutT>(p, sq, lut, tid, kFThreads);
         if (warp == 0) {
-            const float qn = jv_warp_reduce_pair<false>(sq, gq, p.dim, lane, vec4);
+            const float qn = jv_warp_reduce_pair<false, false>(sq, sq, p.dim, lane, (p.dim & 3) == 0);
             if (lane == 0) s_qnorm = qn;
         }
         __syncthreads();

@@ -128,3 +128,19 @@ def test_filtered_and_threshold_queries_use_strict_kernel(jv, fx_l2):
         wd, ws, wc, _ = ora.search(fx.queries, 10, 50, accept_bits=bits)
         np.testing.assert_array_equal(r.docs, wd)
         np.testing.assert_array_equal(r.counts, wc)
+
+
+def test_pinned_host_queries_are_read_in_place(jv, fx_dot):
+    """jv_search_batch reads page-locked host queries zero-copy (no staged H2D); results must not change."""
+    torch = pytest.importorskip("torch")
+    fx = fx_dot
+    pinned = torch.from_numpy(fx.queries.copy()).pin_memory()
+    with fx.gpu_index(jv) as gi:
+        a = gi.search(fx.queries, 10, 50)                 # pageable numpy -> staged copy
+        b = gi.search(pinned.numpy(), 10, 50)             # pinned -> kernels read host memory directly
+        np.testing.assert_array_equal(a.docs, b.docs)
+        np.testing.assert_array_equal(a.scores, b.scores)
+        np.testing.assert_array_equal(a.stats, b.stats)
+        c = gi.search(pinned.numpy(), 10, 50, expand_width=-1)
+        d = gi.search(fx.queries, 10, 50, expand_width=-1)
+        np.testing.assert_array_equal(c.docs, d.docs)
