@@ -140,7 +140,8 @@ def test_pinned_host_queries_are_read_in_place(jv, fx_dot):
         b = gi.search(pinned.numpy(), 10, 50)             # pinned -> kernels read host memory directly
         np.testing.assert_array_equal(a.docs, b.docs)
         np.testing.assert_array_equal(a.scores, b.scores)
-        np.testing.assert_array_equal(a.stats, b.stats)
+        # visited counts include re-scored nodes, which depend on the (timing-dependent) eviction order of the filter
+        np.testing.assert_array_equal(a.stats[:, 1:], b.stats[:, 1:])
         c = gi.search(pinned.numpy(), 10, 50, expand_width=-1)
         d = gi.search(fx.queries, 10, 50, expand_width=-1)
         np.testing.assert_array_equal(c.docs, d.docs)
