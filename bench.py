@@ -200,8 +200,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("JV_BENCH_WORKLOAD", "cfg2-1Mx768-dot-pq192"), choices=list(WORKLOADS))
     ap.add_argument("--layout", default="replicas", choices=["replicas", "shards"])
-    ap.add_argument("--adc-table", default="fp16", choices=["fp16", "fp32"],
-                    help="precision of the per-query ADC table in shared memory (steering scores only; final scores are exact)")
+    ap.add_argument("--adc-table", default="u8", choices=["u8", "fp16", "fp32"],
+                    help="per-query ADC table: u8 = batched 8-bit table kernel + TMA-staged traversal (production), "
+                         "fp16/fp32 = table build fused into the traversal kernel")
     ap.add_argument("--expand-width", type=int, default=0, help="0 = library default (4); 1..8; -1 = strict reference-order kernel")
     ap.add_argument("--overquery", type=int, default=0, help="override the workload's overquery factor (rerankK = k * overquery)")
     ap.add_argument("--latent", type=int, default=0, help="override the intrinsic dimension of the synthetic data")
@@ -281,7 +282,7 @@ def main():
         return 0
 
     # ------------------------------------------------------------------------------------------ our arm
-    flags = N.FLAG_LUT_F16 if args.adc_table == "fp16" else 0
+    flags = {"u8": N.FLAG_LUT_U8, "fp16": N.FLAG_LUT_F16, "fp32": 0}[args.adc_table]
     t0 = time.time()
     gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"], pq_codes=host["codes"],
                      device=local_rank, flags=flags)
@@ -341,6 +342,7 @@ def main():
     clocks.stop()
     dev_ms = sum(t["total_ms"] + t.get("merge_ms", 0.0) for t in timings)
     search_ms = sum(t["search_ms"] for t in timings) / args.steps
+    lut_ms = sum(t.get("lut_ms", 0.0) for t in timings) / args.steps
     rerank_ms = sum(t["rerank_ms"] for t in timings) / args.steps
     launches = sum(t["launches"] for t in timings) + (args.steps if shards else 0)
 
@@ -403,7 +405,8 @@ def main():
         "recall_at_10": rec, "wall_ms_per_step": t_wall / args.steps * 1e3,
         "visited_per_query": float(st[:, 0].mean()), "expanded_per_query": float(st[:, 1].mean()),
         "visited_set_overflows": gi.visited_overflows(),
-        "roofline": {"bound": "hbm", "kernel": "search_kernel (K1 LUT + K2 beam search + ADC)",
+        "roofline": {"bound": "hbm", "kernel": "lut_q8_kernel + q8_search_kernel (K1 table build + K2 beam search + ADC)" if args.adc_table == "u8"
+                     else "fast_search_kernel (K1 LUT + K2 beam search + ADC)", "lut_ms": lut_ms,
                      "achieved": adc_bytes / (search_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": adc_bytes / (search_ms * 1e-3) / 1e9 / peak,
                      "traffic": ncu_traffic(args.workload, args.adc_table, args.expand_width or 4), "peak_source": peak_src,

@@ -83,6 +83,11 @@ typedef enum jv_status {
 #define JV_INDEX_FLAG_LUT_F16 2u      /* hold the per-query ADC table in fp16 in shared memory
                                           (steering scores only; final scores are the exact rerank) */
 #define JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE 4u /* keep the fp32 vectors in pinned host memory (cfg 5) */
+#define JV_INDEX_FLAG_LUT_U8 8u      /* production traversal: per-query ADC table quantised to bytes with one scale per
+                                          query (integer sums, fused-ADC style), built by a batched kernel and staged
+                                          into shared memory with TMA; needs K = 256 and dim % M == 0 with sub-vector
+                                          size 2, 4 or 8, otherwise the fp16/fp32 table path is used.  Steering scores
+                                          only; final scores are the exact rerank. */
 
 typedef struct jv_index_desc {
     int32_t struct_size;       /* = sizeof(jv_index_desc), for forward compatibility          */
@@ -125,7 +130,8 @@ typedef struct jv_batch_timing {
     float d2h_ms;
     float total_ms;
     int32_t launches; /* kernels launched for this batch                               */
-    int32_t reserved;
+    float lut_ms;     /* share of search_ms spent in the batched 8-bit table build (first chunk; 0 when the
+                         table build is fused into the traversal kernel)                  */
 } jv_batch_timing;
 
 typedef struct jv_search_params {
@@ -193,6 +199,9 @@ JV_API int32_t jv_pq_encode_dev(int32_t device, const float *d_vectors, int64_t 
 /* ---- K1 alone (test hook for the ADC table): PQVectors.precomputedScoreFunctionFor, JVectorReader.java:354.
  * out_lut [nq * m * k] fp32: dot (DOT/COSINE/MIP) or squared L2 of the (centred) query sub-vector. */
 JV_API int32_t jv_pq_lut(jv_index *index, const float *queries, int32_t nq, float *out_lut);
+/* K1, 8-bit flavour (JV_INDEX_FLAG_LUT_U8 indexes; test hook): out_q8 [nq * m * 256] bytes in logical (m, c) order,
+ * out_params [nq * 2] = (delta, base): partial-sum estimate = delta * sum_m q8[m][code_m] + base. */
+JV_API int32_t jv_pq_lut_q8(jv_index *index, const float *queries, int32_t nq, uint8_t *out_q8, float *out_params);
 /* ADC scores of explicit (query, node) pairs through the same device code as the traversal. */
 JV_API int32_t jv_pq_adc_scores(jv_index *index, const float *queries, int32_t nq, const int32_t *nodes, int32_t nodes_per_query,
                          float *out_scores);

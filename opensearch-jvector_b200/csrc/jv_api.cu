@@ -1,5 +1,6 @@
 // jv_api.cu — the extern "C" boundary of libjvgpu.so (include/jvgpu.h): argument validation, index
 // lifetime, per-call context pool, H2D/D2H staging, timing.  No torch, no CPU compute fallback.
+#include <math.h>
 #include <stdarg.h>
 
 #include "jv_internal.h"
@@ -235,6 +236,40 @@ int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
             total += (int64_t)n * 4;
             if ((st = launch_node_norms(nullptr, ix, ix->node_norm.as<float>())) != JV_OK) return fail(st);
         }
+        const int S = ix->pq.uniform ? d->dim / d->pq_m : 0;
+        if ((d->flags & JV_INDEX_FLAG_LUT_U8) && d->pq_k == 256 && (S == 2 || S == 4 || S == 8)) {
+            // 8-bit table path: bounding ball of every subspace codebook (same double-precision definition as the
+            // oracle's pq_ball) + lane-major permuted code rows
+            ix->q8_nj = (d->pq_m + 31) / 32;
+            std::vector<float> ctr((size_t)d->dim), rad((size_t)d->pq_m);
+            for (int m = 0; m < d->pq_m; m++) {
+                const float *cb = d->pq_codebooks + ix->pq.cb_off[m];
+                for (int j = 0; j < S; j++) {
+                    double acc = 0.0;
+                    for (int c = 0; c < 256; c++) acc += (double)cb[(size_t)c * S + j];
+                    ctr[(size_t)m * S + j] = (float)(acc / 256.0);
+                }
+                double r2max = 0.0;
+                for (int c = 0; c < 256; c++) {
+                    double r2 = 0.0;
+                    for (int j = 0; j < S; j++) {
+                        const double dd = (double)cb[(size_t)c * S + j] - (double)ctr[(size_t)m * S + j];
+                        r2 += dd * dd;
+                    }
+                    if (r2 > r2max) r2max = r2;
+                }
+                rad[m] = (float)sqrt(r2max) * 1.0009765625f;
+            }
+            if ((st = upload(ix->ball_ctr, ctr.data(), ctr.size() * 4, &total)) != JV_OK) return fail(st);
+            if ((st = upload(ix->ball_rad, rad.data(), rad.size() * 4, &total)) != JV_OK) return fail(st);
+            const size_t qb = n * (size_t)ix->q8_nj * 32;
+            if ((st = ix->codes_q8.alloc(qb)) != JV_OK) return fail(st);
+            total += (int64_t)qb;
+            if ((st = launch_permute_codes(nullptr, ix->codes.as<uint8_t>(), d->n, d->pq_m, ix->code_stride, ix->q8_nj,
+                                           ix->codes_q8.as<uint8_t>())) != JV_OK)
+                return fail(st);
+            ix->q8_ok = true;
+        }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) {
         set_error("index creation kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -307,6 +342,7 @@ static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, i
     a.entry_override = -1;
     a.n_limit = ix->n;
     a.expand_width = p->expand_width;
+    c->lut_timed = false;
     JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     JV_TRY(launch_search(ix, c, a, launches));
     JV_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
@@ -329,6 +365,7 @@ static void fill_timing(SearchCtx *c, jv_batch_timing *t, int launches, bool hos
         cudaEventElapsedTime(&t->total_ms, c->ev[1], c->ev[3]);
     }
     t->launches = launches;
+    if (c->lut_timed) cudaEventElapsedTime(&t->lut_ms, c->ev[1], c->ev[5]);
 }
 
 int32_t jv_search_batch_dev(jv_index *ix, const float *d_queries, int32_t nq, const jv_search_params *p, int32_t *d_out_doc,
@@ -392,7 +429,8 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
     {
         cudaPointerAttributes at;
         void *dp = nullptr;
-        if (cudaPointerGetAttributes(&at, queries) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        // (the 8-bit table path reads every query several times in the batched table build: stage it in HBM)
+        if (!ix->q8_ok && cudaPointerGetAttributes(&at, queries) == cudaSuccess && at.type == cudaMemoryTypeHost &&
             cudaHostGetDevicePointer(&dp, const_cast<float *>(queries), 0) == cudaSuccess && dp != nullptr &&
             (reinterpret_cast<uintptr_t>(dp) & 15) == 0) {
             d_q = static_cast<const float *>(dp);
@@ -549,6 +587,34 @@ int32_t jv_pq_lut(jv_index *ix, const float *queries, int32_t nq, float *out_lut
     JV_CUDA_TRY(cudaMemcpy(dq.p, queries, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice));
     JV_TRY(launch_pq_lut(ix, nullptr, dq.as<float>(), nq, dl.as<float>()));
     JV_CUDA_TRY(cudaMemcpy(out_lut, dl.p, lb, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
+int32_t jv_pq_lut_q8(jv_index *ix, const float *queries, int32_t nq, uint8_t *out_q8, float *out_params) {
+    JV_REQUIRE(ix && queries && out_q8 && out_params && nq >= 0, "bad arguments");
+    JV_REQUIRE(ix->has_pq && ix->q8_ok, "index was not created with JV_INDEX_FLAG_LUT_U8 (or its PQ shape is not supported by the 8-bit table)");
+    if (nq == 0) return JV_OK;
+    DeviceGuard guard(ix->device);
+    const int M = ix->pq.M, lutb = ix->q8_nj * 8192;
+    DevBuf dq, dl, dp;
+    JV_TRY(dq.alloc((size_t)nq * ix->dim * 4));
+    JV_TRY(dl.alloc((size_t)nq * lutb));
+    JV_TRY(dp.alloc((size_t)nq * sizeof(float4)));
+    JV_CUDA_TRY(cudaMemcpy(dq.p, queries, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice));
+    JV_TRY(launch_lut_q8(ix, nullptr, dq.as<float>(), nq, dl.as<uint8_t>(), dp.as<float4>()));
+    JV_CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<uint8_t> raw((size_t)nq * lutb);
+    std::vector<float> prm((size_t)nq * 4);
+    JV_CUDA_TRY(cudaMemcpy(raw.data(), dl.p, raw.size(), cudaMemcpyDeviceToHost));
+    JV_CUDA_TRY(cudaMemcpy(prm.data(), dp.p, prm.size() * 4, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < nq; q++) { // undo the bank-interleaved layout: (m, c) -> ((m/32)*64 + c/4)*128 + (m%32)*4 + c%4
+        const uint8_t *t = raw.data() + (size_t)q * lutb;
+        for (int m = 0; m < M; m++)
+            for (int c = 0; c < 256; c++)
+                out_q8[((size_t)q * M + m) * 256 + c] = t[((size_t)(m >> 5) * 64 + (c >> 2)) * 128 + (m & 31) * 4 + (c & 3)];
+        out_params[2 * q] = prm[4 * (size_t)q];
+        out_params[2 * q + 1] = prm[4 * (size_t)q + 1];
+    }
     return JV_OK;
 }
 

@@ -13,7 +13,9 @@ struct SearchCtx {
     DevBuf approx_keys, approx_count; // [nq*rerank_k] uint64 keys (score, ordinal), best first
     DevBuf counter;                   // persistent-grid work counter
     DevBuf visited;                   // global visited tables (fallback when they do not fit in smem)
+    DevBuf lut8, qparams;             // 8-bit ADC tables of the current chunk + per-query (delta, base, ||q||^2)
     DevBuf slice_doc, slice_score;    // brute force: per-slice partial top-k
+    bool lut_timed = false;           // ev[5] was recorded after the first chunk's table build
     void *pinned = nullptr;           // host staging
     size_t pinned_bytes = 0;
     int32_t init(int device);
@@ -38,6 +40,10 @@ struct jv_index {
     jv::DevBuf dbg;   // int32[4] diagnostic counters + uint64[8] phase cycles
     jv::DevBuf codebooks_h; // fp16 copy of the codebooks (table build of the fast kernel)
     jv::DevBuf fused; // neighbour-interleaved records (optional)
+    // 8-bit table path (JV_INDEX_FLAG_LUT_U8): lane-major permuted codes, bounding balls of the subspace codebooks
+    jv::DevBuf codes_q8, ball_ctr, ball_rad;
+    bool q8_ok = false;
+    int q8_nj = 0; // 32-subspace blocks per code row (M rounded up to 32)
     int fused_stride = 0;
     float *vectors_dev = nullptr; // device-visible pointer to the fp32 vectors (HBM or mapped pinned host)
     void *vectors_host = nullptr;
@@ -69,6 +75,12 @@ struct SearchLaunch {
     int64_t n_limit;         // nodes >= n_limit are ignored (graph builder); n for queries
 };
 int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches);
+
+// K1+K2 with the 8-bit table (jv_q8.cu)
+bool q8_search_supported(const jv_index *ix, int L, int R);
+int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches);
+int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, uint8_t *d_lut, float4 *d_qparams);
+int32_t launch_permute_codes(cudaStream_t stream, const uint8_t *d_codes, int64_t n, int M, int stride, int NJ, uint8_t *d_out);
 
 // K3: exact rerank of the approximate list + top-k + ordinal->doc mapping
 int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int rerank_k, float rerank_floor,

@@ -1,0 +1,747 @@
+// jv_q8.cu — production traversal with an 8-bit quantised ADC table (JV_INDEX_FLAG_LUT_U8).
+//
+// K1 (PQVectors.precomputedScoreFunctionFor, JVectorReader.java:352-357) and K2 (GraphSearcher.search + PQDecoder ADC,
+// JVectorReader.java:165-173) split into two kernels so each can be laid out for the hardware:
+//
+//   lut_q8_kernel     one CTA builds the tables of QT queries at once: thread = subspace, the codebook streams through
+//                     shared memory (cp.async, double buffered per warp) and every centroid read is reused for QT
+//                     queries from registers.  Entries are quantised to bytes with ONE scale per query (the sum of M
+//                     bytes is then an exact integer, independent of summation order) and written in the bank-
+//                     interleaved layout the traversal wants.  Definitions = oracle q8_quantise (bit-identical).
+//   q8_search_kernel  one CTA (4 warps) per query, persistent grid.  The 48 KB table (M=192) arrives with one TMA bulk
+//                     copy (cp.async.bulk + mbarrier); 4 CTAs share an SM.  Per step every warp expands one candidate:
+//                     reads its adjacency row (128 B, coalesced), tests the visited filter, and scores its own fresh
+//                     neighbours — 8 lanes per code row, 4 rows per warp at a time, table lookups bank-conflict-free by
+//                     construction.  Survivors are merged into the sorted list once per step (2 block barriers / step).
+//
+// Table layout in shared memory (and in the HBM staging buffer):  byte (m, c)  ->  ((m/32)*64 + c/4)*128 + (m%32)*4 + c%4
+// i.e. bank = m % 32.  Code rows are stored permuted (codes_q8): lane sl of a row group owns subspaces m = 8t + sl, its
+// 4*NJ bytes contiguous, so at lookup t the 8 lanes of a group hit 8 different banks and the 4 groups of a warp are
+// rotated onto the 4 different bank quarters.
+#include <stdlib.h>
+
+#include "jv_search_common.cuh"
+
+namespace jv {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+template <int BYTES> __device__ __forceinline__ void cp_async(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t sat_u8_rn(float x) {
+    uint32_t u;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// index-creation helper: codes [n][stride] -> codes_q8 [n][MP] (lane-major permutation, zero padded)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void permute_codes_kernel(const uint8_t *__restrict__ codes, int64_t n, int M, int stride, int NJ, uint8_t *__restrict__ out) {
+    const int MP = NJ * 32, seg = NJ * 4;
+    const int64_t total = n * MP;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / MP;
+        const int o = (int)(i - row * MP);
+        const int sl = o / seg, t = o - sl * seg;
+        const int m = 8 * t + sl;
+        out[i] = m < M ? codes[row * stride + m] : (uint8_t)0;
+    }
+}
+
+int32_t launch_permute_codes(cudaStream_t stream, const uint8_t *d_codes, int64_t n, int M, int stride, int NJ, uint8_t *d_out) {
+    if (n == 0) return JV_OK;
+    const int64_t total = n * NJ * 32;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    permute_codes_kernel<<<(int)blocks, 256, 0, stream>>>(d_codes, n, M, stride, NJ, d_out);
+    JV_CUDA_TRY(cudaGetLastError());
+    return JV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: batched 8-bit table build
+// ---------------------------------------------------------------------------------------------------------------
+struct LutQ8Params {
+    const float *queries; // [nq][dim]
+    const float *codebooks, *gcent, *ball_ctr, *ball_rad;
+    uint8_t *lut;   // [nq][NJ*8192]
+    float4 *qparams; // [nq] (delta, base, ||q||^2, 0)
+    int nq, dim, M, NJ, sim;
+};
+
+template <int S>
+__global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
+    constexpr int QT = S == 2 ? 8 : 32 / S;     // queries per CTA (QT * S <= 32 query registers per thread)
+    constexpr int CH = 32 / S;                 // codes per staged chunk: 128 B per subspace
+    constexpr int PB = S == 2 ? 8 : 16;        // cp.async piece
+    constexpr int PIECES = 128 / PB;           // per subspace per chunk
+    constexpr int ROWB = 128 + (S == 2 ? 8 : 16); // padded row: conflict-free vector reads at lane stride
+    constexpr int NCHUNK = 256 / CH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int MP = p.NJ * 32;
+    unsigned char *stage = smem_raw + (size_t)warp * 2 * 32 * ROWB;
+    float *lo_s = reinterpret_cast<float *>(smem_raw + (size_t)nw * 2 * 32 * ROWB); // [QT][MP]
+    __shared__ uint32_t range_s[QT];
+    __shared__ float inv_s[QT], qn_s[QT];
+    const int q0 = blockIdx.x * QT;
+    const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
+
+    if (tid < QT) range_s[tid] = 0u;
+    __syncthreads();
+
+    auto load_q = [&](int m, float (&qr)[QT][S]) {
+#pragma unroll
+        for (int t = 0; t < QT; t++) {
+            const bool ok = m < p.M && q0 + t < p.nq;
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                float v = ok ? __ldg(p.queries + (int64_t)(q0 + t) * p.dim + m * S + j) : 0.f;
+                if (ok && l2 && p.gcent) v = __fsub_rn(v, __ldg(p.gcent + m * S + j));
+                qr[t][j] = v;
+            }
+        }
+    };
+
+    // ---- phase 0: per-subspace bounds from the bounding ball (oracle q8_bounds), shared range per query
+    for (int j = warp; j < p.NJ; j += nw) {
+        const int m = j * 32 + lane;
+        float qr[QT][S];
+        load_q(m, qr);
+        float ctr[S], rad = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < S; jj++) ctr[jj] = m < p.M ? __ldg(p.ball_ctr + m * S + jj) : 0.f;
+        if (m < p.M) rad = __ldg(p.ball_rad + m);
+#pragma unroll
+        for (int t = 0; t < QT; t++) {
+            float lo = 0.f, r = 0.f;
+            if (m < p.M) {
+                if (l2) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < S; jj++) {
+                        const float d = __fsub_rn(qr[t][jj], ctr[jj]);
+                        acc = __fmaf_rn(d, d, acc);
+                    }
+                    const float d = __fsqrt_rn(acc);
+                    float a = __fsub_rn(d, rad);
+                    if (a < 0.f) a = 0.f;
+                    const float b = __fadd_rn(d, rad);
+                    lo = __fmul_rn(a, a);
+                    r = __fsub_rn(__fmul_rn(b, b), lo);
+                } else {
+                    float qq = 0.f, qc = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < S; jj++) qq = __fmaf_rn(qr[t][jj], qr[t][jj], qq);
+#pragma unroll
+                    for (int jj = 0; jj < S; jj++) qc = __fmaf_rn(qr[t][jj], ctr[jj], qc);
+                    const float w = __fmul_rn(__fsqrt_rn(qq), rad);
+                    lo = __fsub_rn(qc, w);
+                    r = __fsub_rn(__fadd_rn(qc, w), lo);
+                }
+            }
+            lo_s[t * MP + m] = lo;
+            if (r > 0.f) atomicMax(&range_s[t], __float_as_uint(r)); // r >= 0: the bit pattern orders like the value
+        }
+    }
+    __syncthreads();
+    // ||q||^2 (canonical order) for the cosine decoder: one warp per query
+    for (int t = warp; t < QT; t += nw) {
+        float qn = 0.f;
+        if (q0 + t < p.nq) {
+            const float *gq = p.queries + (int64_t)(q0 + t) * p.dim;
+            qn = jv_warp_reduce_pair<false>(gq, gq, p.dim, lane, (p.dim & 3) == 0 && (reinterpret_cast<uintptr_t>(gq) & 15) == 0);
+        }
+        if (lane == 0) qn_s[t] = qn;
+    }
+    __syncthreads();
+    if (tid < QT) {
+        const float range = __uint_as_float(range_s[tid]);
+        const float inv = range > 0.f ? __fdiv_rn(255.0f, range) : 0.f;
+        float base = 0.f;
+        for (int m = 0; m < p.M; m++) base = __fadd_rn(base, lo_s[tid * MP + m]);
+        inv_s[tid] = inv;
+        if (q0 + tid < p.nq) p.qparams[q0 + tid] = make_float4(__fdiv_rn(range, 255.0f), base, qn_s[tid], 0.f);
+    }
+    __syncthreads();
+
+    // ---- main pass: thread = subspace (lane) of block j; chunks of CH codes staged per warp
+    for (int j = warp; j < p.NJ; j += nw) {
+        const int m = j * 32 + lane;
+        float qr[QT][S], inv[QT], nlo[QT];
+        load_q(m, qr);
+#pragma unroll
+        for (int t = 0; t < QT; t++) {
+            inv[t] = inv_s[t];
+            nlo[t] = -__fmul_rn(lo_s[t * MP + m], inv[t]);
+        }
+        auto issue = [&](int ch, int buf) {
+#pragma unroll
+            for (int r = 0; r < PIECES; r++) {
+                const int pid = lane + 32 * r;
+                const int b = pid / PIECES, piece = pid % PIECES;
+                const int mm = j * 32 + b;
+                if (mm < p.M)
+                    cp_async<PB>(stage + (size_t)(buf * 32 + b) * ROWB + piece * PB,
+                                 reinterpret_cast<const unsigned char *>(p.codebooks + ((int64_t)mm * 256 + ch * CH) * S) + piece * PB);
+            }
+            cp_async_commit();
+        };
+        issue(0, 0);
+        for (int ch = 0; ch < NCHUNK; ch++) {
+            const int buf = ch & 1;
+            if (ch + 1 < NCHUNK) {
+                issue(ch + 1, buf ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const unsigned char *row = stage + (size_t)(buf * 32 + lane) * ROWB;
+#pragma unroll
+            for (int c4 = 0; c4 < CH / 4; c4++) {
+                uint32_t w[QT];
+#pragma unroll
+                for (int t = 0; t < QT; t++) w[t] = 0u;
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    float cv[S];
+                    const unsigned char *cp = row + (c4 * 4 + cc) * S * 4;
+                    if (S == 2) {
+                        const float2 v = *reinterpret_cast<const float2 *>(cp);
+                        cv[0] = v.x, cv[1] = v.y;
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < S / 4; h++) {
+                            const float4 v = *reinterpret_cast<const float4 *>(cp + h * 16);
+                            cv[4 * h] = v.x, cv[4 * h + 1] = v.y, cv[4 * h + 2] = v.z, cv[4 * h + 3] = v.w;
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < QT; t++) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < S; jj++) {
+                            if (l2) {
+                                const float d = __fsub_rn(qr[t][jj], cv[jj]);
+                                acc = __fmaf_rn(d, d, acc);
+                            } else {
+                                acc = __fmaf_rn(qr[t][jj], cv[jj], acc);
+                            }
+                        }
+                        w[t] |= sat_u8_rn(__fmaf_rn(acc, inv[t], nlo[t])) << (8 * cc);
+                    }
+                }
+                const int c4g = ch * (CH / 4) + c4; // = c >> 2
+#pragma unroll
+                for (int t = 0; t < QT; t++) {
+                    if (q0 + t < p.nq)
+                        reinterpret_cast<uint32_t *>(p.lut + (int64_t)(q0 + t) * p.NJ * 8192)[(j * 64 + c4g) * 32 + lane] = m < p.M ? w[t] : 0u;
+                }
+            }
+            __syncwarp(); // the buffer is refilled two iterations from now
+        }
+    }
+}
+
+static size_t lut_q8_smem(int nw, int S, int MP) {
+    const int rowb = 128 + (S == 2 ? 8 : 16), qt = S == 2 ? 8 : 32 / S;
+    return (size_t)nw * 2 * 32 * rowb + (size_t)qt * MP * 4;
+}
+
+int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, uint8_t *d_lut, float4 *d_qparams) {
+    JV_REQUIRE(ix->has_pq && ix->q8_ok, "index has no 8-bit table support (needs K = 256 and a uniform sub-vector size of 2, 4 or 8)");
+    LutQ8Params p;
+    p.queries = d_queries;
+    p.codebooks = ix->codebooks.as<float>();
+    p.gcent = ix->gcent.as<float>();
+    p.ball_ctr = ix->ball_ctr.as<float>();
+    p.ball_rad = ix->ball_rad.as<float>();
+    p.lut = d_lut;
+    p.qparams = d_qparams;
+    p.nq = nq;
+    p.dim = ix->dim;
+    p.M = ix->pq.M;
+    p.NJ = ix->q8_nj;
+    p.sim = ix->sim;
+    const int S = ix->dim / ix->pq.M;
+    const int nw = p.NJ < 8 ? p.NJ : 8;
+    const size_t smem = lut_q8_smem(nw, S, p.NJ * 32);
+    const int qt = S == 2 ? 8 : 32 / S;
+    const int grid = (nq + qt - 1) / qt;
+    if (S == 4) {
+        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lut_q8_kernel<4><<<grid, nw * 32, smem, stream>>>(p);
+    } else if (S == 2) {
+        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lut_q8_kernel<2><<<grid, nw * 32, smem, stream>>>(p);
+    } else {
+        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lut_q8_kernel<8><<<grid, nw * 32, smem, stream>>>(p);
+    }
+    JV_CUDA_TRY(cudaGetLastError());
+    return JV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: traversal
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kQW = 4;            // warps per CTA = candidates expanded per step
+constexpr int kQThreads = kQW * 32;
+constexpr int kQMaxE = kQW;
+
+struct Q8Params {
+    const int32_t *adjacency;
+    const uint8_t *codes_q8;
+    const float *node_norm;
+    const uint8_t *lut;      // [nq][lutb]
+    const float4 *qparams;   // [nq]
+    uint64_t *approx_keys;   // [nq][L]
+    int32_t *approx_count;
+    jv_query_stats *stats;
+    int *work_counter;
+    int *dbg;
+    int64_t n;
+    int nq, L, R, entry, sim, NJ, lutb, hash_log2, E, surv_cap;
+};
+
+__device__ __forceinline__ uint64_t qkey_make(float score, int32_t node) {
+    return ((uint64_t)jv_f2ord(score) << 32) | ((uint64_t)(uint32_t)(0x7fffffff - node) << 1) | 1ull;
+}
+__device__ __forceinline__ int32_t qkey_node(uint64_t k) { return 0x7fffffff - (int32_t)((k >> 1) & 0x7fffffffu); }
+__device__ __forceinline__ float qkey_score(uint64_t k) { return jv_ord2f((uint32_t)(k >> 32)); }
+
+// number of list entries strictly better than `a` (= key >> 1); list sorted descending
+__device__ __forceinline__ int q_count_better(const uint64_t *list, int n, uint64_t a) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((list[mid] >> 1) > a)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// visited filter: true when `nb` was NOT present (and records it).  2 tags of 15 bits + valid bit per word; (set, tag) is
+// a bijection of the ordinal when n <= 2^(set_bits+15), so there are no false positives; evictions only cause re-scoring.
+__device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, bool tagged, int32_t nb) {
+    if (tagged) {
+        const uint32_t x = ((uint32_t)nb * 0x9E3779B1u) & ((1u << (set_bits + 15)) - 1u);
+        const uint32_t set = x >> 15, tag = (x & 0x7fffu) | 0x8000u;
+        uint32_t old = filter[set];
+        for (;;) {
+            if ((old & 0xffffu) == tag || (old >> 16) == tag) return false;
+            const uint32_t seen = atomicCAS(&filter[set], old, (old << 16) | tag);
+            if (seen == old) return true;
+            old = seen;
+        }
+    } else {
+        const uint32_t h = ((uint32_t)nb * 2654435761u) >> (32 - set_bits);
+        return atomicExch(&filter[h], (uint32_t)nb) != (uint32_t)nb;
+    }
+}
+
+// NJ_T > 0: code words per lane known at compile time (registers, all loads of U rows in flight before the first lookup)
+template <int NJ_T>
+__global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params p) {
+    constexpr int U = 2; // row groups in flight per warp pass: 4 groups x U rows
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = p.L, E = p.E, H = 1 << p.hash_log2, R = p.R;
+    const int NJ = NJ_T > 0 ? NJ_T : p.NJ;
+
+    unsigned char *sp = smem_raw;
+    const uint8_t *lut = sp;
+    sp += p.lutb;
+    uint64_t *list0 = reinterpret_cast<uint64_t *>(sp);
+    sp += (size_t)L * 8;
+    uint64_t *list1 = reinterpret_cast<uint64_t *>(sp);
+    sp += (size_t)L * 8;
+    uint64_t *surv = reinterpret_cast<uint64_t *>(sp);
+    sp += (size_t)p.surv_cap * 8;
+    int32_t *wids = reinterpret_cast<int32_t *>(sp) + warp * 32;
+    sp += (size_t)kQW * 32 * 4;
+    uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
+
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_query, s_ns[2], s_vis, w_sel[kQW][2 * kQMaxE], w_pos[kQW][2 * kQMaxE];
+
+    const bool tagged = p.n <= ((int64_t)1 << (p.hash_log2 + 15));
+    // ADC lane geometry: group g = lane / 8 scores one code row, lane sl owns subspaces m = 8t + sl.  At lookup (j, i) the
+    // group reads bank quarter (i + g) & 3, so the 32 lanes of a warp always hit 32 different banks.
+    const int g = lane >> 3, sl = lane & 7;
+    uint32_t sel[4], lb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t qd = (uint32_t)(i + g) & 3u;
+        sel[i] = 0x4440u | qd;
+        lb[i] = qd * 32u + (uint32_t)sl * 4u;
+    }
+    const int seg = NJ * 4; // bytes of a code row owned by one lane
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase = 0;
+
+    // ADC sum of the code row of `nb` for this lane's subspaces (caller reduces over the 8 lanes of the group)
+    auto lookups = [&](const uint32_t *cw) -> uint32_t {
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t c = __byte_perm(cw[j], 0u, sel[i]);
+                const uint32_t off = ((c & 0xFCu) << 5) + (c & 3u);
+                s += lut[j * 8192 + lb[i] + off];
+            }
+        }
+        return s;
+    };
+    auto row_sum = [&](int32_t nb) -> uint32_t { // one row per group, no batching (entry node, generic NJ)
+        uint32_t s = 0;
+        if (nb >= 0) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nb * (NJ * 32) + sl * seg);
+            if (NJ_T > 0) {
+                uint32_t cw[NJ_T > 0 ? NJ_T : 1];
+#pragma unroll
+                for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) cw[j] = __ldg(row + j);
+                s = lookups(cw);
+            } else {
+                for (int j = 0; j < NJ; j++) {
+                    const uint32_t cwj = __ldg(row + j);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t c = __byte_perm(cwj, 0u, sel[i]);
+                        const uint32_t off = ((c & 0xFCu) << 5) + (c & 3u);
+                        s += lut[j * 8192 + lb[i] + off];
+                    }
+                }
+            }
+        }
+        s += __shfl_xor_sync(JV_FULL_MASK, s, 4);
+        s += __shfl_xor_sync(JV_FULL_MASK, s, 2);
+        s += __shfl_xor_sync(JV_FULL_MASK, s, 1);
+        return s;
+    };
+
+    for (;;) {
+        __syncthreads(); // everyone is done with the previous query's table, lists and counters
+        if (tid == 0) {
+            s_query = atomicAdd(p.work_counter, 1);
+            s_ns[0] = 0;
+            s_vis = 0;
+        }
+        __syncthreads();
+        const int qi = s_query;
+        if (qi >= p.nq) break;
+        if (tid == 0) { // K1 result: one TMA bulk copy HBM/L2 -> shared memory
+            mbar_expect_tx(&s_bar, (uint32_t)p.lutb);
+            bulk_g2s(smem_raw, p.lut + (int64_t)qi * p.lutb, (uint32_t)p.lutb, &s_bar);
+        }
+        for (int i = tid; i < H; i += kQThreads) filter[i] = tagged ? 0u : kEmpty;
+        const float4 qp = __ldg(p.qparams + qi);
+        const float delta = qp.x, base = qp.y, qnorm = qp.z;
+        auto finish = [&](uint32_t isum, int32_t nb) -> float {
+            const float s = __fmaf_rn(delta, (float)isum, base);
+            const float nn = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + nb) : 0.f;
+            return adc_finish(p.sim, s, nn, qnorm);
+        };
+        __syncthreads(); // filter cleared
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+
+        int n = 0, cur = 0, my_visited = 0, expanded = 0, step = 0;
+        if (p.entry >= 0 && p.entry < p.n) {
+            if (warp == 0) {
+                const uint32_t s = row_sum(g == 0 ? p.entry : -1);
+                if (lane == 0) {
+                    list0[0] = qkey_make(finish(s, p.entry), p.entry);
+                    q_filter_insert(filter, p.hash_log2, tagged, p.entry);
+                }
+                my_visited = 1;
+            }
+            n = 1;
+        }
+        __syncthreads();
+
+        while (n > 0) {
+            uint64_t *list = cur ? list1 : list0, *out = cur ? list0 : list1;
+            const int par = step & 1;
+            // ---- (a) every warp scans the list flags itself: no serial section, no barrier
+            int found = 0;
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                const int i = c0 + lane;
+                const bool un = i < n && (list[i] & 1ull);
+                const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                if (un && rank < 2 * E) { // ranks E..2E-1 are runners-up: their rows are prefetched into L2
+                    w_sel[warp][rank] = qkey_node(list[i]);
+                    w_pos[warp][rank] = i;
+                }
+                found += __popc(ballot);
+                if (found >= 2 * E) break;
+            }
+            __syncwarp();
+            const int nsel = found < E ? found : E;
+            if (nsel == 0) break;
+            const uint64_t worst = n >= L ? (list[L - 1] >> 1) : 0ull;
+
+            // ---- (b) warp w expands candidate w: adjacency row -> visited filter -> ADC of the fresh neighbours
+            if (warp < nsel) {
+                const int32_t cand = w_sel[warp][warp];
+                if (nsel + warp < found && nsel + warp < 2 * E) { // runner-up row -> L2 for the next step
+                    const int lines = (R * 4 + 127) >> 7;
+                    if (lane < lines)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.adjacency + (int64_t)w_sel[warp][nsel + warp] * R) + lane * 128));
+                }
+                for (int r0 = 0; r0 < R; r0 += 32) {
+                    int32_t nb = -1;
+                    if (r0 + lane < R) nb = __ldg(p.adjacency + (int64_t)cand * R + r0 + lane);
+                    const bool fresh = nb >= 0 && nb < p.n && q_filter_insert(filter, p.hash_log2, tagged, nb);
+                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, fresh);
+                    const int cnt = __popc(ballot);
+                    if (fresh) wids[__popc(ballot & ((1u << lane) - 1u))] = nb;
+                    __syncwarp();
+                    my_visited += cnt;
+                    auto offer = [&](uint32_t isum, int32_t node) {
+                        const uint64_t k = qkey_make(finish(isum, node), node);
+                        const uint64_t a = k >> 1;
+                        if (a > worst) {
+                            const int pos = q_count_better(list, n, a);
+                            if (!(pos < n && (list[pos] >> 1) == a)) surv[atomicAdd(&s_ns[par], 1)] = k; // drop re-scored list members
+                        }
+                    };
+                    if (NJ_T > 0) {
+                        for (int i0 = 0; i0 < cnt; i0 += 4 * U) {
+                            uint32_t cw[U][NJ_T > 0 ? NJ_T : 1];
+                            int32_t nbv[U];
+#pragma unroll
+                            for (int u = 0; u < U; u++) {
+                                const int idx = i0 + u * 4 + g;
+                                nbv[u] = idx < cnt ? wids[idx] : -1;
+                                if (nbv[u] >= 0) {
+                                    const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nbv[u] * (NJ * 32) + sl * seg);
+#pragma unroll
+                                    for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cw[u][j]) : "l"(row + j));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) cw[u][j] = 0u;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; u++) {
+                                if (i0 + u * 4 >= cnt) break; // warp-uniform
+                                uint32_t s = nbv[u] >= 0 ? lookups(cw[u]) : 0u;
+                                s += __shfl_xor_sync(JV_FULL_MASK, s, 4);
+                                s += __shfl_xor_sync(JV_FULL_MASK, s, 2);
+                                s += __shfl_xor_sync(JV_FULL_MASK, s, 1);
+                                if (sl == 0 && nbv[u] >= 0) offer(s, nbv[u]);
+                            }
+                        }
+                    } else {
+                        for (int i0 = 0; i0 < cnt; i0 += 4) {
+                            const int idx = i0 + g;
+                            const int32_t node = idx < cnt ? wids[idx] : -1;
+                            const uint32_t s = row_sum(node);
+                            if (sl == 0 && node >= 0) offer(s, node);
+                        }
+                    }
+                    __syncwarp(); // wids is reused by the next chunk of the row
+                }
+            }
+            __syncthreads(); // B1: all survivors are in surv[]
+            const int ns = s_ns[par];
+            if (tid == 0) s_ns[par ^ 1] = 0; // next step's counter (pushes start after B2)
+            expanded += nsel;
+
+            // ---- (c) single-pass merge: survivors are distinct (atomic filter insertion) and not in the list;
+            //          position = own rank + number of better keys on the other side.  Selected entries lose their flag here.
+            auto count_surv_better = [&](uint64_t a) -> int {
+                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = 0;
+                for (; j + 4 <= ns; j += 4) {
+                    c0 += ((surv[j] >> 1) > a) ? 1 : 0;
+                    c1 += ((surv[j + 1] >> 1) > a) ? 1 : 0;
+                    c2 += ((surv[j + 2] >> 1) > a) ? 1 : 0;
+                    c3 += ((surv[j + 3] >> 1) > a) ? 1 : 0;
+                }
+                for (; j < ns; j++) c0 += ((surv[j] >> 1) > a) ? 1 : 0;
+                return (c0 + c1) + (c2 + c3);
+            };
+            for (int t = tid; t < ns; t += kQThreads) {
+                const uint64_t mine = surv[t];
+                const uint64_t a = mine >> 1;
+                const int pos = q_count_better(list, n, a) + count_surv_better(a);
+                if (pos < L) out[pos] = mine;
+            }
+            for (int t = kQThreads - 1 - tid; t < n; t += kQThreads) { // list entries on the high threads: survivors use the low ones
+                uint64_t k = list[t];
+                bool selected = false;
+                for (int e = 0; e < nsel; e++) selected |= (w_pos[warp][e] == t);
+                if (selected) k &= ~1ull;
+                const int pos = t + count_surv_better(k >> 1);
+                if (pos < L) out[pos] = k;
+            }
+            __syncthreads(); // B2
+            n = n + ns < L ? n + ns : L;
+            cur ^= 1;
+            step++;
+        }
+
+        // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank kernel
+        if (lane == 0 && my_visited) atomicAdd(&s_vis, my_visited);
+        __syncthreads();
+        {
+            const uint64_t *list = cur ? list1 : list0;
+            uint64_t *o = p.approx_keys + (int64_t)qi * L;
+            for (int i = tid; i < L; i += kQThreads) o[i] = i < n ? jv_mk_key(qkey_score(list[i]), qkey_node(list[i])) : 0ull;
+            if (tid == 0) {
+                p.approx_count[qi] = n;
+                if (p.stats) {
+                    jv_query_stats st;
+                    st.visited = s_vis;
+                    st.expanded = expanded;
+                    st.expanded_base = expanded;
+                    st.reranked = 0;
+                    p.stats[qi] = st;
+                }
+            }
+        }
+    }
+}
+
+template <int NJ_T>
+static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
+    auto kern = q8_search_kernel<NJ_T>;
+    const size_t fixed = (size_t)p.lutb + (size_t)p.L * 16 + (size_t)p.surv_cap * 8 + (size_t)kQW * 32 * 4;
+    const size_t sm_total = 228 * 1024;
+    int64_t want = (int64_t)p.L * p.R; // words; 2 tags each
+    if (want < 1024) want = 1024;
+    int best_occ = 0, best_log2 = 0;
+    for (int occ = 8; occ >= 1; occ--) {
+        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 512 - (int64_t)fixed; // 1 KB system + static __shared__
+        if (per < 1024 * 4) continue;
+        int lg = 10;
+        while (lg < 15 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
+        best_occ = occ;
+        best_log2 = lg;
+        break;
+    }
+    if (!best_occ) {
+        set_error("search (8-bit table): shared memory budget exceeded (%zu fixed bytes)", fixed);
+        return JV_ERR_UNSUPPORTED;
+    }
+    p.hash_log2 = best_log2;
+    const size_t smem = fixed + ((size_t)4 << best_log2);
+    JV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    JV_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kQThreads, smem));
+    if (occ < 1) {
+        set_error("search (8-bit table): kernel does not fit on an SM (smem %zu)", smem);
+        return JV_ERR_UNSUPPORTED;
+    }
+    int grid = ix->sm_count * occ;
+    if (grid > p.nq) grid = p.nq;
+    JV_CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(int), ctx->stream));
+    kern<<<grid, kQThreads, smem, ctx->stream>>>(p);
+    JV_CUDA_TRY(cudaGetLastError());
+    return JV_OK;
+}
+
+bool q8_search_supported(const jv_index *ix, int L, int R) {
+    if (!ix->has_pq || !ix->q8_ok) return false;
+    const size_t fixed = (size_t)ix->q8_nj * 8192 + (size_t)L * 16 + (size_t)kQMaxE * R * 8 + (size_t)kQW * 32 * 4;
+    return fixed + 4096 + 2048 <= 227 * 1024;
+}
+
+// LUT build + traversal for queries [0, nq) in chunks bounded by the table staging buffer
+int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches) {
+    const int lutb = ix->q8_nj * 8192;
+    // staging buffer: <= 512 MB of tables per chunk (10 922 queries at M = 192)
+    int chunk = (int)((size_t)512 * 1024 * 1024 / (size_t)lutb);
+    if (const char *e = getenv("JVGPU_Q8_CHUNK")) { // test knob: force small chunks
+        const int v = atoi(e);
+        if (v > 0 && v < chunk) chunk = v;
+    }
+    if (chunk > a.nq) chunk = a.nq;
+    if (chunk < 1) chunk = 1;
+    JV_TRY(ctx->lut8.ensure((size_t)chunk * lutb));
+    JV_TRY(ctx->qparams.ensure((size_t)chunk * sizeof(float4)));
+    JV_TRY(ctx->counter.ensure(sizeof(int)));
+    int E = a.expand_width <= 0 ? kQMaxE : (a.expand_width > kQMaxE ? kQMaxE : a.expand_width);
+    for (int q0 = 0; q0 < a.nq; q0 += chunk) {
+        const int nqc = a.nq - q0 < chunk ? a.nq - q0 : chunk;
+        JV_TRY(launch_lut_q8(ix, ctx->stream, a.d_queries + (int64_t)q0 * ix->dim, nqc, ctx->lut8.as<uint8_t>(), ctx->qparams.as<float4>()));
+        if (q0 == 0) {
+            JV_CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
+            ctx->lut_timed = true;
+        }
+        Q8Params p;
+        memset(&p, 0, sizeof(p));
+        p.adjacency = ix->adjacency.as<int32_t>();
+        p.codes_q8 = ix->codes_q8.as<uint8_t>();
+        p.node_norm = ix->node_norm.as<float>();
+        p.lut = ctx->lut8.as<uint8_t>();
+        p.qparams = ctx->qparams.as<float4>();
+        p.approx_keys = a.d_approx_keys + (int64_t)q0 * a.rerank_k;
+        p.approx_count = a.d_approx_count + q0;
+        p.stats = a.d_stats ? a.d_stats + q0 : nullptr;
+        p.work_counter = ctx->counter.as<int>();
+        p.dbg = ix->dbg.as<int>();
+        p.n = ix->n;
+        p.nq = nqc;
+        p.L = a.rerank_k;
+        p.R = ix->R;
+        p.entry = a.entry_override >= 0 ? a.entry_override : ix->entry;
+        p.sim = ix->sim;
+        p.NJ = ix->q8_nj;
+        p.lutb = lutb;
+        p.E = E;
+        p.surv_cap = E * ((ix->R + 31) / 32) * 32;
+        int32_t st;
+        switch (ix->q8_nj) {
+        case 1: st = launch_q8_typed<1>(ix, ctx, p); break;
+        case 2: st = launch_q8_typed<2>(ix, ctx, p); break;
+        case 3: st = launch_q8_typed<3>(ix, ctx, p); break;
+        case 4: st = launch_q8_typed<4>(ix, ctx, p); break;
+        case 6: st = launch_q8_typed<6>(ix, ctx, p); break;
+        case 8: st = launch_q8_typed<8>(ix, ctx, p); break;
+        default: st = launch_q8_typed<0>(ix, ctx, p); break;
+        }
+        JV_TRY(st);
+        if (launches) *launches += 2;
+    }
+    return JV_OK;
+}
+
+}  // namespace jv

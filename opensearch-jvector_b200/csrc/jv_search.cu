@@ -315,7 +315,10 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     const bool f16 = (ix->flags & JV_INDEX_FLAG_LUT_F16) != 0;
     // production path: unfiltered, threshold-free queries go to the fast kernel (jv_search_fast.cu); filters and
     // range thresholds need the reference's two-queue semantics and stay on the strict kernel below.
-    if (a.expand_width >= 0 && a.d_accept == nullptr && !(a.threshold > 0.f) && (!ix->has_pq || (p.M & 3) == 0)) {
+    const bool plain = a.expand_width >= 0 && a.d_accept == nullptr && !(a.threshold > 0.f);
+    if (plain && (ix->flags & JV_INDEX_FLAG_LUT_U8) && a.d_query_ids == nullptr && q8_search_supported(ix, a.rerank_k, ix->R))
+        return launch_search_q8(ix, ctx, a, launches);
+    if (plain && (!ix->has_pq || (p.M & 3) == 0)) {
         const int32_t fs = launch_search_fast(ix, ctx, p, a.expand_width == 0 ? 4 : a.expand_width, f16);
         if (fs == JV_OK && launches) *launches += 1;
         return fs;

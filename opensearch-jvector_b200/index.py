@@ -239,6 +239,14 @@ class GpuIndex:
         N.check(N.load().jv_pq_lut(self.handle, _ptr(q), q.shape[0], _ptr(out)))
         return out
 
+    def pq_lut_q8(self, queries):
+        """8-bit ADC tables of an index created with FLAG_LUT_U8: (q8 [nq, M, 256] u8, params [nq, 2] = (delta, base))."""
+        q = _f32(np.atleast_2d(queries))
+        q8 = np.empty((q.shape[0], self.pq_m, 256), dtype=np.uint8)
+        params = np.empty((q.shape[0], 2), dtype=np.float32)
+        N.check(N.load().jv_pq_lut_q8(self.handle, _ptr(q), q.shape[0], _ptr(q8), _ptr(params)))
+        return q8, params
+
     def adc_scores(self, queries, nodes) -> np.ndarray:
         q = _f32(np.atleast_2d(queries))
         nd = np.ascontiguousarray(np.atleast_2d(nodes), dtype=np.int32)

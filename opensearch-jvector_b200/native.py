@@ -11,7 +11,7 @@ LIB_PATH = _HERE / "lib" / "libjvgpu.so"
 JV_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_INTERNAL = -1, -2, -3, -4, -5
 SIM_EUCLIDEAN, SIM_DOT, SIM_COSINE, SIM_MIP = 0, 1, 2, 3
-FLAG_FUSED_LAYOUT, FLAG_LUT_F16, FLAG_NO_VECTORS_ON_DEVICE = 1, 2, 4
+FLAG_FUSED_LAYOUT, FLAG_LUT_F16, FLAG_NO_VECTORS_ON_DEVICE, FLAG_LUT_U8 = 1, 2, 4, 8
 
 
 class IndexDesc(C.Structure):
@@ -31,7 +31,7 @@ class QueryStats(C.Structure):
 
 class BatchTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("search_ms", C.c_float), ("rerank_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("total_ms", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("total_ms", C.c_float), ("launches", C.c_int32), ("lut_ms", C.c_float)]
 
 
 class SearchParams(C.Structure):
@@ -57,6 +57,7 @@ SYMBOLS = {
     "jv_pq_encode": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "jv_pq_encode_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "jv_pq_lut": (_I32, [_P, _P, _I32, _P]),
+    "jv_pq_lut_q8": (_I32, [_P, _P, _I32, _P, _P]),
     "jv_pq_adc_scores": (_I32, [_P, _P, _I32, _P, _I32, _P]),
     "jv_merge_topk": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "jv_merge_topk_dev": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),

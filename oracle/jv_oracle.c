@@ -387,6 +387,103 @@ static inline float adc_score(int sim, const float *lut, int M, int K, const uin
 }
 
 /* ------------------------------------------------------------------------------------------
+ * 8-bit quantised ADC table ("adc_order = -8"): the GPU production traversal keeps the per-query table as
+ * bytes (one shared scale per query) and sums integers, as jVector's fused-ADC / FAISS fast-scan style
+ * scorers do.  Scores only steer the traversal; returned scores come from the exact rerank.
+ *   ball_m   = bounding ball (centre, radius) of subspace m's centroids            (index constant)
+ *   [lo_m, hi_m] = bound on the table row m from the ball: dot  q_m.ctr_m -/+ |q_m| r_m,
+ *                                                          L2   (max(0, |q_m-ctr_m| - r_m))^2 .. (|q_m-ctr_m| + r_m)^2
+ *   range = max_m (hi_m - lo_m);  inv = 255/range;  delta = range/255;  base = sum_m lo_m  (in m order)
+ *   q8[m][c] = sat_u8(rint(fmaf(lut[m][c], inv, -(lo_m*inv))))
+ *   partial-sum estimate = fmaf(delta, (float)sum_m q8[m][code_m], base)
+ * The device kernel (jv_lut_q8.cu) performs exactly these operations, so tables and sums are bit-identical.
+ * ------------------------------------------------------------------------------------------ */
+static void pq_ball(const pq_shape *s, const float *codebooks, float *ctr, float *rad) {
+    for (int m = 0; m < s->M; m++) {
+        const float *cb = codebooks + s->cb_off[m];
+        const int len = s->size[m];
+        for (int j = 0; j < len; j++) {
+            double acc = 0.0;
+            for (int c = 0; c < s->K; c++) acc += (double)cb[(int64_t)c * len + j];
+            ctr[s->off[m] + j] = (float)(acc / (double)s->K);
+        }
+        double r2max = 0.0;
+        for (int c = 0; c < s->K; c++) {
+            double r2 = 0.0;
+            for (int j = 0; j < len; j++) {
+                double d = (double)cb[(int64_t)c * len + j] - (double)ctr[s->off[m] + j];
+                r2 += d * d;
+            }
+            if (r2 > r2max) r2max = r2;
+        }
+        rad[m] = (float)sqrt(r2max) * 1.0009765625f; /* 2^-10 slack over the rounded radius */
+    }
+}
+
+/* lo[m], returns range; qq = (centred) query */
+static float q8_bounds(const pq_shape *s, int sim, const float *qq, const float *ctr, const float *rad, float *lo) {
+    float range = 0.f;
+    for (int m = 0; m < s->M; m++) {
+        const float *x = qq + s->off[m], *c = ctr + s->off[m];
+        const int len = s->size[m];
+        float l, h;
+        if (sim == JV_SIM_EUCLIDEAN) {
+            const float d = sqrtf(sub_l2sq(x, c, len));
+            float a = d - rad[m];
+            if (a < 0.f) a = 0.f;
+            const float b = d + rad[m];
+            l = a * a;
+            h = b * b;
+        } else {
+            const float w = sqrtf(sub_dot(x, x, len)) * rad[m];
+            const float qc = sub_dot(x, c, len);
+            l = qc - w;
+            h = qc + w;
+        }
+        lo[m] = l;
+        const float r = h - l;
+        if (r > range) range = r;
+    }
+    return range;
+}
+
+static inline uint8_t sat_u8_rn(float x) {
+    if (!(x > 0.f)) return 0; /* also NaN */
+    if (x >= 255.f) return 255;
+    return (uint8_t)(int)rintf(x);
+}
+
+/* lut (fp32, [M][K]) -> q8 [M][K]; params[0] = delta, params[1] = base */
+static void q8_quantise(const pq_shape *s, int sim, const float *qq, const float *ctr, const float *rad, const float *lut,
+                        uint8_t *q8, float *lo_scratch, float *params) {
+    const float range = q8_bounds(s, sim, qq, ctr, rad, lo_scratch);
+    const float inv = range > 0.f ? 255.0f / range : 0.f;
+    float base = 0.f;
+    for (int m = 0; m < s->M; m++) base += lo_scratch[m];
+    for (int m = 0; m < s->M; m++) {
+        const float nlo = -(lo_scratch[m] * inv);
+        for (int c = 0; c < s->K; c++) q8[m * s->K + c] = sat_u8_rn(fmaf(lut[m * s->K + c], inv, nlo));
+    }
+    params[0] = range / 255.0f;
+    params[1] = base;
+}
+
+static inline float adc_score_q8(int sim, const uint8_t *q8, const float *params, int M, int K, const uint8_t *code,
+                                 float node_norm, float qnorm) {
+    uint32_t isum = 0;
+    for (int m = 0; m < M; m++) isum += q8[m * K + code[m]];
+    const float s = fmaf(params[0], (float)isum, params[1]);
+    switch (sim) {
+    case JV_SIM_EUCLIDEAN:
+        return 1.0f / (1.0f + s);
+    case JV_SIM_COSINE:
+        return (1.0f + s / sqrtf(node_norm * qnorm)) * 0.5f;
+    default:
+        return (1.0f + s) * 0.5f;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Index view + per-thread search scratch
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -395,6 +492,7 @@ typedef struct {
     int has_pq;
     int adc_order;    /* see adc_sum */
     float *node_norm; /* cosine + PQ only */
+    float *ball_ctr, *ball_rad; /* adc_order -8 only */
 } jvo_index;
 
 JVO_EXPORT jvo_index *jvo_index_create(const jv_index_desc *desc) {
@@ -411,11 +509,20 @@ JVO_EXPORT jvo_index *jvo_index_create(const jv_index_desc *desc) {
     }
     return ix;
 }
-JVO_EXPORT void jvo_index_set_adc_order(jvo_index *ix, int32_t order) { ix->adc_order = order; }
+JVO_EXPORT void jvo_index_set_adc_order(jvo_index *ix, int32_t order) {
+    ix->adc_order = order;
+    if (order == -8 && ix->has_pq && !ix->ball_ctr) {
+        ix->ball_ctr = (float *)malloc(sizeof(float) * (size_t)ix->d.dim);
+        ix->ball_rad = (float *)malloc(sizeof(float) * (size_t)ix->d.pq_m);
+        pq_ball(&ix->pq, ix->d.pq_codebooks, ix->ball_ctr, ix->ball_rad);
+    }
+}
 JVO_EXPORT void jvo_index_destroy(jvo_index *ix) {
     if (!ix) return;
     if (ix->has_pq) pq_shape_free(&ix->pq);
     free(ix->node_norm);
+    free(ix->ball_ctr);
+    free(ix->ball_rad);
     free(ix);
 }
 
@@ -425,6 +532,8 @@ typedef struct {
     int32_t *touched;
     int ntouched, touched_cap;
     float *lut, *qc;
+    uint8_t *lut8; /* adc_order -8 */
+    float *lo8, q8p[2];
     uint64_t *sorted;
 } scratch_t;
 
@@ -433,7 +542,11 @@ static scratch_t *scratch_new(const jvo_index *ix) {
     s->visited = (uint64_t *)calloc((size_t)((ix->d.n + 63) / 64), 8);
     s->touched_cap = 4096;
     s->touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)s->touched_cap);
-    if (ix->has_pq) s->lut = (float *)malloc(sizeof(float) * (size_t)ix->d.pq_m * ix->d.pq_k);
+    if (ix->has_pq) {
+        s->lut = (float *)malloc(sizeof(float) * (size_t)ix->d.pq_m * ix->d.pq_k);
+        s->lut8 = (uint8_t *)malloc((size_t)ix->d.pq_m * ix->d.pq_k);
+        s->lo8 = (float *)malloc(sizeof(float) * (size_t)ix->d.pq_m);
+    }
     s->qc = (float *)malloc(sizeof(float) * (size_t)ix->d.dim);
     return s;
 }
@@ -443,6 +556,8 @@ static void scratch_free(scratch_t *s) {
     free(s->visited);
     free(s->touched);
     free(s->lut);
+    free(s->lut8);
+    free(s->lo8);
     free(s->qc);
     free(s->sorted);
     free(s);
@@ -472,6 +587,23 @@ static inline int accepted(const jvo_index *ix, const uint64_t *bits, int32_t or
     return (int)((bits[doc >> 6] >> (doc & 63)) & 1ULL);
 }
 
+/* builds S->lut (and, for adc_order -8, S->lut8 + S->q8p) for one query */
+static void build_tables(const jvo_index *ix, scratch_t *S, const float *q) {
+    const jv_index_desc *d = &ix->d;
+    pq_build_lut(&ix->pq, d->similarity, d->pq_codebooks, d->pq_global_centroid, q, S->lut, S->qc);
+    if (ix->adc_order == -8) {
+        const float *qq = (d->similarity == JV_SIM_EUCLIDEAN && d->pq_global_centroid) ? S->qc : q;
+        q8_quantise(&ix->pq, d->similarity, qq, ix->ball_ctr, ix->ball_rad, S->lut, S->lut8, S->lo8, S->q8p);
+    }
+}
+static inline float approx_score(const jvo_index *ix, const scratch_t *S, int32_t node, float qnorm) {
+    const jv_index_desc *d = &ix->d;
+    const float nn = ix->node_norm ? ix->node_norm[node] : 0.f;
+    const uint8_t *code = d->pq_codes + (int64_t)node * d->pq_m;
+    if (ix->adc_order == -8) return adc_score_q8(d->similarity, S->lut8, S->q8p, d->pq_m, d->pq_k, code, nn, qnorm);
+    return adc_score(d->similarity, S->lut, d->pq_m, d->pq_k, code, nn, qnorm, ix->adc_order);
+}
+
 /* ------------------------------------------------------------------------------------------
  * GraphSearcher.search for ONE query on the flat (level-0) graph, followed by the
  * rerank step, ordinal->doc mapping and collector ordering — i.e. JVectorReader.search,
@@ -487,11 +619,10 @@ static void search_one(const jvo_index *ix, scratch_t *S, const float *q, int k,
     const int use_pq = ix->has_pq;
     const float qnorm = canon_dot(q, q, dim);
     const float mip_mul = (sim == JV_SIM_MIP && !use_pq) ? 2.0f : 1.0f; /* wrapExactScoreFunction, :220-239 */
-    if (use_pq) pq_build_lut(&ix->pq, sim, d->pq_codebooks, d->pq_global_centroid, q, S->lut, S->qc);
+    if (use_pq) build_tables(ix, S, q);
 
 #define APPROX(node)                                                                                                    \
-    (use_pq ? adc_score(sim, S->lut, d->pq_m, d->pq_k, d->pq_codes + (int64_t)(node) * d->pq_m,                          \
-                        ix->node_norm ? ix->node_norm[node] : 0.f, qnorm, ix->adc_order)                                 \
+    (use_pq ? approx_score(ix, S, (node), qnorm)                                                                        \
             : exact_score(sim, q, qnorm, d->vectors + (int64_t)(node) * dim, dim) * mip_mul)
 
     S->cand.n = 0;
@@ -619,15 +750,28 @@ JVO_EXPORT void jvo_pq_adc_scores(const jvo_index *ix, const float *queries, int
     for (int i = 0; i < nq; i++) {
         const float *q = queries + (int64_t)i * d->dim;
         float qnorm = canon_dot(q, q, d->dim);
-        pq_build_lut(&ix->pq, d->similarity, d->pq_codebooks, d->pq_global_centroid, q, S->lut, S->qc);
+        build_tables(ix, S, q);
         for (int j = 0; j < per_query; j++) {
             int32_t node = nodes[(int64_t)i * per_query + j];
-            out[(int64_t)i * per_query + j] =
-                adc_score(d->similarity, S->lut, d->pq_m, d->pq_k, d->pq_codes + (int64_t)node * d->pq_m,
-                          ix->node_norm ? ix->node_norm[node] : 0.f, qnorm, ix->adc_order);
+            out[(int64_t)i * per_query + j] = approx_score(ix, S, node, qnorm);
         }
     }
     scratch_free(S);
+}
+
+/* K1 (8-bit): out_q8 [nq][M][K] in logical (m, c) order, out_params [nq][2] = (delta, base) */
+JVO_EXPORT int32_t jvo_pq_lut_q8(const jvo_index *ix, const float *queries, int32_t nq, uint8_t *out_q8, float *out_params) {
+    if (!ix->has_pq || ix->adc_order != -8) return -1;
+    scratch_t *S = scratch_new(ix);
+    const size_t mk = (size_t)ix->d.pq_m * ix->d.pq_k;
+    for (int i = 0; i < nq; i++) {
+        build_tables(ix, S, queries + (int64_t)i * ix->d.dim);
+        memcpy(out_q8 + (size_t)i * mk, S->lut8, mk);
+        out_params[2 * i] = S->q8p[0];
+        out_params[2 * i + 1] = S->q8p[1];
+    }
+    scratch_free(S);
+    return 0;
 }
 
 /* K5: brute-force exact top-k = Lucene exactSearch over JVectorVectorScorer.score()

@@ -247,6 +247,17 @@ class OracleIndex:
         lib().jvo_pq_adc_scores(C.c_void_p(self._h), _p(q), C.c_int32(q.shape[0]), _p(nd), C.c_int32(nd.shape[1]), _p(out))
         return out
 
+    def lut_q8(self, queries):
+        """8-bit ADC tables (adc_order = -8): (q8 [nq, M, K] u8, params [nq, 2] = (delta, base))."""
+        q = _f32(np.atleast_2d(queries))
+        m, k = self.desc.pq_m, self.desc.pq_k
+        q8 = np.empty((q.shape[0], m, k), dtype=np.uint8)
+        params = np.empty((q.shape[0], 2), dtype=np.float32)
+        rc = lib().jvo_pq_lut_q8(C.c_void_p(self._h), _p(q), C.c_int32(q.shape[0]), _p(q8), _p(params))
+        if rc != 0:
+            raise ValueError("lut_q8 needs a PQ index created with adc_order=-8")
+        return q8, params
+
     def exact_topk(self, queries, k: int, accept_bits=None, threads: int = 0):
         q = _f32(np.atleast_2d(queries))
         nq = q.shape[0]

@@ -47,6 +47,21 @@ def clustered(n: int, dim: int, nq: int, seed: int, clusters: int = 32, spread: 
     return base, qs
 
 
+def embedded(n: int, dim: int, nq: int, seed: int, latent: int = 24, clusters: int = 32):
+    """Embedding-shaped data (bench.py gen_data at test scale): a Gaussian mixture in a `latent`-d space mapped into
+    `dim` dimensions by a fixed random map plus small isotropic noise, L2-normalised."""
+    rng = np.random.default_rng(seed)
+    W = (rng.standard_normal((latent, dim)) / np.sqrt(latent)).astype(np.float32)
+    cent = rng.standard_normal((clusters, latent)).astype(np.float32)
+
+    def draw(m):
+        z = cent[rng.integers(0, clusters, m)] + 0.6 * rng.standard_normal((m, latent)).astype(np.float32)
+        x = z @ W + 0.02 * rng.standard_normal((m, dim)).astype(np.float32)
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+    return draw(n), draw(nq)
+
+
 def make_fixture(sim: int, base: np.ndarray, queries: np.ndarray, max_degree: int = 16, beam_width: int = 100, pq_m: int = 0,
                  pq_k: int = 256, ord_to_doc=None, max_doc=None, seed: int = 7) -> Fixture:
     """Segment built entirely by the oracle's fixture builders (CPU): graph + optional PQ."""

@@ -1,0 +1,151 @@
+"""The production traversal with the 8-bit quantised ADC table (JV_INDEX_FLAG_LUT_U8, csrc/jv_q8.cu).
+
+* K1: the batched table kernel must reproduce the oracle's quantised tables and (delta, base) bit for bit.
+* K2: integer sums are order-independent, so at expand_width = 1 the traversal is the oracle's (adc_order = -8) best-first
+  order up to score ties at the list boundary (integer sums tie more often than fp32 ones): ids identical for almost
+  every query; for wider expansion the north-star gate applies (recall@10 within 0.005 at bench scale; unit-test
+  fixtures of 64..100 queries have a sampling error of ~0.01).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import clustered, embedded, make_fixture, recall
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx_dot():  # sub-dim 4, M = 16 (half a bank block)
+    base, q = clustered(8000, 64, 100, seed=41, normalize=True)
+    return make_fixture(O.SIM_DOT, base, q, max_degree=32, pq_m=16)
+
+
+@pytest.fixture(scope="module")
+def fx_l2():  # sub-dim 2, M = 48 (1.5 bank blocks), centred codebooks
+    base, q = clustered(6000, 96, 64, seed=42)
+    return make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=16, pq_m=48)
+
+
+@pytest.fixture(scope="module")
+def fx_cos8():  # sub-dim 8
+    base, q = clustered(4000, 128, 64, seed=43)
+    return make_fixture(O.SIM_COSINE, base, q, max_degree=16, pq_m=16)
+
+
+@pytest.fixture(scope="module")
+def fx_dot192():  # the cfg-2 shape at test scale: 768-d, M = 192 (6 bank blocks), R = 32
+    base, q = embedded(5000, 768, 64, seed=44)
+    return make_fixture(O.SIM_DOT, base, q, max_degree=32, pq_m=192)
+
+
+ALL = ["fx_dot", "fx_l2", "fx_cos8", "fx_dot192"]
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_quantised_tables_match_oracle_bit_for_bit(jv, request, name):
+    fx = request.getfixturevalue(name)
+    ora = fx.oracle_index(adc_order=-8)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        nq = min(len(fx.queries), 37)  # not a multiple of the queries-per-CTA tile
+        q8, prm = gi.pq_lut_q8(fx.queries[:nq])
+        w8, wprm = ora.lut_q8(fx.queries[:nq])
+        np.testing.assert_array_equal(prm.view(np.uint32), wprm.view(np.uint32))
+        np.testing.assert_array_equal(q8, w8)
+        assert q8.max() > 128  # the shared scale is actually used
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_width1_follows_the_oracle_order(jv, request, name):
+    fx = request.getfixturevalue(name)
+    ora = fx.oracle_index(adc_order=-8)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        gt, _, _ = gi.exact_topk(fx.queries, 10)
+        for k, rk in ((10, 50), (1, 1), (20, 200)):
+            r = gi.search(fx.queries, k, rk, expand_width=1)
+            wd, ws, wc, wst = ora.search(fx.queries, k, rk)
+            np.testing.assert_array_equal(r.counts, wc)
+            same = np.mean([np.array_equal(a, b) for a, b in zip(r.docs, wd)])
+            assert same >= 0.9, same
+            # returned scores are exact-rerank scores: identical wherever the same doc is returned
+            for i in range(len(fx.queries)):
+                ref = {int(d): s for d, s in zip(wd[i], ws[i]) if d >= 0}
+                for d, s in zip(r.docs[i], r.scores[i]):
+                    if int(d) in ref:
+                        assert s == ref[int(d)]
+            if k == 10:
+                assert recall(r.docs, gt) >= recall(wd, gt) - 0.01
+                # ties at the list boundary change the expansion count by a few nodes at most
+                assert abs(r.stats[:, 1].mean() - wst[:, 1].mean()) <= 0.05 * wst[:, 1].mean() + 1
+                assert r.stats[:, 0].mean() <= 1.2 * wst[:, 0].mean() + 4  # re-scored nodes (filter evictions) count as visits
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("width", [0, 2, 4])
+def test_wide_expansion_recall_parity(jv, request, name, width):
+    fx = request.getfixturevalue(name)
+    ora = fx.oracle_index()  # the reference path: fp32 table
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        gt, _, _ = gi.exact_topk(fx.queries, 10)
+        r = gi.search(fx.queries, 10, 50, expand_width=width)
+        wd, ws, wc, wst = ora.search(fx.queries, 10, 50)
+        assert recall(r.docs, gt) >= recall(wd, gt) - 0.015
+        np.testing.assert_array_equal(r.counts, wc)
+        assert (r.stats[:, 3] == 50).all()  # everything in the approximate list is reranked (floor 0)
+        r2 = gi.search(fx.queries, 10, 50, expand_width=width)
+        np.testing.assert_array_equal(r.docs, r2.docs)  # integer sums: run-to-run deterministic results
+        np.testing.assert_array_equal(r.scores, r2.scores)
+
+
+def test_large_rerank_k_and_chunked_batches(jv, fx_l2, monkeypatch):
+    fx = fx_l2
+    ora = fx.oracle_index()
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        gt, _, _ = gi.exact_topk(fx.queries, 100)
+        r = gi.search(fx.queries, 100, 500)  # cfg 5 flavour: k = 100, rerankK = 500
+        wd = ora.search(fx.queries, 100, 500)[0]
+        assert recall(r.docs, gt) >= recall(wd, gt) - 0.005
+        assert (r.counts == 100).all()
+        a = gi.search(fx.queries, 10, 50)
+        monkeypatch.setenv("JVGPU_Q8_CHUNK", "7")  # table staging buffer of 7 queries: 10 chunks for 64 queries
+        b = gi.search(fx.queries, 10, 50)
+        monkeypatch.delenv("JVGPU_Q8_CHUNK")
+        np.testing.assert_array_equal(a.docs, b.docs)
+        np.testing.assert_array_equal(a.scores, b.scores)
+        np.testing.assert_array_equal(a.stats[:, 1:], b.stats[:, 1:])
+
+
+def test_filters_and_unsupported_shapes_fall_back(jv, fx_l2):
+    fx = fx_l2
+    ora = fx.oracle_index(adc_order=32)
+    bits = O.make_accept_bits(np.random.default_rng(1).random(fx.base.shape[0]) < 0.3)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:  # filtered queries: strict kernel, fp32 table
+        r = gi.search(fx.queries, 10, 50, accept_bits=bits)
+        wd, ws, wc, _ = ora.search(fx.queries, 10, 50, accept_bits=bits)
+        np.testing.assert_array_equal(r.docs, wd)
+        np.testing.assert_array_equal(r.counts, wc)
+    # non-uniform sub-vectors (dim 30, M = 4 -> sizes 8,8,7,7): no 8-bit path, the flag is ignored
+    base, q = clustered(3000, 30, 32, seed=5)
+    odd = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=16, pq_m=4)
+    with odd.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        r = gi.search(q, 10, 50, expand_width=1)
+        wd = odd.oracle_index(adc_order=1).search(q, 10, 50)[0]
+        np.testing.assert_array_equal(r.docs, wd)
+        with pytest.raises(ValueError):
+            gi.pq_lut_q8(q)
+
+
+def test_single_query_and_tiny_graph(jv, fx_dot):
+    with fx_dot.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        one = gi.search(fx_dot.queries[:1], 10, 50)
+        many = gi.search(fx_dot.queries, 10, 50)
+        np.testing.assert_array_equal(one.docs[0], many.docs[0])
+    base, q = clustered(300, 16, 4, seed=3)  # K = 256 needs n >= 256
+    small = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=8, pq_m=8)
+    with small.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        r = gi.search(q, 10, 400)  # rerankK larger than the graph: every node ends up in the list
+        wd, ws, wc, _ = small.oracle_index(adc_order=-8).search(q, 10, 400)
+        np.testing.assert_array_equal(r.docs, wd)
+        np.testing.assert_array_equal(r.counts, wc)
