@@ -595,7 +595,7 @@ int32_t jv_pq_lut_q8(jv_index *ix, const float *queries, int32_t nq, uint8_t *ou
     JV_REQUIRE(ix->has_pq && ix->q8_ok, "index was not created with JV_INDEX_FLAG_LUT_U8 (or its PQ shape is not supported by the 8-bit table)");
     if (nq == 0) return JV_OK;
     DeviceGuard guard(ix->device);
-    const int M = ix->pq.M, lutb = ix->q8_nj * 8192;
+    const int M = ix->pq.M, lutb = q8_lut_bytes(ix->q8_nj);
     DevBuf dq, dl, dp;
     JV_TRY(dq.alloc((size_t)nq * ix->dim * 4));
     JV_TRY(dl.alloc((size_t)nq * lutb));
@@ -607,11 +607,13 @@ int32_t jv_pq_lut_q8(jv_index *ix, const float *queries, int32_t nq, uint8_t *ou
     std::vector<float> prm((size_t)nq * 4);
     JV_CUDA_TRY(cudaMemcpy(raw.data(), dl.p, raw.size(), cudaMemcpyDeviceToHost));
     JV_CUDA_TRY(cudaMemcpy(prm.data(), dp.p, prm.size() * 4, cudaMemcpyDeviceToHost));
-    for (int q = 0; q < nq; q++) { // undo the bank-interleaved layout: (m, c) -> ((m/32)*64 + c/4)*128 + (m%32)*4 + c%4
+    for (int q = 0; q < nq; q++) { // undo the bank-interleaved layout (header of jv_q8.cu)
         const uint8_t *t = raw.data() + (size_t)q * lutb;
-        for (int m = 0; m < M; m++)
+        for (int m = 0; m < M; m++) {
+            const int j = m >> 5;
             for (int c = 0; c < 256; c++)
-                out_q8[((size_t)q * M + m) * 256 + c] = t[((size_t)(m >> 5) * 64 + (c >> 2)) * 128 + (m & 31) * 4 + (c & 3)];
+                out_q8[((size_t)q * M + m) * 256 + c] = t[(size_t)(j >> 1) * 16384 + (size_t)(c & 63) * 256 + (j & 1) * 128 + (m & 31) * 4 + (c >> 6)];
+        }
         out_params[2 * q] = prm[4 * (size_t)q];
         out_params[2 * q + 1] = prm[4 * (size_t)q + 1];
     }

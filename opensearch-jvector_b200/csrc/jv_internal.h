@@ -78,6 +78,7 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
 
 // K1+K2 with the 8-bit table (jv_q8.cu)
 bool q8_search_supported(const jv_index *ix, int L, int R);
+int q8_lut_bytes(int nj); // table bytes per query in the bank-interleaved layout
 int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches);
 int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, uint8_t *d_lut, float4 *d_qparams);
 int32_t launch_permute_codes(cudaStream_t stream, const uint8_t *d_codes, int64_t n, int M, int stride, int NJ, uint8_t *d_out);

@@ -12,12 +12,16 @@
 //                     copy (cp.async.bulk + mbarrier); 4 CTAs share an SM.  Per step every warp expands one candidate:
 //                     reads its adjacency row (128 B, coalesced), tests the visited filter, and scores its own fresh
 //                     neighbours — 8 lanes per code row, 4 rows per warp at a time, table lookups bank-conflict-free by
-//                     construction.  Survivors are merged into the sorted list once per step (2 block barriers / step).
+//                     construction.  Neighbours that beat the list's worst entry are queued and rank-merged into the
+//                     sorted list once per step (re-scored duplicates dropped; 3 block barriers / step).  For DOT /
+//                     EUCLIDEAN the list is ordered by the integer sum itself (no float arithmetic per row).
 //
-// Table layout in shared memory (and in the HBM staging buffer):  byte (m, c)  ->  ((m/32)*64 + c/4)*128 + (m%32)*4 + c%4
-// i.e. bank = m % 32.  Code rows are stored permuted (codes_q8): lane sl of a row group owns subspaces m = 8t + sl, its
-// 4*NJ bytes contiguous, so at lookup t the 8 lanes of a group hit 8 different banks and the 4 groups of a warp are
-// rotated onto the 4 different bank quarters.
+// Table layout in shared memory (and in the HBM staging buffer), j = m / 32:
+//     byte (m, c)  ->  (j / 2) * 16384 + (c % 64) * 256 + (j % 2) * 128 + (m % 32) * 4 + c / 64
+// i.e. bank = m % 32 and the offset of code c inside its bank column is ((c & 63) << 8) | (c >> 6): one PRMT (byte 0 from
+// cw >> 6, byte 1 from cw) + one LOP3 ((v & 0x3F03) | lane base) per lookup.  Code rows are stored permuted (codes_q8):
+// lane sl of a row group owns subspaces m = 8t + sl, its 4*NJ bytes contiguous, so at lookup t the 8 lanes of a group hit
+// 8 different banks and the 4 groups of a warp are rotated onto the 4 different bank quarters.
 #include <stdlib.h>
 
 #include "jv_search_common.cuh"
@@ -91,9 +95,9 @@ int32_t launch_permute_codes(cudaStream_t stream, const uint8_t *d_codes, int64_
 struct LutQ8Params {
     const float *queries; // [nq][dim]
     const float *codebooks, *gcent, *ball_ctr, *ball_rad;
-    uint8_t *lut;   // [nq][NJ*8192]
+    uint8_t *lut;   // [nq][lutb]
     float4 *qparams; // [nq] (delta, base, ||q||^2, 0)
-    int nq, dim, M, NJ, sim;
+    int nq, dim, M, NJ, sim, lutb;
 };
 
 template <int S>
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
     constexpr int PIECES = 128 / PB;           // per subspace per chunk
     constexpr int ROWB = 128 + (S == 2 ? 8 : 16); // padded row: conflict-free vector reads at lane stride
     constexpr int NCHUNK = 256 / CH;
+    constexpr int EP = CH / 4;                 // consecutive codes per 64-code quarter in a chunk (32 B per quarter)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int MP = p.NJ * 32;
@@ -202,15 +207,18 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
             inv[t] = inv_s[t];
             nlo[t] = -__fmul_rn(lo_s[t * MP + m], inv[t]);
         }
+        // a chunk holds, for each of the 32 subspaces, the codes {q*64 + ch*EP + e : q < 4, e < EP}: the 4 codes that
+        // share one table word ((c & 63) fixed, byte = c >> 6) sit in the same chunk
         auto issue = [&](int ch, int buf) {
 #pragma unroll
             for (int r = 0; r < PIECES; r++) {
                 const int pid = lane + 32 * r;
                 const int b = pid / PIECES, piece = pid % PIECES;
+                const int quarter = piece / (PIECES / 4), within = piece % (PIECES / 4);
                 const int mm = j * 32 + b;
                 if (mm < p.M)
                     cp_async<PB>(stage + (size_t)(buf * 32 + b) * ROWB + piece * PB,
-                                 reinterpret_cast<const unsigned char *>(p.codebooks + ((int64_t)mm * 256 + ch * CH) * S) + piece * PB);
+                                 reinterpret_cast<const unsigned char *>(p.codebooks + ((int64_t)mm * 256 + quarter * 64 + ch * EP) * S) + within * PB);
             }
             cp_async_commit();
         };
@@ -226,14 +234,14 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
             __syncwarp();
             const unsigned char *row = stage + (size_t)(buf * 32 + lane) * ROWB;
 #pragma unroll
-            for (int c4 = 0; c4 < CH / 4; c4++) {
+            for (int e = 0; e < EP; e++) {
                 uint32_t w[QT];
 #pragma unroll
                 for (int t = 0; t < QT; t++) w[t] = 0u;
 #pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
+                for (int quarter = 0; quarter < 4; quarter++) {
                     float cv[S];
-                    const unsigned char *cp = row + (c4 * 4 + cc) * S * 4;
+                    const unsigned char *cp = row + (quarter * EP + e) * S * 4;
                     if (S == 2) {
                         const float2 v = *reinterpret_cast<const float2 *>(cp);
                         cv[0] = v.x, cv[1] = v.y;
@@ -256,20 +264,22 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
                                 acc = __fmaf_rn(qr[t][jj], cv[jj], acc);
                             }
                         }
-                        w[t] |= sat_u8_rn(__fmaf_rn(acc, inv[t], nlo[t])) << (8 * cc);
+                        w[t] |= sat_u8_rn(__fmaf_rn(acc, inv[t], nlo[t])) << (8 * quarter);
                     }
                 }
-                const int c4g = ch * (CH / 4) + c4; // = c >> 2
+                const int c6 = ch * EP + e; // = c & 63
+                const size_t word = ((size_t)(j >> 1) * 16384 + (size_t)c6 * 256 + (size_t)(j & 1) * 128) / 4 + lane;
 #pragma unroll
                 for (int t = 0; t < QT; t++) {
-                    if (q0 + t < p.nq)
-                        reinterpret_cast<uint32_t *>(p.lut + (int64_t)(q0 + t) * p.NJ * 8192)[(j * 64 + c4g) * 32 + lane] = m < p.M ? w[t] : 0u;
+                    if (q0 + t < p.nq) reinterpret_cast<uint32_t *>(p.lut + (int64_t)(q0 + t) * p.lutb)[word] = m < p.M ? w[t] : 0u;
                 }
             }
             __syncwarp(); // the buffer is refilled two iterations from now
         }
     }
 }
+
+int q8_lut_bytes(int nj) { return ((nj + 1) / 2) * 16384; }
 
 static size_t lut_q8_smem(int nw, int S, int MP) {
     const int rowb = 128 + (S == 2 ? 8 : 16), qt = S == 2 ? 8 : 32 / S;
@@ -291,6 +301,7 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
     p.M = ix->pq.M;
     p.NJ = ix->q8_nj;
     p.sim = ix->sim;
+    p.lutb = q8_lut_bytes(ix->q8_nj);
     const int S = ix->dim / ix->pq.M;
     const int nw = p.NJ < 8 ? p.NJ : 8;
     const size_t smem = lut_q8_smem(nw, S, p.NJ * 32);
@@ -332,24 +343,13 @@ struct Q8Params {
     int nq, L, R, entry, sim, NJ, lutb, hash_log2, E, surv_cap;
 };
 
-__device__ __forceinline__ uint64_t qkey_make(float score, int32_t node) {
-    return ((uint64_t)jv_f2ord(score) << 32) | ((uint64_t)(uint32_t)(0x7fffffff - node) << 1) | 1ull;
+// list key: order word (32 bits) | (0x7fffffff - node) << 1 | unexpanded.  The order word is the integer ADC sum itself
+// for DOT/MIP (larger = better), its complement for EUCLIDEAN, and the ordered-float score for COSINE (the cosine
+// decoder divides by the node norm, so its order is not the order of the sums).
+__device__ __forceinline__ uint64_t qkey_pack(uint32_t ord, int32_t node) {
+    return ((uint64_t)ord << 32) | ((uint64_t)(uint32_t)(0x7fffffff - node) << 1) | 1ull;
 }
 __device__ __forceinline__ int32_t qkey_node(uint64_t k) { return 0x7fffffff - (int32_t)((k >> 1) & 0x7fffffffu); }
-__device__ __forceinline__ float qkey_score(uint64_t k) { return jv_ord2f((uint32_t)(k >> 32)); }
-
-// number of list entries strictly better than `a` (= key >> 1); list sorted descending
-__device__ __forceinline__ int q_count_better(const uint64_t *list, int n, uint64_t a) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((list[mid] >> 1) > a)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
 
 // visited filter: true when `nb` was NOT present (and records it).  2 tags of 15 bits + valid bit per word; (set, tag) is
 // a bijection of the ordinal when n <= 2^(set_bits+15), so there are no false positives; evictions only cause re-scoring.
@@ -374,6 +374,7 @@ __device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, 
 template <int NJ_T>
 __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params p) {
     constexpr int U = 2; // row groups in flight per warp pass: 4 groups x U rows
+    constexpr int NJC = NJ_T > 0 ? NJ_T : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.L, E = p.E, H = 1 << p.hash_log2, R = p.R;
@@ -386,16 +387,18 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
     sp += (size_t)L * 8;
     uint64_t *list1 = reinterpret_cast<uint64_t *>(sp);
     sp += (size_t)L * 8;
-    uint64_t *surv = reinterpret_cast<uint64_t *>(sp);
+    uint64_t *surv = reinterpret_cast<uint64_t *>(sp); // queued survivors as key >> 1 (always unexpanded); 0 = dropped duplicate
     sp += (size_t)p.surv_cap * 8;
     int32_t *wids = reinterpret_cast<int32_t *>(sp) + warp * 32;
     sp += (size_t)kQW * 32 * 4;
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
 
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_query, s_ns[2], s_vis, w_sel[kQW][2 * kQMaxE], w_pos[kQW][2 * kQMaxE];
+    __shared__ int s_query, s_ns[2], s_ndup[2], s_vis, w_sel[kQW][2 * kQMaxE], w_pos[kQW][2 * kQMaxE];
 
     const bool tagged = p.n <= ((int64_t)1 << (p.hash_log2 + 15));
+    const bool isum_keys = p.sim != JV_SIM_COSINE;
+    const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
     // ADC lane geometry: group g = lane / 8 scores one code row, lane sl owns subspaces m = 8t + sl.  At lookup (j, i) the
     // group reads bank quarter (i + g) & 3, so the 32 lanes of a warp always hit 32 different banks.
     const int g = lane >> 3, sl = lane & 7;
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t qd = (uint32_t)(i + g) & 3u;
-        sel[i] = 0x4440u | qd;
+        sel[i] = 0x4400u | (qd << 4) | (4u + qd); // byte 0 <- (cw >> 6).byte[qd], byte 1 <- cw.byte[qd]
         lb[i] = qd * 32u + (uint32_t)sl * 4u;
     }
     const int seg = NJ * 4; // bytes of a code row owned by one lane
@@ -414,45 +417,31 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
     }
     uint32_t phase = 0;
 
-    // ADC sum of the code row of `nb` for this lane's subspaces (caller reduces over the 8 lanes of the group)
-    auto lookups = [&](const uint32_t *cw) -> uint32_t {
+    // table entries selected by code word j of this lane (4 subspaces); caller reduces over the 8 lanes of the group
+    auto lookup4 = [&](uint32_t cw, int j) -> uint32_t {
+        const uint32_t sh = cw >> 6;
+        const uint8_t *base = lut + (j >> 1) * 16384 + (j & 1) * 128;
         uint32_t s = 0;
 #pragma unroll
-        for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t c = __byte_perm(cw[j], 0u, sel[i]);
-                const uint32_t off = ((c & 0xFCu) << 5) + (c & 3u);
-                s += lut[j * 8192 + lb[i] + off];
-            }
+        for (int i = 0; i < 4; i++) {
+            const uint32_t v = __byte_perm(cw, sh, sel[i]);
+            s += base[(v & 0x3F03u) | lb[i]];
         }
         return s;
     };
-    auto row_sum = [&](int32_t nb) -> uint32_t { // one row per group, no batching (entry node, generic NJ)
-        uint32_t s = 0;
-        if (nb >= 0) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nb * (NJ * 32) + sl * seg);
-            if (NJ_T > 0) {
-                uint32_t cw[NJ_T > 0 ? NJ_T : 1];
-#pragma unroll
-                for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) cw[j] = __ldg(row + j);
-                s = lookups(cw);
-            } else {
-                for (int j = 0; j < NJ; j++) {
-                    const uint32_t cwj = __ldg(row + j);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint32_t c = __byte_perm(cwj, 0u, sel[i]);
-                        const uint32_t off = ((c & 0xFCu) << 5) + (c & 3u);
-                        s += lut[j * 8192 + lb[i] + off];
-                    }
-                }
-            }
-        }
+    auto reduce8 = [&](uint32_t s) -> uint32_t {
         s += __shfl_xor_sync(JV_FULL_MASK, s, 4);
         s += __shfl_xor_sync(JV_FULL_MASK, s, 2);
         s += __shfl_xor_sync(JV_FULL_MASK, s, 1);
         return s;
+    };
+    auto row_sum = [&](int32_t nb) -> uint32_t { // one row per group, loads interleaved with lookups (entry node, generic NJ)
+        uint32_t s = 0;
+        if (nb >= 0) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nb * (NJ * 32) + sl * seg);
+            for (int j = 0; j < NJ; j++) s += lookup4(__ldg(row + j), j);
+        }
+        return reduce8(s);
     };
 
     for (;;) {
@@ -460,6 +449,7 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
         if (tid == 0) {
             s_query = atomicAdd(p.work_counter, 1);
             s_ns[0] = 0;
+            s_ndup[0] = 0;
             s_vis = 0;
         }
         __syncthreads();
@@ -472,10 +462,14 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
         for (int i = tid; i < H; i += kQThreads) filter[i] = tagged ? 0u : kEmpty;
         const float4 qp = __ldg(p.qparams + qi);
         const float delta = qp.x, base = qp.y, qnorm = qp.z;
-        auto finish = [&](uint32_t isum, int32_t nb) -> float {
+        auto score_of = [&](uint32_t isum, int32_t nb) -> float {
             const float s = __fmaf_rn(delta, (float)isum, base);
             const float nn = p.sim == JV_SIM_COSINE ? __ldg(p.node_norm + nb) : 0.f;
             return adc_finish(p.sim, s, nn, qnorm);
+        };
+        auto ord_of = [&](uint32_t isum, int32_t nb) -> uint32_t {
+            if (isum_keys) return l2 ? ~isum : isum;
+            return jv_f2ord(score_of(isum, nb));
         };
         __syncthreads(); // filter cleared
         mbar_wait(&s_bar, phase);
@@ -486,7 +480,7 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
             if (warp == 0) {
                 const uint32_t s = row_sum(g == 0 ? p.entry : -1);
                 if (lane == 0) {
-                    list0[0] = qkey_make(finish(s, p.entry), p.entry);
+                    list0[0] = qkey_pack(ord_of(s, p.entry), p.entry);
                     q_filter_insert(filter, p.hash_log2, tagged, p.entry);
                 }
                 my_visited = 1;
@@ -534,17 +528,13 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                     if (fresh) wids[__popc(ballot & ((1u << lane) - 1u))] = nb;
                     __syncwarp();
                     my_visited += cnt;
-                    auto offer = [&](uint32_t isum, int32_t node) {
-                        const uint64_t k = qkey_make(finish(isum, node), node);
-                        const uint64_t a = k >> 1;
-                        if (a > worst) {
-                            const int pos = q_count_better(list, n, a);
-                            if (!(pos < n && (list[pos] >> 1) == a)) surv[atomicAdd(&s_ns[par], 1)] = k; // drop re-scored list members
-                        }
+                    auto offer = [&](uint32_t isum, int32_t node) { // re-scored list members are dropped in (c)
+                        const uint64_t a = qkey_pack(ord_of(isum, node), node) >> 1;
+                        if (a > worst) surv[atomicAdd(&s_ns[par], 1)] = a;
                     };
                     if (NJ_T > 0) {
                         for (int i0 = 0; i0 < cnt; i0 += 4 * U) {
-                            uint32_t cw[U][NJ_T > 0 ? NJ_T : 1];
+                            uint32_t cw[U][NJC];
                             int32_t nbv[U];
 #pragma unroll
                             for (int u = 0; u < U; u++) {
@@ -553,19 +543,21 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                                 if (nbv[u] >= 0) {
                                     const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nbv[u] * (NJ * 32) + sl * seg);
 #pragma unroll
-                                    for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cw[u][j]) : "l"(row + j));
+                                    for (int j = 0; j < NJC; j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cw[u][j]) : "l"(row + j));
                                 } else {
 #pragma unroll
-                                    for (int j = 0; j < (NJ_T > 0 ? NJ_T : 1); j++) cw[u][j] = 0u;
+                                    for (int j = 0; j < NJC; j++) cw[u][j] = 0u;
                                 }
                             }
 #pragma unroll
                             for (int u = 0; u < U; u++) {
                                 if (i0 + u * 4 >= cnt) break; // warp-uniform
-                                uint32_t s = nbv[u] >= 0 ? lookups(cw[u]) : 0u;
-                                s += __shfl_xor_sync(JV_FULL_MASK, s, 4);
-                                s += __shfl_xor_sync(JV_FULL_MASK, s, 2);
-                                s += __shfl_xor_sync(JV_FULL_MASK, s, 1);
+                                uint32_t s = 0;
+                                if (nbv[u] >= 0) {
+#pragma unroll
+                                    for (int j = 0; j < NJC; j++) s += lookup4(cw[u][j], j);
+                                }
+                                s = reduce8(s);
                                 if (sl == 0 && nbv[u] >= 0) offer(s, nbv[u]);
                             }
                         }
@@ -580,29 +572,62 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                     __syncwarp(); // wids is reused by the next chunk of the row
                 }
             }
-            __syncthreads(); // B1: all survivors are in surv[]
+            __syncthreads(); // B1: all survivors are queued
             const int ns = s_ns[par];
-            if (tid == 0) s_ns[par ^ 1] = 0; // next step's counter (pushes start after B2)
             expanded += nsel;
 
-            // ---- (c) single-pass merge: survivors are distinct (atomic filter insertion) and not in the list;
-            //          position = own rank + number of better keys on the other side.  Selected entries lose their flag here.
+            // ---- (c) merge.  Phase 1: position of every survivor in the list (binary search); a survivor equal to a list
+            //          entry is a re-scored member (evicted from the visited filter earlier) and is dropped.
+            int my_pos[2] = {0, 0}; // survivors tid and tid + 128 (E * R <= 256)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int t = tid + c * kQThreads;
+                if (t < ns) {
+                    const uint64_t a = surv[t];
+                    int lo = 0, hi = n;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((list[mid] >> 1) > a)
+                            lo = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                    if (lo < n && (list[lo] >> 1) == a) {
+                        surv[t] = 0ull;
+                        atomicAdd(&s_ndup[par], 1);
+                    }
+                    my_pos[c] = lo;
+                }
+            }
+            __syncthreads(); // B1.5: duplicates are zeroed
+            if (tid == 0) { // next step's counters (pushes start after B2)
+                s_ns[par ^ 1] = 0;
+                s_ndup[par ^ 1] = 0;
+            }
+            const int ndup = s_ndup[par];
+            //          Phase 2: position = own rank + number of better keys on the other side (survivors are distinct:
+            //          atomic filter insertion).  Selected entries lose their "unexpanded" flag here.
             auto count_surv_better = [&](uint64_t a) -> int {
                 int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = 0;
                 for (; j + 4 <= ns; j += 4) {
-                    c0 += ((surv[j] >> 1) > a) ? 1 : 0;
-                    c1 += ((surv[j + 1] >> 1) > a) ? 1 : 0;
-                    c2 += ((surv[j + 2] >> 1) > a) ? 1 : 0;
-                    c3 += ((surv[j + 3] >> 1) > a) ? 1 : 0;
+                    c0 += (surv[j] > a) ? 1 : 0;
+                    c1 += (surv[j + 1] > a) ? 1 : 0;
+                    c2 += (surv[j + 2] > a) ? 1 : 0;
+                    c3 += (surv[j + 3] > a) ? 1 : 0;
                 }
-                for (; j < ns; j++) c0 += ((surv[j] >> 1) > a) ? 1 : 0;
+                for (; j < ns; j++) c0 += (surv[j] > a) ? 1 : 0;
                 return (c0 + c1) + (c2 + c3);
             };
-            for (int t = tid; t < ns; t += kQThreads) {
-                const uint64_t mine = surv[t];
-                const uint64_t a = mine >> 1;
-                const int pos = q_count_better(list, n, a) + count_surv_better(a);
-                if (pos < L) out[pos] = mine;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int t = tid + c * kQThreads;
+                if (t < ns) {
+                    const uint64_t a = surv[t];
+                    if (a != 0ull) {
+                        const int pos = my_pos[c] + count_surv_better(a);
+                        if (pos < L) out[pos] = (a << 1) | 1ull;
+                    }
+                }
             }
             for (int t = kQThreads - 1 - tid; t < n; t += kQThreads) { // list entries on the high threads: survivors use the low ones
                 uint64_t k = list[t];
@@ -613,7 +638,7 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                 if (pos < L) out[pos] = k;
             }
             __syncthreads(); // B2
-            n = n + ns < L ? n + ns : L;
+            n = n + ns - ndup < L ? n + ns - ndup : L;
             cur ^= 1;
             step++;
         }
@@ -624,7 +649,17 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
         {
             const uint64_t *list = cur ? list1 : list0;
             uint64_t *o = p.approx_keys + (int64_t)qi * L;
-            for (int i = tid; i < L; i += kQThreads) o[i] = i < n ? jv_mk_key(qkey_score(list[i]), qkey_node(list[i])) : 0ull;
+            for (int i = tid; i < L; i += kQThreads) {
+                uint64_t outk = 0ull;
+                if (i < n) {
+                    const uint64_t k = list[i];
+                    const int32_t node = qkey_node(k);
+                    const uint32_t ord = (uint32_t)(k >> 32);
+                    const float sc = isum_keys ? score_of(l2 ? ~ord : ord, node) : jv_ord2f(ord);
+                    outk = jv_mk_key(sc, node);
+                }
+                o[i] = outk;
+            }
             if (tid == 0) {
                 p.approx_count[qi] = n;
                 if (p.stats) {
@@ -679,14 +714,14 @@ static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
 }
 
 bool q8_search_supported(const jv_index *ix, int L, int R) {
-    if (!ix->has_pq || !ix->q8_ok) return false;
-    const size_t fixed = (size_t)ix->q8_nj * 8192 + (size_t)L * 16 + (size_t)kQMaxE * R * 8 + (size_t)kQW * 32 * 4;
+    if (!ix->has_pq || !ix->q8_ok || R > 64) return false; // <= 2 queued survivors per thread and step
+    const size_t fixed = (size_t)q8_lut_bytes(ix->q8_nj) + (size_t)L * 16 + (size_t)kQMaxE * ((R + 31) / 32) * 32 * 8 + (size_t)kQW * 32 * 4;
     return fixed + 4096 + 2048 <= 227 * 1024;
 }
 
 // LUT build + traversal for queries [0, nq) in chunks bounded by the table staging buffer
 int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches) {
-    const int lutb = ix->q8_nj * 8192;
+    const int lutb = q8_lut_bytes(ix->q8_nj);
     // staging buffer: <= 512 MB of tables per chunk (10 922 queries at M = 192)
     int chunk = (int)((size_t)512 * 1024 * 1024 / (size_t)lutb);
     if (const char *e = getenv("JVGPU_Q8_CHUNK")) { // test knob: force small chunks
