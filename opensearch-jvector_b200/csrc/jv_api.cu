@@ -175,8 +175,8 @@ int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
         jv_index_destroy(ix);
         return s;
     };
-    if ((st = ix->dbg.alloc(128)) != JV_OK) return fail(st);
-    cudaMemset(ix->dbg.p, 0, 128);
+    if ((st = ix->dbg.alloc(256)) != JV_OK) return fail(st);
+    cudaMemset(ix->dbg.p, 0, 256);
     const size_t n = (size_t)d->n;
     if ((st = upload(ix->adjacency, d->adjacency, n * d->max_degree * 4, &total)) != JV_OK) return fail(st);
     if (d->flags & JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE) {
@@ -300,15 +300,15 @@ int32_t jv_index_device_bytes(const jv_index *ix, int64_t *out_bytes) {
 }
 
 int32_t jv_index_debug_counter(jv_index *ix, int32_t which, int64_t *out_value) {
-    JV_REQUIRE(ix && out_value && ((which >= 0 && which < 4) || (which >= 8 && which < 16) || which == 100), "bad arguments");
+    JV_REQUIRE(ix && out_value && ((which >= 0 && which < 4) || (which >= 8 && which < 24) || which == 100), "bad arguments");
     DeviceGuard guard(ix->device);
     if (which == 100) { // reset
-        JV_CUDA_TRY(cudaMemset(ix->dbg.p, 0, 128));
+        JV_CUDA_TRY(cudaMemset(ix->dbg.p, 0, 256));
         *out_value = 0;
         return JV_OK;
     }
-    unsigned char raw[128];
-    JV_CUDA_TRY(cudaMemcpy(raw, ix->dbg.p, 128, cudaMemcpyDeviceToHost));
+    unsigned char raw[256];
+    JV_CUDA_TRY(cudaMemcpy(raw, ix->dbg.p, 256, cudaMemcpyDeviceToHost));
     if (which < 4) {
         int32_t v;
         memcpy(&v, raw + which * 4, 4);

@@ -24,6 +24,8 @@
 // 8 different banks and the 4 groups of a warp are rotated onto the 4 different bank quarters.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "jv_search_common.cuh"
 
 namespace jv {
@@ -324,9 +326,7 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
 // ---------------------------------------------------------------------------------------------------------------
 // K2: traversal
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kQW = 4;            // warps per CTA = candidates expanded per step
-constexpr int kQThreads = kQW * 32;
-constexpr int kQMaxE = kQW;
+constexpr int kQMaxE = 4;          // candidates per step (one per warp)
 
 struct Q8Params {
     const int32_t *adjacency;
@@ -370,10 +370,12 @@ __device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, 
     }
 }
 
-// NJ_T > 0: code words per lane known at compile time (registers, all loads of U rows in flight before the first lookup)
-template <int NJ_T>
-__global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params p) {
-    constexpr int U = 2; // row groups in flight per warp pass: 4 groups x U rows
+// NJ_T > 0: code words per lane known at compile time (registers, all loads of U rows in flight before the first lookup).
+// W = warps per CTA (4 row groups each); PROF = per-phase cycle counters (jv_index_debug_counter).
+template <int NJ_T, int W, bool PROF>
+__global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) {
+    constexpr int kQW = W, kQThreads = W * 32, NG = 4 * W;
+    constexpr int U = W == 4 ? 3 : 2; // rows in flight per row group and pass: NG * U rows >= the fresh neighbours of a typical step
     constexpr int NJC = NJ_T > 0 ? NJ_T : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -389,12 +391,14 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
     sp += (size_t)L * 8;
     uint64_t *surv = reinterpret_cast<uint64_t *>(sp); // queued survivors as key >> 1 (always unexpanded); 0 = dropped duplicate
     sp += (size_t)p.surv_cap * 8;
-    int32_t *wids = reinterpret_cast<int32_t *>(sp) + warp * 32;
-    sp += (size_t)kQW * 32 * 4;
+    int32_t *pool = reinterpret_cast<int32_t *>(sp); // fresh neighbour ids of the current step
+    sp += (size_t)p.surv_cap * 4;
+    int32_t *gapcnt = reinterpret_cast<int32_t *>(sp); // [L + 1] survivors per list gap (merge)
+    sp += (size_t)((L + 2) & ~1) * 4;
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
 
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_query, s_ns[2], s_ndup[2], s_vis, w_sel[kQW][2 * kQMaxE], w_pos[kQW][2 * kQMaxE];
+    __shared__ int s_query, s_ns[2], s_nn[2], s_ndup[2], w_sel[kQW][2 * kQMaxE], w_pos[kQW][2 * kQMaxE];
 
     const bool tagged = p.n <= ((int64_t)1 << (p.hash_log2 + 15));
     const bool isum_keys = p.sim != JV_SIM_COSINE;
@@ -449,17 +453,26 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
         if (tid == 0) {
             s_query = atomicAdd(p.work_counter, 1);
             s_ns[0] = 0;
+            s_nn[0] = 0;
             s_ndup[0] = 0;
-            s_vis = 0;
         }
         __syncthreads();
         const int qi = s_query;
         if (qi >= p.nq) break;
+        long long ck[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // per-phase cycles (thread 0), see jv_index_debug_counter
+        long long t_prev = PROF ? clock64() : 0;
+#define JV_PHASE(i)                            \
+    if (PROF) {                                \
+        const long long t_now = clock64();     \
+        ck[i] += t_now - t_prev;               \
+        t_prev = t_now;                        \
+    }
         if (tid == 0) { // K1 result: one TMA bulk copy HBM/L2 -> shared memory
             mbar_expect_tx(&s_bar, (uint32_t)p.lutb);
             bulk_g2s(smem_raw, p.lut + (int64_t)qi * p.lutb, (uint32_t)p.lutb, &s_bar);
         }
         for (int i = tid; i < H; i += kQThreads) filter[i] = tagged ? 0u : kEmpty;
+        for (int i = tid; i <= L; i += kQThreads) gapcnt[i] = 0;
         const float4 qp = __ldg(p.qparams + qi);
         const float delta = qp.x, base = qp.y, qnorm = qp.z;
         auto score_of = [&](uint32_t isum, int32_t nb) -> float {
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
 
-        int n = 0, cur = 0, my_visited = 0, expanded = 0, step = 0;
+        int n = 0, cur = 0, visited = 0, expanded = 0, step = 0;
         if (p.entry >= 0 && p.entry < p.n) {
             if (warp == 0) {
                 const uint32_t s = row_sum(g == 0 ? p.entry : -1);
@@ -483,11 +496,12 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                     list0[0] = qkey_pack(ord_of(s, p.entry), p.entry);
                     q_filter_insert(filter, p.hash_log2, tagged, p.entry);
                 }
-                my_visited = 1;
             }
             n = 1;
+            visited = 1;
         }
         __syncthreads();
+        JV_PHASE(0)
 
         while (n > 0) {
             uint64_t *list = cur ? list1 : list0, *out = cur ? list0 : list1;
@@ -510,71 +524,116 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
             const int nsel = found < E ? found : E;
             if (nsel == 0) break;
             const uint64_t worst = n >= L ? (list[L - 1] >> 1) : 0ull;
+            JV_PHASE(2)
 
-            // ---- (b) warp w expands candidate w: adjacency row -> visited filter -> ADC of the fresh neighbours
-            if (warp < nsel) {
-                const int32_t cand = w_sel[warp][warp];
-                if (nsel + warp < found && nsel + warp < 2 * E) { // runner-up row -> L2 for the next step
+            // ---- (b1) warp w expands candidates w, w + 4, ..: adjacency row -> visited filter -> shared pool of fresh ids
+            for (int e = warp; e < nsel; e += kQW) {
+                const int32_t cand = w_sel[warp][e];
+                if (nsel + e < found && nsel + e < 2 * E) { // runner-up row -> L2 for the next step
                     const int lines = (R * 4 + 127) >> 7;
                     if (lane < lines)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.adjacency + (int64_t)w_sel[warp][nsel + warp] * R) + lane * 128));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.adjacency + (int64_t)w_sel[warp][nsel + e] * R) + lane * 128));
                 }
                 for (int r0 = 0; r0 < R; r0 += 32) {
                     int32_t nb = -1;
                     if (r0 + lane < R) nb = __ldg(p.adjacency + (int64_t)cand * R + r0 + lane);
                     const bool fresh = nb >= 0 && nb < p.n && q_filter_insert(filter, p.hash_log2, tagged, nb);
                     const uint32_t ballot = __ballot_sync(JV_FULL_MASK, fresh);
-                    const int cnt = __popc(ballot);
-                    if (fresh) wids[__popc(ballot & ((1u << lane) - 1u))] = nb;
-                    __syncwarp();
-                    my_visited += cnt;
-                    auto offer = [&](uint32_t isum, int32_t node) { // re-scored list members are dropped in (c)
-                        const uint64_t a = qkey_pack(ord_of(isum, node), node) >> 1;
-                        if (a > worst) surv[atomicAdd(&s_ns[par], 1)] = a;
-                    };
-                    if (NJ_T > 0) {
-                        for (int i0 = 0; i0 < cnt; i0 += 4 * U) {
-                            uint32_t cw[U][NJC];
-                            int32_t nbv[U];
+                    int slot = 0;
+                    if (lane == 0 && ballot) slot = atomicAdd(&s_nn[par], __popc(ballot));
+                    slot = __shfl_sync(JV_FULL_MASK, slot, 0);
+                    if (fresh) pool[slot + __popc(ballot & ((1u << lane) - 1u))] = nb;
+                }
+            }
+            __syncthreads(); // B0: the pool of fresh neighbours is complete
+            const int nn = s_nn[par];
+            JV_PHASE(3)
+
+            // ---- (b2) ADC of the pooled rows, spread evenly over the 16 row groups of the CTA: all code words of a
+            //           group's U rows are in flight before the first table lookup (one DRAM round trip per step)
+            {
+                const int gid = warp * 4 + g;
+                auto offer = [&](uint32_t isum, int32_t node) { // re-scored list members are dropped in (c)
+                    const uint64_t a = qkey_pack(ord_of(isum, node), node) >> 1;
+                    if (a > worst) surv[atomicAdd(&s_ns[par], 1)] = a;
+                };
+                if (NJ_T > 0) {
+                    // one pass over NU rows per group; NU is warp-uniform (rows are dealt to the warps 4 at a time)
+                    auto pass = [&](int i0, auto nu_tag) {
+                        constexpr int NU = decltype(nu_tag)::value;
+                        uint32_t cw[NU][NJC], s[NU];
+                        int32_t nbv[NU];
 #pragma unroll
-                            for (int u = 0; u < U; u++) {
-                                const int idx = i0 + u * 4 + g;
-                                nbv[u] = idx < cnt ? wids[idx] : -1;
-                                if (nbv[u] >= 0) {
-                                    const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nbv[u] * (NJ * 32) + sl * seg);
+                        for (int u = 0; u < NU; u++) {
+                            const int idx = i0 + u * NG + gid;
+                            nbv[u] = idx < nn ? pool[idx] : -1;
+                            s[u] = 0u;
+                            if (nbv[u] >= 0) {
+                                const unsigned char *row = p.codes_q8 + (int64_t)nbv[u] * (NJ * 32) + sl * seg;
+                                if (NJC % 2 == 0) { // 8-byte aligned lane segments
 #pragma unroll
-                                    for (int j = 0; j < NJC; j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cw[u][j]) : "l"(row + j));
+                                    for (int j = 0; j < NJC / 2; j++)
+                                        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(cw[u][2 * j]), "=r"(cw[u][2 * j + 1]) : "l"(row + 8 * j));
                                 } else {
 #pragma unroll
-                                    for (int j = 0; j < NJC; j++) cw[u][j] = 0u;
+                                    for (int j = 0; j < NJC; j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cw[u][j]) : "l"(row + 4 * j));
                                 }
-                            }
+                            } else {
 #pragma unroll
-                            for (int u = 0; u < U; u++) {
-                                if (i0 + u * 4 >= cnt) break; // warp-uniform
-                                uint32_t s = 0;
-                                if (nbv[u] >= 0) {
-#pragma unroll
-                                    for (int j = 0; j < NJC; j++) s += lookup4(cw[u][j], j);
-                                }
-                                s = reduce8(s);
-                                if (sl == 0 && nbv[u] >= 0) offer(s, nbv[u]);
+                                for (int j = 0; j < NJC; j++) cw[u][j] = 0u;
                             }
                         }
-                    } else {
-                        for (int i0 = 0; i0 < cnt; i0 += 4) {
-                            const int idx = i0 + g;
-                            const int32_t node = idx < cnt ? wids[idx] : -1;
-                            const uint32_t s = row_sum(node);
-                            if (sl == 0 && node >= 0) offer(s, node);
+                        if (PROF) { // sub-phase 8: code words in registers
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int u = 0; u < NU; u++)
+#pragma unroll
+                                for (int j = 0; j < NJC; j++) acc |= cw[u][j];
+                            asm volatile("" ::"r"(acc));
+                            JV_PHASE(8)
                         }
+#pragma unroll
+                        for (int j = 0; j < NJC; j++) {
+#pragma unroll
+                            for (int u = 0; u < NU; u++) s[u] += lookup4(cw[u][j], j); // a group without a row looks up code 0: harmless
+                        }
+#pragma unroll
+                        for (int u = 0; u < NU; u++) s[u] = reduce8(s[u]);
+                        if (PROF) {
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int u = 0; u < NU; u++) acc |= s[u];
+                            asm volatile("" ::"r"(acc));
+                            JV_PHASE(9)
+                        }
+#pragma unroll
+                        for (int u = 0; u < NU; u++)
+                            if (sl == 0 && nbv[u] >= 0) offer(s[u], nbv[u]);
+                        JV_PHASE(10)
+                    };
+                    for (int i0 = 0; i0 < nn; i0 += NG * U) {
+                        const int left = nn - i0 - warp * 4; // rows of this pass at or after this warp's first group
+                        if (U >= 3 && left > 2 * NG)
+                            pass(i0, std::integral_constant<int, U >= 3 ? 3 : 1>());
+                        else if (left > NG)
+                            pass(i0, std::integral_constant<int, 2>());
+                        else if (left > 0)
+                            pass(i0, std::integral_constant<int, 1>());
                     }
-                    __syncwarp(); // wids is reused by the next chunk of the row
+                } else {
+                    for (int i0 = 0; i0 < nn; i0 += NG) {
+                        const int idx = i0 + gid;
+                        const int32_t node = idx < nn ? pool[idx] : -1;
+                        const uint32_t sm = row_sum(node);
+                        if (sl == 0 && node >= 0) offer(sm, node);
+                    }
                 }
             }
             __syncthreads(); // B1: all survivors are queued
             const int ns = s_ns[par];
+            JV_PHASE(4)
             expanded += nsel;
+            visited += nn;
 
             // ---- (c) merge.  Phase 1: position of every survivor in the list (binary search); a survivor equal to a list
             //          entry is a re-scored member (evicted from the visited filter earlier) and is dropped.
@@ -595,13 +654,17 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                     if (lo < n && (list[lo] >> 1) == a) {
                         surv[t] = 0ull;
                         atomicAdd(&s_ndup[par], 1);
+                    } else {
+                        atomicAdd(&gapcnt[lo], 1); // lo list entries are better than this survivor
                     }
                     my_pos[c] = lo;
                 }
             }
             __syncthreads(); // B1.5: duplicates are zeroed
+            JV_PHASE(1)
             if (tid == 0) { // next step's counters (pushes start after B2)
                 s_ns[par ^ 1] = 0;
+                s_nn[par ^ 1] = 0;
                 s_ndup[par ^ 1] = 0;
             }
             const int ndup = s_ndup[par];
@@ -629,23 +692,41 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                     }
                 }
             }
-            for (int t = kQThreads - 1 - tid; t < n; t += kQThreads) { // list entries on the high threads: survivors use the low ones
-                uint64_t k = list[t];
-                bool selected = false;
-                for (int e = 0; e < nsel; e++) selected |= (w_pos[warp][e] == t);
-                if (selected) k &= ~1ull;
-                const int pos = t + count_surv_better(k >> 1);
-                if (pos < L) out[pos] = k;
+            // list entry t moves down by the number of survivors better than it = survivors in gaps 0..t (inclusive prefix
+            // sum of gapcnt): warp-level scan, chunks of 32 entries dealt to the warps from the top (survivors use the low ones)
+            for (int c0 = (kQW - 1 - warp) * 32; c0 < n; c0 += kQW * 32) {
+                int offset = 0;
+                for (int cc = 0; cc < c0; cc += 32) { // survivors in the gaps of earlier chunks
+                    int v = gapcnt[cc + lane];
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(JV_FULL_MASK, v, o);
+                    offset += v;
+                }
+                const int t = c0 + lane;
+                int v = t < n ? gapcnt[t] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(JV_FULL_MASK, v, o);
+                    if (lane >= o) v += up;
+                }
+                if (t < n) {
+                    uint64_t k = list[t];
+                    bool selected = false;
+                    for (int e = 0; e < nsel; e++) selected |= (w_pos[warp][e] == t);
+                    if (selected) k &= ~1ull;
+                    const int pos = t + offset + v;
+                    if (pos < L) out[pos] = k;
+                }
             }
             __syncthreads(); // B2
+            JV_PHASE(5)
+            for (int i = tid; i <= L; i += kQThreads) gapcnt[i] = 0; // consumed above; the next increments come after B1
             n = n + ns - ndup < L ? n + ns - ndup : L;
             cur ^= 1;
             step++;
         }
 
         // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank kernel
-        if (lane == 0 && my_visited) atomicAdd(&s_vis, my_visited);
-        __syncthreads();
         {
             const uint64_t *list = cur ? list1 : list0;
             uint64_t *o = p.approx_keys + (int64_t)qi * L;
@@ -664,7 +745,7 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                 p.approx_count[qi] = n;
                 if (p.stats) {
                     jv_query_stats st;
-                    st.visited = s_vis;
+                    st.visited = visited;
                     st.expanded = expanded;
                     st.expanded_base = expanded;
                     st.reranked = 0;
@@ -672,19 +753,28 @@ __global__ void __launch_bounds__(kQThreads, 4) q8_search_kernel(const Q8Params 
                 }
             }
         }
+        JV_PHASE(6)
+        if (PROF && tid == 0 && p.dbg) { // phases: 0 setup + table wait, 1 merge/dedupe, 2 select, 3 neighbour rows, 4 scoring, 5 merge/rank, 6 emit
+            unsigned long long *ph = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p.dbg) + 64);
+            for (int i = 0; i < 7; i++) atomicAdd(ph + i, (unsigned long long)ck[i]);
+            atomicAdd(ph + 7, (unsigned long long)step);
+            for (int i = 8; i < 12; i++) atomicAdd(ph + i, (unsigned long long)ck[i]); // scoring sub-phases: code words arrive, lookups, offers
+        }
+#undef JV_PHASE
     }
 }
 
-template <int NJ_T>
+template <int NJ_T, int W, bool PROF>
 static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
-    auto kern = q8_search_kernel<NJ_T>;
-    const size_t fixed = (size_t)p.lutb + (size_t)p.L * 16 + (size_t)p.surv_cap * 8 + (size_t)kQW * 32 * 4;
+    constexpr int kQThreads = W * 32;
+    auto kern = q8_search_kernel<NJ_T, W, PROF>;
+    const size_t fixed = (size_t)p.lutb + (size_t)p.L * 16 + (size_t)p.surv_cap * 12 + (size_t)((p.L + 2) & ~1) * 4;
     const size_t sm_total = 228 * 1024;
     int64_t want = (int64_t)p.L * p.R; // words; 2 tags each
     if (want < 1024) want = 1024;
     int best_occ = 0, best_log2 = 0;
     for (int occ = 8; occ >= 1; occ--) {
-        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 512 - (int64_t)fixed; // 1 KB system + static __shared__
+        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 384 - (int64_t)fixed; // 1 KB system + static __shared__
         if (per < 1024 * 4) continue;
         int lg = 10;
         while (lg < 15 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
@@ -715,7 +805,7 @@ static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
 
 bool q8_search_supported(const jv_index *ix, int L, int R) {
     if (!ix->has_pq || !ix->q8_ok || R > 64) return false; // <= 2 queued survivors per thread and step
-    const size_t fixed = (size_t)q8_lut_bytes(ix->q8_nj) + (size_t)L * 16 + (size_t)kQMaxE * ((R + 31) / 32) * 32 * 8 + (size_t)kQW * 32 * 4;
+    const size_t fixed = (size_t)q8_lut_bytes(ix->q8_nj) + (size_t)L * 16 + (size_t)kQMaxE * ((R + 31) / 32) * 32 * 12 + (size_t)((L + 2) & ~1) * 4;
     return fixed + 4096 + 2048 <= 227 * 1024;
 }
 
@@ -733,7 +823,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
     JV_TRY(ctx->lut8.ensure((size_t)chunk * lutb));
     JV_TRY(ctx->qparams.ensure((size_t)chunk * sizeof(float4)));
     JV_TRY(ctx->counter.ensure(sizeof(int)));
-    int E = a.expand_width <= 0 ? kQMaxE : (a.expand_width > kQMaxE ? kQMaxE : a.expand_width);
+    int E = a.expand_width <= 0 ? 4 : (a.expand_width > kQMaxE ? kQMaxE : a.expand_width);
     for (int q0 = 0; q0 < a.nq; q0 += chunk) {
         const int nqc = a.nq - q0 < chunk ? a.nq - q0 : chunk;
         JV_TRY(launch_lut_q8(ix, ctx->stream, a.d_queries + (int64_t)q0 * ix->dim, nqc, ctx->lut8.as<uint8_t>(), ctx->qparams.as<float4>()));
@@ -764,15 +854,25 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         p.E = E;
         p.surv_cap = E * ((ix->R + 31) / 32) * 32;
         int32_t st;
+        const bool prof = getenv("JVGPU_PROFILE") != nullptr; // per-phase cycle counters (costs registers): diagnostics only
+        const int warps = getenv("JVGPU_Q8_WARPS") ? atoi(getenv("JVGPU_Q8_WARPS")) : 4;
+#define JV_Q8_CASE(NJV)                                                                         \
+    case NJV:                                                                                   \
+        st = warps == 8 ? (prof ? launch_q8_typed<NJV, 8, true>(ix, ctx, p) : launch_q8_typed<NJV, 8, false>(ix, ctx, p)) \
+                        : (prof ? launch_q8_typed<NJV, 4, true>(ix, ctx, p) : launch_q8_typed<NJV, 4, false>(ix, ctx, p)); \
+        break;
         switch (ix->q8_nj) {
-        case 1: st = launch_q8_typed<1>(ix, ctx, p); break;
-        case 2: st = launch_q8_typed<2>(ix, ctx, p); break;
-        case 3: st = launch_q8_typed<3>(ix, ctx, p); break;
-        case 4: st = launch_q8_typed<4>(ix, ctx, p); break;
-        case 6: st = launch_q8_typed<6>(ix, ctx, p); break;
-        case 8: st = launch_q8_typed<8>(ix, ctx, p); break;
-        default: st = launch_q8_typed<0>(ix, ctx, p); break;
+            JV_Q8_CASE(1)
+            JV_Q8_CASE(2)
+            JV_Q8_CASE(3)
+            JV_Q8_CASE(4)
+            JV_Q8_CASE(6)
+            JV_Q8_CASE(8)
+        default:
+            st = prof ? launch_q8_typed<0, 4, true>(ix, ctx, p) : launch_q8_typed<0, 4, false>(ix, ctx, p);
+            break;
         }
+#undef JV_Q8_CASE
         JV_TRY(st);
         if (launches) *launches += 2;
     }

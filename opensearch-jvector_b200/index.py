@@ -158,7 +158,8 @@ class GpuIndex:
         N.check(N.load().jv_index_debug_counter(self.handle, 0, C.addressof(b)))
         return int(b.value)
 
-    PHASES = ("setup", "table_build", "select", "neighbour_rows", "scoring", "merge", "emit", "steps")
+    PHASES = ("setup", "table_build", "select", "neighbour_rows", "scoring", "merge", "emit", "steps",
+              "sub_code_words", "sub_lookups", "sub_offers", "sub_spare")
 
     def phase_cycles(self, reset: bool = False) -> dict:
         """Per-phase SM cycles of the fast traversal kernel (thread 0 of each CTA, summed) + step count."""
