@@ -2,6 +2,7 @@
 // lifetime, per-call context pool, H2D/D2H staging, timing.  No torch, no CPU compute fallback.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "jv_internal.h"
 
@@ -19,7 +20,9 @@ const char *get_error() { return g_err; }
 
 int32_t SearchCtx::init(int) {
     JV_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    JV_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (auto &e : ev) JV_CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : chunk_ev) JV_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return JV_OK;
 }
 int32_t SearchCtx::ensure_pinned(size_t bytes) {
@@ -33,8 +36,12 @@ int32_t SearchCtx::ensure_pinned(size_t bytes) {
 }
 void SearchCtx::destroy() {
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto &e : ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : chunk_ev)
+        if (e) cudaEventDestroy(e);
+    copy_stream = nullptr;
     if (pinned) cudaFreeHost(pinned);
     stream = nullptr;
     pinned = nullptr;
@@ -326,7 +333,7 @@ int32_t jv_index_debug_counter(jv_index *ix, int32_t which, int64_t *out_value) 
 // -------------------------------------------------------------------------------------------------
 static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, int32_t nq, const jv_search_params *p,
                            const uint64_t *d_accept, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
-                           jv_query_stats *d_stats, int *launches) {
+                           jv_query_stats *d_stats, int *launches, bool timed = true) {
     JV_TRY(c->approx_keys.ensure((size_t)nq * p->rerank_k * 8));
     JV_TRY(c->approx_count.ensure((size_t)nq * 4));
     SearchLaunch a;
@@ -342,13 +349,15 @@ static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, i
     a.entry_override = -1;
     a.n_limit = ix->n;
     a.expand_width = p->expand_width;
-    c->lut_timed = false;
-    JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (timed) {
+        c->lut_timed = false;
+        JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    }
     JV_TRY(launch_search(ix, c, a, launches));
-    JV_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (timed) JV_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     JV_TRY(launch_rerank(ix, c, d_queries, nq, p->k, p->rerank_k, p->rerank_floor, a.d_approx_keys, a.d_approx_count, d_out_doc,
                          d_out_score, d_out_count, d_stats, launches));
-    JV_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    if (timed) JV_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     return JV_OK;
 }
 
@@ -440,11 +449,44 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
         }
     }
     JV_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    if (!zero_copy) JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
     if (abytes) JV_CUDA_TRY(cudaMemcpyAsync(c->accept.p, p->accept_bits, abytes, cudaMemcpyHostToDevice, c->stream));
     int launches = 0;
-    JV_TRY(search_core(ix, c, d_q, nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
-                       c->out_count.as<int32_t>(), c->stats.as<jv_query_stats>(), &launches));
+    // Large staged batches are pipelined: the queries travel in up to 8 chunks on a copy stream and the kernels of chunk i
+    // (table build, traversal, rerank) run while chunk i+1 is still on the PCIe bus.  Per-query accept bitsets keep the
+    // single-shot path (their stride is relative to the whole batch).
+    int nchunks = (!zero_copy && nq >= 4096 && !(p->accept_bits && p->accept_stride_words)) ? (nq >= 16384 ? 8 : 4) : 1;
+    if (const char *e = getenv("JVGPU_H2D_CHUNKS")) { // diagnostics: 1 disables the pipeline
+        const int v = atoi(e);
+        if (v >= 1 && v <= 8 && nchunks > 1) nchunks = v;
+    }
+    const bool serial_dbg = getenv("JVGPU_H2D_SERIAL") != nullptr;
+    if (nchunks > 1) {
+        JV_CUDA_TRY(cudaEventRecord(c->chunk_ev[0], c->stream)); // the copy stream must not overtake earlier work on these buffers
+        JV_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));
+        const int per = (nq + nchunks - 1) / nchunks;
+        // approximate-list scratch for the largest chunk is allocated once, before anything is enqueued
+        JV_TRY(c->approx_keys.ensure((size_t)per * p->rerank_k * 8));
+        JV_TRY(c->approx_count.ensure((size_t)per * 4));
+        for (int ci = 0; ci < nchunks; ci++) {
+            const int q0 = ci * per, nqc = nq - q0 < per ? nq - q0 : per;
+            if (nqc <= 0) break;
+            JV_CUDA_TRY(cudaMemcpyAsync(c->queries.as<float>() + (size_t)q0 * ix->dim, queries + (size_t)q0 * ix->dim, (size_t)nqc * ix->dim * 4,
+                                        cudaMemcpyHostToDevice, c->copy_stream));
+            JV_CUDA_TRY(cudaEventRecord(c->chunk_ev[ci], c->copy_stream));
+        }
+        for (int ci = 0; ci < nchunks; ci++) {
+            const int q0 = ci * per, nqc = nq - q0 < per ? nq - q0 : per;
+            if (nqc <= 0) break;
+            JV_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ev[serial_dbg ? nchunks - 1 : ci], 0));
+            JV_TRY(search_core(ix, c, c->queries.as<float>() + (size_t)q0 * ix->dim, nqc, p, d_accept, c->out_doc.as<int32_t>() + (size_t)q0 * p->k,
+                               c->out_score.as<float>() + (size_t)q0 * p->k, c->out_count.as<int32_t>() + q0,
+                               c->stats.as<jv_query_stats>() + q0, &launches, ci == 0));
+        }
+    } else {
+        if (!zero_copy) JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+        JV_TRY(search_core(ix, c, d_q, nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
+                           c->out_count.as<int32_t>(), c->stats.as<jv_query_stats>(), &launches));
+    }
     JV_CUDA_TRY(cudaMemcpyAsync(out_doc, c->out_doc.p, kb, cudaMemcpyDeviceToHost, c->stream));
     JV_CUDA_TRY(cudaMemcpyAsync(out_score, c->out_score.p, kb, cudaMemcpyDeviceToHost, c->stream));
     JV_CUDA_TRY(cudaMemcpyAsync(out_count, c->out_count.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -9,6 +9,8 @@ namespace jv {
 struct SearchCtx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;  // H2D of query chunks overlapping the kernels of the previous chunk
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf queries, out_doc, out_score, out_count, stats, accept;
     DevBuf approx_keys, approx_count; // [nq*rerank_k] uint64 keys (score, ordinal), best first
     DevBuf counter;                   // persistent-grid work counter

@@ -670,15 +670,18 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             const int ndup = s_ndup[par];
             //          Phase 2: position = own rank + number of better keys on the other side (survivors are distinct:
             //          atomic filter insertion).  Selected entries lose their "unexpanded" flag here.
-            auto count_surv_better = [&](uint64_t a) -> int {
-                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = 0;
-                for (; j + 4 <= ns; j += 4) {
-                    c0 += (surv[j] > a) ? 1 : 0;
-                    c1 += (surv[j + 1] > a) ? 1 : 0;
-                    c2 += (surv[j + 2] > a) ? 1 : 0;
-                    c3 += (surv[j + 3] > a) ? 1 : 0;
+            //          Two survivors can carry the SAME key: when the visited filter evicts an entry that was inserted in
+            //          this very step, the node is scored twice.  Equal keys are ordered by queue index, so every element
+            //          still gets its own slot (no holes); the copy is removed when the list is emitted.
+            auto count_gt = [&](int j0, int j1, uint64_t thr) -> int { // survivors j0..j1-1 with key > thr
+                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = j0;
+                for (; j + 4 <= j1; j += 4) {
+                    c0 += (surv[j] > thr) ? 1 : 0;
+                    c1 += (surv[j + 1] > thr) ? 1 : 0;
+                    c2 += (surv[j + 2] > thr) ? 1 : 0;
+                    c3 += (surv[j + 3] > thr) ? 1 : 0;
                 }
-                for (; j < ns; j++) c0 += (surv[j] > a) ? 1 : 0;
+                for (; j < j1; j++) c0 += (surv[j] > thr) ? 1 : 0;
                 return (c0 + c1) + (c2 + c3);
             };
 #pragma unroll
@@ -686,8 +689,11 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
                 const int t = tid + c * kQThreads;
                 if (t < ns) {
                     const uint64_t a = surv[t];
+                    // copies of my key among this warp's 32 survivors (one MATCH instruction); earlier queue index wins ties
+                    const uint32_t same = __match_any_sync(__activemask(), a) & ((1u << lane) - 1u);
                     if (a != 0ull) {
-                        const int pos = my_pos[c] + count_surv_better(a);
+                        const int t0 = t & ~31; // this warp's survivors start here
+                        const int pos = my_pos[c] + count_gt(0, t0, a - 1ull) + count_gt(t0, ns, a) + __popc(same);
                         if (pos < L) out[pos] = (a << 1) | 1ull;
                     }
                 }
@@ -730,27 +736,31 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
         {
             const uint64_t *list = cur ? list1 : list0;
             uint64_t *o = p.approx_keys + (int64_t)qi * L;
-            for (int i = tid; i < L; i += kQThreads) {
-                uint64_t outk = 0ull;
-                if (i < n) {
-                    const uint64_t k = list[i];
-                    const int32_t node = qkey_node(k);
-                    const uint32_t ord = (uint32_t)(k >> 32);
-                    const float sc = isum_keys ? score_of(l2 ? ~ord : ord, node) : jv_ord2f(ord);
-                    outk = jv_mk_key(sc, node);
-                }
-                o[i] = outk;
+            auto key_of = [&](uint64_t k) -> uint64_t {
+                const int32_t node = qkey_node(k);
+                const uint32_t ord = (uint32_t)(k >> 32);
+                const float sc = isum_keys ? score_of(l2 ? ~ord : ord, node) : jv_ord2f(ord);
+                return jv_mk_key(sc, node);
+            };
+            int dup = 0; // a node scored twice in one step (see the merge) sits in two adjacent slots
+            for (int i = tid + 1; i < n; i += kQThreads) dup |= ((list[i] >> 1) == (list[i - 1] >> 1)) ? 1 : 0;
+            if (!__syncthreads_or(dup)) {
+                for (int i = tid; i < L; i += kQThreads) o[i] = i < n ? key_of(list[i]) : 0ull;
+                if (tid == 0) p.approx_count[qi] = n;
+            } else if (tid == 0) { // rare: serial compaction
+                int w = 0;
+                for (int i = 0; i < n; i++)
+                    if (i == 0 || (list[i] >> 1) != (list[i - 1] >> 1)) o[w++] = key_of(list[i]);
+                p.approx_count[qi] = w;
+                for (; w < L; w++) o[w] = 0ull;
             }
-            if (tid == 0) {
-                p.approx_count[qi] = n;
-                if (p.stats) {
-                    jv_query_stats st;
-                    st.visited = visited;
-                    st.expanded = expanded;
-                    st.expanded_base = expanded;
-                    st.reranked = 0;
-                    p.stats[qi] = st;
-                }
+            if (tid == 0 && p.stats) {
+                jv_query_stats st;
+                st.visited = visited;
+                st.expanded = expanded;
+                st.expanded_base = expanded;
+                st.reranked = 0;
+                p.stats[qi] = st;
             }
         }
         JV_PHASE(6)

@@ -354,7 +354,11 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
             if (tid < ns) {
                 const uint64_t mine = surv[tid];
                 const uint64_t a = mine >> 1;
-                const int pos = count_better(list, n, a) + count_surv_better(a);
+                int pos = count_better(list, n, a) + count_surv_better(a);
+                // a node can be queued twice in one step (the visited filter evicted an entry that was inserted in this
+                // very step): equal keys are ordered by queue index so that every element keeps its own slot (no holes);
+                // the copy is removed when the list is emitted
+                for (int j = 0; j < tid; j++) pos += ((surv[j] >> 1) == a) ? 1 : 0;
                 if (pos < L) out[pos] = mine;
             }
             for (int t = kFThreads - 1 - tid; t < n; t += kFThreads) { // list entries on the high warps: survivors use the low ones
@@ -373,9 +377,19 @@ __global__ void __launch_bounds__(kFThreads, 2) fast_search_kernel(const SearchP
         {
             const uint64_t *list = cur ? list1 : list0;
             uint64_t *o = p.approx_keys + (int64_t)qi * L;
-            for (int i = tid; i < L; i += kFThreads) o[i] = i < n ? jv_mk_key(fkey_score(list[i]), fkey_node(list[i])) : 0ull;
+            int dup = 0; // a node scored twice in one step sits in two adjacent slots (see the merge)
+            for (int i = tid + 1; i < n; i += kFThreads) dup |= ((list[i] >> 1) == (list[i - 1] >> 1)) ? 1 : 0;
+            if (!__syncthreads_or(dup)) {
+                for (int i = tid; i < L; i += kFThreads) o[i] = i < n ? jv_mk_key(fkey_score(list[i]), fkey_node(list[i])) : 0ull;
+                if (tid == 0) p.approx_count[qi] = n;
+            } else if (tid == 0) { // rare: serial compaction
+                int w = 0;
+                for (int i = 0; i < n; i++)
+                    if (i == 0 || (list[i] >> 1) != (list[i - 1] >> 1)) o[w++] = jv_mk_key(fkey_score(list[i]), fkey_node(list[i]));
+                p.approx_count[qi] = w;
+                for (; w < L; w++) o[w] = 0ull;
+            }
             if (tid == 0) {
-                p.approx_count[qi] = n;
                 if (p.stats) {
                     jv_query_stats st;
                     st.visited = visited;

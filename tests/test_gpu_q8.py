@@ -149,3 +149,22 @@ def test_single_query_and_tiny_graph(jv, fx_dot):
         wd, ws, wc, _ = small.oracle_index(adc_order=-8).search(q, 10, 400)
         np.testing.assert_array_equal(r.docs, wd)
         np.testing.assert_array_equal(r.counts, wc)
+
+
+def test_large_host_batches_are_pipelined_in_chunks(jv, fx_dot):
+    """jv_search_batch splits staged batches of >= 4096 queries into chunks whose H2D copy overlaps the previous chunk's
+    kernels; results must be those of the small batch, query by query."""
+    fx = fx_dot
+    reps = 4200 // len(fx.queries) + 1
+    big = np.tile(fx.queries, (reps, 1))[:4200]
+    for flags in (jv.native.FLAG_LUT_U8, 0):
+        with fx.gpu_index(jv, flags=flags) as gi:
+            small = gi.search(fx.queries, 10, 50)
+            r = gi.search(big, 10, 50)
+            nq = len(fx.queries)
+            for t in range(0, 4200, nq):
+                m = min(nq, 4200 - t)
+                np.testing.assert_array_equal(r.docs[t:t + m], small.docs[:m])
+                np.testing.assert_array_equal(r.scores[t:t + m], small.scores[:m])
+                np.testing.assert_array_equal(r.counts[t:t + m], small.counts[:m])
+                np.testing.assert_array_equal(r.stats[t:t + m, 1:], small.stats[:m, 1:])
