@@ -451,33 +451,36 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
     JV_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     if (abytes) JV_CUDA_TRY(cudaMemcpyAsync(c->accept.p, p->accept_bits, abytes, cudaMemcpyHostToDevice, c->stream));
     int launches = 0;
-    // Large staged batches are pipelined: the queries travel in up to 8 chunks on a copy stream and the kernels of chunk i
-    // (table build, traversal, rerank) run while chunk i+1 is still on the PCIe bus.  Per-query accept bitsets keep the
-    // single-shot path (their stride is relative to the whole batch).
-    int nchunks = (!zero_copy && nq >= 4096 && !(p->accept_bits && p->accept_stride_words)) ? (nq >= 16384 ? 8 : 4) : 1;
-    if (const char *e = getenv("JVGPU_H2D_CHUNKS")) { // diagnostics: 1 disables the pipeline
-        const int v = atoi(e);
-        if (v >= 1 && v <= 8 && nchunks > 1) nchunks = v;
+    // Large staged batches are pipelined: a small first chunk (1/8 of the batch: its copy is the only one that is exposed)
+    // and then chunks of <= 16384 queries travel on a copy stream while the kernels of the previous chunk (table build,
+    // traversal, rerank) run.  Per-query accept bitsets keep the single-shot path (their stride is relative to the batch).
+    int bounds[9] = {0, nq, 0, 0, 0, 0, 0, 0, 0}, nchunks = 1;
+    if (!zero_copy && nq >= 4096 && !(p->accept_bits && p->accept_stride_words) && getenv("JVGPU_H2D_SINGLE") == nullptr) {
+        int first = nq / 8;
+        bounds[1] = first;
+        nchunks = 1;
+        int rest = nq - first, parts = (rest + 16383) / 16384;
+        if (parts > 7) parts = 7;
+        for (int i = 1; i <= parts; i++) bounds[1 + i] = first + (int)((int64_t)rest * i / parts);
+        nchunks = 1 + parts;
     }
-    const bool serial_dbg = getenv("JVGPU_H2D_SERIAL") != nullptr;
     if (nchunks > 1) {
         JV_CUDA_TRY(cudaEventRecord(c->chunk_ev[0], c->stream)); // the copy stream must not overtake earlier work on these buffers
         JV_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));
-        const int per = (nq + nchunks - 1) / nchunks;
+        int per = 0;
+        for (int ci = 0; ci < nchunks; ci++) per = bounds[ci + 1] - bounds[ci] > per ? bounds[ci + 1] - bounds[ci] : per;
         // approximate-list scratch for the largest chunk is allocated once, before anything is enqueued
         JV_TRY(c->approx_keys.ensure((size_t)per * p->rerank_k * 8));
         JV_TRY(c->approx_count.ensure((size_t)per * 4));
         for (int ci = 0; ci < nchunks; ci++) {
-            const int q0 = ci * per, nqc = nq - q0 < per ? nq - q0 : per;
-            if (nqc <= 0) break;
+            const int q0 = bounds[ci], nqc = bounds[ci + 1] - q0;
             JV_CUDA_TRY(cudaMemcpyAsync(c->queries.as<float>() + (size_t)q0 * ix->dim, queries + (size_t)q0 * ix->dim, (size_t)nqc * ix->dim * 4,
                                         cudaMemcpyHostToDevice, c->copy_stream));
             JV_CUDA_TRY(cudaEventRecord(c->chunk_ev[ci], c->copy_stream));
         }
         for (int ci = 0; ci < nchunks; ci++) {
-            const int q0 = ci * per, nqc = nq - q0 < per ? nq - q0 : per;
-            if (nqc <= 0) break;
-            JV_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ev[serial_dbg ? nchunks - 1 : ci], 0));
+            const int q0 = bounds[ci], nqc = bounds[ci + 1] - q0;
+            JV_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ev[ci], 0));
             JV_TRY(search_core(ix, c, c->queries.as<float>() + (size_t)q0 * ix->dim, nqc, p, d_accept, c->out_doc.as<int32_t>() + (size_t)q0 * p->k,
                                c->out_score.as<float>() + (size_t)q0 * p->k, c->out_count.as<int32_t>() + q0,
                                c->stats.as<jv_query_stats>() + q0, &launches, ci == 0));
