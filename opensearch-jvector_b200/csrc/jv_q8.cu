@@ -606,9 +606,26 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
                             asm volatile("" ::"r"(acc));
                             JV_PHASE(9)
                         }
+                        // queue the rows that beat the list's worst entry: one shared-memory atomic per warp and pass
+                        uint64_t ka[NU];
+                        uint32_t bal[NU];
+                        int total = 0;
 #pragma unroll
-                        for (int u = 0; u < NU; u++)
-                            if (sl == 0 && nbv[u] >= 0) offer(s[u], nbv[u]);
+                        for (int u = 0; u < NU; u++) {
+                            ka[u] = nbv[u] >= 0 ? (qkey_pack(ord_of(s[u], nbv[u]), nbv[u]) >> 1) : 0ull;
+                            bal[u] = __ballot_sync(JV_FULL_MASK, sl == 0 && ka[u] > worst);
+                            total += __popc(bal[u]);
+                        }
+                        if (total) { // warp-uniform
+                            int slot = 0;
+                            if (lane == 0) slot = atomicAdd(&s_ns[par], total);
+                            slot = __shfl_sync(JV_FULL_MASK, slot, 0);
+#pragma unroll
+                            for (int u = 0; u < NU; u++) {
+                                if ((bal[u] >> lane) & 1u) surv[slot + __popc(bal[u] & ((1u << lane) - 1u))] = ka[u];
+                                slot += __popc(bal[u]);
+                            }
+                        }
                         JV_PHASE(10)
                     };
                     for (int i0 = 0; i0 < nn; i0 += NG * U) {
@@ -804,6 +821,10 @@ static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
     if (occ < 1) {
         set_error("search (8-bit table): kernel does not fit on an SM (smem %zu)", smem);
         return JV_ERR_UNSUPPORTED;
+    }
+    if (const char *e = getenv("JVGPU_Q8_OCC")) { // diagnostics: cap the CTAs per SM
+        const int v = atoi(e);
+        if (v >= 1 && v < occ) occ = v;
     }
     int grid = ix->sm_count * occ;
     if (grid > p.nq) grid = p.nq;
