@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.helpers import lucene_score, make_fixture, recall
+from tests.helpers import clustered, lucene_score, make_fixture, recall
 
 
 def _search_ids(fx, q, k, over=5, accept=None):
@@ -230,3 +230,25 @@ def test_merge_topk_ties_prefer_lower_doc():
     scores = np.array([[[0.9, 0.5, 0.0]], [[0.9, 0.5, 0.1]]], np.float32)
     d, s, c = O.merge_topk(docs, scores, 3)
     assert list(d[0]) == [2, 5, 7] and c[0] == 3
+
+
+def test_quantised_adc_table_bounds_and_recall():
+    """adc_order = -8 (the 8-bit table the GPU production traversal uses): every entry lies inside its ball bound, the
+    integer sum reproduces the fp32 ADC sum within M * delta / 2, and recall@10 stays within the north-star gate."""
+    base, q = clustered(3000, 64, 60, seed=17, normalize=True)
+    for sim, m in ((O.SIM_DOT, 16), (O.SIM_EUCLIDEAN, 32), (O.SIM_COSINE, 8)):
+        fx = make_fixture(sim, base, q, max_degree=16, pq_m=m)
+        ix8, ix = fx.oracle_index(adc_order=-8), fx.oracle_index()
+        q8, prm = ix8.lut_q8(q)
+        lut = O.pq_lut(sim, 64, m, 256, fx.codebooks, fx.gcent, q)
+        delta, lo_sum = prm[:, 0], prm[:, 1]
+        assert (delta > 0).all() and q8.max() <= 255
+        codes = fx.codes[:200]
+        isum = q8[:, np.arange(m)[None, :], codes].astype(np.int64).sum(axis=2)          # [nq, 200]
+        fsum = lut[:, np.arange(m)[None, :], codes].astype(np.float64).sum(axis=2)
+        approx = delta[:, None].astype(np.float64) * isum + lo_sum[:, None]
+        assert (np.abs(approx - fsum) <= m * delta[:, None] * 0.5 + 1e-4).all()
+        gt = ix.exact_topk(q, 10)[0]
+        r8 = ix8.search(q, 10, 50)[0]
+        r32 = ix.search(q, 10, 50)[0]
+        assert recall(r8, gt) >= recall(r32, gt) - 0.01
