@@ -326,7 +326,7 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
 // ---------------------------------------------------------------------------------------------------------------
 // K2: traversal
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kQMaxE = 4;          // candidates per step (one per warp)
+constexpr int kQMaxE = 6;          // candidates per step (warp w expands candidates w, w + W, ..)
 
 struct Q8Params {
     const int32_t *adjacency;
@@ -801,7 +801,7 @@ static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
     if (want < 1024) want = 1024;
     int best_occ = 0, best_log2 = 0;
     for (int occ = 8; occ >= 1; occ--) {
-        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 384 - (int64_t)fixed; // 1 KB system + static __shared__
+        const int64_t per = (int64_t)(sm_total / occ) - 1024 - 512 - (int64_t)fixed; // 1 KB system + static __shared__
         if (per < 1024 * 4) continue;
         int lg = 10;
         while (lg < 15 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
