@@ -232,8 +232,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1 and args.impl == "ours":
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL writes its debug output (version banner included) to stdout by default: send it to stderr so that
+        # rank 0's stdout is exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
