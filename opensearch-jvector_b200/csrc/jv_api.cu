@@ -353,10 +353,17 @@ static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, i
         c->lut_timed = false;
         JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     }
-    JV_TRY(launch_search(ix, c, a, launches));
+    a.fuse_k = p->k;
+    a.rerank_floor = p->rerank_floor;
+    a.d_out_doc = d_out_doc;
+    a.d_out_score = d_out_score;
+    a.d_out_count = d_out_count;
+    bool reranked = false;
+    JV_TRY(launch_search(ix, c, a, launches, &reranked));
     if (timed) JV_CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    JV_TRY(launch_rerank(ix, c, d_queries, nq, p->k, p->rerank_k, p->rerank_floor, a.d_approx_keys, a.d_approx_count, d_out_doc,
-                         d_out_score, d_out_count, d_stats, launches));
+    if (!reranked)
+        JV_TRY(launch_rerank(ix, c, d_queries, nq, p->k, p->rerank_k, p->rerank_floor, a.d_approx_keys, a.d_approx_count, d_out_doc,
+                             d_out_score, d_out_count, d_stats, launches));
     if (timed) JV_CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     return JV_OK;
 }

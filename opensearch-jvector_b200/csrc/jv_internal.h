@@ -75,13 +75,20 @@ struct SearchLaunch {
     int expand_width = 0;    // 0 = default (4), >= 1 explicit width (fast kernel); -1 = strict reference-order kernel
     int entry_override;      // -1 = index entry
     int64_t n_limit;         // nodes >= n_limit are ignored (graph builder); n for queries
+    // optional: let the traversal kernel run K3 as its epilogue (production 8-bit path); fuse_k = 0 -> never fused
+    int fuse_k = 0;
+    float rerank_floor = 0.f;
+    int32_t *d_out_doc = nullptr;
+    float *d_out_score = nullptr;
+    int32_t *d_out_count = nullptr;
 };
-int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches);
+// *reranked (nullable) is set when the launched kernel already produced the final top-k (fused K3)
+int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked = nullptr);
 
 // K1+K2 with the 8-bit table (jv_q8.cu)
 bool q8_search_supported(const jv_index *ix, int L, int R);
 int q8_lut_bytes(int nj); // table bytes per query in the bank-interleaved layout
-int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches);
+int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked);
 int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, uint8_t *d_lut, float4 *d_qparams);
 int32_t launch_permute_codes(cudaStream_t stream, const uint8_t *d_codes, int64_t n, int M, int stride, int NJ, uint8_t *d_out);
 

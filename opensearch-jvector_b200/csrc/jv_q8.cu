@@ -26,6 +26,7 @@
 
 #include <type_traits>
 
+#include "jv_rerank_body.cuh"
 #include "jv_search_common.cuh"
 
 namespace jv {
@@ -341,6 +342,13 @@ struct Q8Params {
     int *dbg;
     int64_t n;
     int nq, L, R, entry, sim, NJ, lutb, hash_log2, E, surv_cap;
+    // fused K3 (exact rerank + top-k as the epilogue of every query; fuse_k = 0: write approx_keys for a separate rerank kernel)
+    int fuse_k, dim;
+    float rerank_floor;
+    const float *queries, *vectors, *vec_norm;
+    const int32_t *ord_to_doc;
+    int32_t *out_doc, *out_count;
+    float *out_score;
 };
 
 // list key: order word (32 bits) | (0x7fffffff - node) << 1 | unexpanded.  The order word is the integer ADC sum itself
@@ -749,10 +757,11 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             step++;
         }
 
-        // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank kernel
+        // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank step
         {
             const uint64_t *list = cur ? list1 : list0;
-            uint64_t *o = p.approx_keys + (int64_t)qi * L;
+            uint64_t *akeys = cur ? list0 : list1; // fused rerank: converted keys go to the idle list buffer
+            uint64_t *o = p.fuse_k ? akeys : p.approx_keys + (int64_t)qi * L;
             auto key_of = [&](uint64_t k) -> uint64_t {
                 const int32_t node = qkey_node(k);
                 const uint32_t ord = (uint32_t)(k >> 32);
@@ -761,23 +770,41 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             };
             int dup = 0; // a node scored twice in one step (see the merge) sits in two adjacent slots
             for (int i = tid + 1; i < n; i += kQThreads) dup |= ((list[i] >> 1) == (list[i - 1] >> 1)) ? 1 : 0;
+            int cnt = n;
             if (!__syncthreads_or(dup)) {
-                for (int i = tid; i < L; i += kQThreads) o[i] = i < n ? key_of(list[i]) : 0ull;
-                if (tid == 0) p.approx_count[qi] = n;
-            } else if (tid == 0) { // rare: serial compaction
-                int w = 0;
-                for (int i = 0; i < n; i++)
-                    if (i == 0 || (list[i] >> 1) != (list[i - 1] >> 1)) o[w++] = key_of(list[i]);
-                p.approx_count[qi] = w;
-                for (; w < L; w++) o[w] = 0ull;
+                for (int i = tid; i < (p.fuse_k ? n : L); i += kQThreads) o[i] = i < n ? key_of(list[i]) : 0ull;
+            } else { // rare: serial compaction
+                if (tid == 0) {
+                    int w = 0;
+                    for (int i = 0; i < n; i++)
+                        if (i == 0 || (list[i] >> 1) != (list[i - 1] >> 1)) o[w++] = key_of(list[i]);
+                    s_nn[0] = w; // broadcast slot (reset at the top of the next query)
+                    for (; !p.fuse_k && w < L; w++) o[w] = 0ull;
+                }
+                __syncthreads();
+                cnt = s_nn[0];
             }
-            if (tid == 0 && p.stats) {
-                jv_query_stats st;
-                st.visited = visited;
-                st.expanded = expanded;
-                st.expanded_base = expanded;
-                st.reranked = 0;
-                p.stats[qi] = st;
+            int reranked = 0;
+            if (p.fuse_k) {
+                // ---- K3 as the epilogue: the table is no longer needed, its shared memory holds the fp32 query and the keys
+                __syncthreads();
+                float *sq = reinterpret_cast<float *>(smem_raw);
+                uint64_t *rkeys = reinterpret_cast<uint64_t *>(smem_raw + ((((size_t)p.dim * 4) + 15) & ~(size_t)15));
+                const bool vec4 = (p.dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
+                reranked = rerank_query<kQThreads>(p.vectors, p.vec_norm, p.ord_to_doc, p.dim, p.sim, 1, p.queries + (int64_t)qi * p.dim, vec4,
+                                                   p.fuse_k, cnt, p.rerank_floor, akeys, sq, rkeys, p.out_doc + (int64_t)qi * p.fuse_k,
+                                                   p.out_score + (int64_t)qi * p.fuse_k, p.out_count + qi);
+            }
+            if (tid == 0) {
+                p.approx_count[qi] = cnt;
+                if (p.stats) {
+                    jv_query_stats st;
+                    st.visited = visited;
+                    st.expanded = expanded;
+                    st.expanded_base = expanded;
+                    st.reranked = reranked;
+                    p.stats[qi] = st;
+                }
             }
         }
         JV_PHASE(6)
@@ -841,7 +868,7 @@ bool q8_search_supported(const jv_index *ix, int L, int R) {
 }
 
 // LUT build + traversal for queries [0, nq) in chunks bounded by the table staging buffer
-int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches) {
+int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked) {
     const int lutb = q8_lut_bytes(ix->q8_nj);
     // staging buffer: <= 512 MB of tables per chunk (10 922 queries at M = 192)
     int chunk = (int)((size_t)512 * 1024 * 1024 / (size_t)lutb);
@@ -883,6 +910,24 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         p.NJ = ix->q8_nj;
         p.lutb = lutb;
         p.E = E;
+        p.dim = ix->dim;
+        // K3 can run as the traversal's epilogue (JVGPU_Q8_FUSED=1).  Measured at cfg2: 2.67 ms fused vs 2.34 ms with the
+        // separate rerank kernel — a 4-warp CTA gathers its 50 rows one DRAM round trip after the other while it holds
+        // 1/4 of an SM; the stand-alone K3 keeps 16 CTAs per SM in flight (0.31 ms, 0.76 of the HBM roofline) — so off by default.
+        const bool fuse = a.fuse_k > 0 && !ix->vectors_on_host && (size_t)ix->dim * 4 + 16 + (size_t)a.rerank_k * 8 <= (size_t)lutb &&
+                          getenv("JVGPU_Q8_FUSED") != nullptr;
+        if (fuse) {
+            p.fuse_k = a.fuse_k;
+            p.rerank_floor = a.rerank_floor;
+            p.queries = a.d_queries + (int64_t)q0 * ix->dim;
+            p.vectors = ix->vectors_dev;
+            p.vec_norm = ix->vec_norm.as<float>();
+            p.ord_to_doc = ix->ord_to_doc.as<int32_t>();
+            p.out_doc = a.d_out_doc + (int64_t)q0 * a.fuse_k;
+            p.out_score = a.d_out_score + (int64_t)q0 * a.fuse_k;
+            p.out_count = a.d_out_count + q0;
+        }
+        if (reranked) *reranked = fuse;
         p.surv_cap = E * ((ix->R + 31) / 32) * 32;
         int32_t st;
         const bool prof = getenv("JVGPU_PROFILE") != nullptr; // per-phase cycle counters (costs registers): diagnostics only

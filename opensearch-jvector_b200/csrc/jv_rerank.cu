@@ -7,6 +7,7 @@
 // All exact scores use the canonical fp32 reduction of jv_common.cuh, bit-identical to the oracle, so
 // top-k ids match exactly with ties broken towards the lower docId.
 #include "jv_internal.h"
+#include "jv_rerank_body.cuh"
 
 namespace jv {
 
@@ -24,70 +25,12 @@ rerank_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_n
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sq = reinterpret_cast<float *>(smem_raw);
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw + ((((size_t)dim * 4) + 15) & ~(size_t)15));
-    __shared__ float s_qnorm;
-    __shared__ int s_valid, s_reranked;
-    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_valid = 0, s_reranked = 0;
-    const float *gq = queries + (int64_t)qi * dim;
+    const int qi = blockIdx.x;
     const bool vec4 = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
-    const int cnt = approx_count[qi];
-    if (has_pq) {
-        for (int i = tid; i < dim; i += kRerankThreads) sq[i] = __ldg(gq + i);
-        __syncthreads();
-        if (warp == 0) {
-            float qn = jv_warp_reduce_pair<false, false>(sq, sq, dim, lane, (dim & 3) == 0);
-            if (lane == 0) s_qnorm = qn;
-        }
-        __syncthreads();
-    }
-    int reranked = 0;
-    for (int j = warp; j < cnt; j += kRerankThreads / 32) {
-        const uint64_t ak = approx_keys[(int64_t)qi * L + j];
-        const int32_t node = jv_key_id(ak);
-        float s = jv_key_score(ak);
-        uint64_t key = 0ull;
-        const int32_t doc = ord_to_doc ? __ldg(ord_to_doc + node) : node;
-        if (has_pq) {
-            if (s >= rerank_floor) {
-                const float *x = vectors + (int64_t)node * dim;
-                float raw = sim == JV_SIM_EUCLIDEAN ? jv_warp_reduce_pair<true>(sq, x, dim, lane, vec4)
-                                                    : jv_warp_reduce_pair<false>(sq, x, dim, lane, vec4);
-                float xn = sim == JV_SIM_COSINE ? __ldg(vec_norm + node) : 0.f;
-                s = jv_finish_score(sim, raw, s_qnorm, xn); // the PQ reranker is NOT x2-wrapped (JVectorReader.java:352-356)
-                key = jv_mk_key(s, doc);
-                reranked++;
-            }
-        } else {
-            key = jv_mk_key(s, doc); // traversal scores are already exact (and MIP-doubled)
-        }
-        if (lane == 0) keys[j] = key;
-    }
-    __syncthreads();
-    // rank selection: rank = number of strictly better keys (keys are unique: doc ids differ)
-    int valid_local = 0;
-    for (int j = tid; j < cnt; j += kRerankThreads) {
-        const uint64_t my = keys[j];
-        if (my == 0ull) continue;
-        valid_local++;
-        int rank = 0;
-        for (int t = 0; t < cnt; t++) rank += keys[t] > my ? 1 : 0;
-        if (rank < k) {
-            out_doc[(int64_t)qi * k + rank] = jv_key_id(my);
-            out_score[(int64_t)qi * k + rank] = jv_key_score(my);
-        }
-    }
-    if (valid_local) atomicAdd(&s_valid, valid_local);
-    if (lane == 0 && reranked) atomicAdd(&s_reranked, reranked); // `reranked` is warp-uniform
-    __syncthreads();
-    const int nout = s_valid < k ? s_valid : k;
-    for (int j = nout + tid; j < k; j += kRerankThreads) {
-        out_doc[(int64_t)qi * k + j] = -1;
-        out_score[(int64_t)qi * k + j] = 0.f;
-    }
-    if (tid == 0) {
-        out_count[qi] = nout;
-        if (stats) stats[qi].reranked = s_reranked;
-    }
+    const int reranked = rerank_query<kRerankThreads>(vectors, vec_norm, ord_to_doc, dim, sim, has_pq, queries + (int64_t)qi * dim, vec4, k,
+                                                      approx_count[qi], rerank_floor, approx_keys + (int64_t)qi * L, sq, keys,
+                                                      out_doc + (int64_t)qi * k, out_score + (int64_t)qi * k, out_count + qi);
+    if (threadIdx.x == 0 && stats) stats[qi].reranked = reranked;
 }
 
 int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int rerank_k, float rerank_floor,

@@ -286,7 +286,8 @@ static int32_t launch_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_
     return JV_OK;
 }
 
-int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches) {
+int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked) {
+    if (reranked) *reranked = false;
     if (a.nq <= 0) return JV_OK;
     JV_REQUIRE(ix->R <= kMaxR, "max_degree %d exceeds the supported %d", ix->R, kMaxR);
     SearchParams p;
@@ -317,7 +318,7 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     // range thresholds need the reference's two-queue semantics and stay on the strict kernel below.
     const bool plain = a.expand_width >= 0 && a.d_accept == nullptr && !(a.threshold > 0.f);
     if (plain && (ix->flags & JV_INDEX_FLAG_LUT_U8) && a.d_query_ids == nullptr && q8_search_supported(ix, a.rerank_k, ix->R))
-        return launch_search_q8(ix, ctx, a, launches);
+        return launch_search_q8(ix, ctx, a, launches, reranked);
     if (plain && (!ix->has_pq || (p.M & 3) == 0)) {
         const int32_t fs = launch_search_fast(ix, ctx, p, a.expand_width == 0 ? 4 : a.expand_width, f16);
         if (fs == JV_OK && launches) *launches += 1;
