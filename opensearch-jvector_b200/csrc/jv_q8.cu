@@ -103,7 +103,7 @@ struct LutQ8Params {
     int nq, dim, M, NJ, sim, lutb;
 };
 
-template <int S>
+template <int S, bool L2>
 __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
     constexpr int QT = S == 2 ? 8 : 32 / S;     // queries per CTA (QT * S <= 32 query registers per thread)
     constexpr int CH = 32 / S;                 // codes per staged chunk: 128 B per subspace
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
     __shared__ uint32_t range_s[QT];
     __shared__ float inv_s[QT], qn_s[QT];
     const int q0 = blockIdx.x * QT;
-    const bool l2 = p.sim == JV_SIM_EUCLIDEAN;
+    constexpr bool l2 = L2;
 
     if (tid < QT) range_s[tid] = 0u;
     __syncthreads();
@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
     __syncthreads();
 
     // ---- main pass: thread = subspace (lane) of block j; chunks of CH codes staged per warp
+    uint32_t *obase = reinterpret_cast<uint32_t *>(p.lut + (int64_t)q0 * p.lutb) + lane;
+    const uint32_t tstride = (uint32_t)p.lutb >> 2;
+    const bool full = q0 + QT <= p.nq;
     for (int j = warp; j < p.NJ; j += nw) {
         const int m = j * 32 + lane;
         float qr[QT][S], inv[QT], nlo[QT];
@@ -238,9 +241,7 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
             const unsigned char *row = stage + (size_t)(buf * 32 + lane) * ROWB;
 #pragma unroll
             for (int e = 0; e < EP; e++) {
-                uint32_t w[QT];
-#pragma unroll
-                for (int t = 0; t < QT; t++) w[t] = 0u;
+                int qv[QT][4]; // rounded entries of the 4 codes that share a table word
 #pragma unroll
                 for (int quarter = 0; quarter < 4; quarter++) {
                     float cv[S];
@@ -267,14 +268,18 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
                                 acc = __fmaf_rn(qr[t][jj], cv[jj], acc);
                             }
                         }
-                        w[t] |= sat_u8_rn(__fmaf_rn(acc, inv[t], nlo[t])) << (8 * quarter);
+                        qv[t][quarter] = __float2int_rn(__fmaf_rn(acc, inv[t], nlo[t])); // NaN -> 0; saturated to a byte below
                     }
                 }
                 const int c6 = ch * EP + e; // = c & 63
-                const size_t word = ((size_t)(j >> 1) * 16384 + (size_t)c6 * 256 + (size_t)(j & 1) * 128) / 4 + lane;
+                const uint32_t word = (uint32_t)((j >> 1) * 16384 + c6 * 256 + (j & 1) * 128) / 4u;
 #pragma unroll
                 for (int t = 0; t < QT; t++) {
-                    if (q0 + t < p.nq) reinterpret_cast<uint32_t *>(p.lut + (int64_t)(q0 + t) * p.lutb)[word] = m < p.M ? w[t] : 0u;
+                    // two cvt.pack.sat.u8.s32: bytes (q0, q1, q2, q3) = clamp(entry, 0, 255)
+                    uint32_t hi, w;
+                    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(qv[t][3]), "r"(qv[t][2]), "r"(0));
+                    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(qv[t][1]), "r"(qv[t][0]), "r"(hi));
+                    if (full || q0 + t < p.nq) obase[(uint32_t)t * tstride + word] = m < p.M ? w : 0u;
                 }
             }
             __syncwarp(); // the buffer is refilled two iterations from now
@@ -310,16 +315,20 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
     const size_t smem = lut_q8_smem(nw, S, p.NJ * 32);
     const int qt = S == 2 ? 8 : 32 / S;
     const int grid = (nq + qt - 1) / qt;
+    const bool l2 = ix->sim == JV_SIM_EUCLIDEAN;
+#define JV_LUT_LAUNCH(SV, LV)                                                                                              \
+    do {                                                                                                                   \
+        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<SV, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        lut_q8_kernel<SV, LV><<<grid, nw * 32, smem, stream>>>(p);                                                          \
+    } while (0)
     if (S == 4) {
-        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lut_q8_kernel<4><<<grid, nw * 32, smem, stream>>>(p);
+        if (l2) JV_LUT_LAUNCH(4, true); else JV_LUT_LAUNCH(4, false);
     } else if (S == 2) {
-        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lut_q8_kernel<2><<<grid, nw * 32, smem, stream>>>(p);
+        if (l2) JV_LUT_LAUNCH(2, true); else JV_LUT_LAUNCH(2, false);
     } else {
-        JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lut_q8_kernel<8><<<grid, nw * 32, smem, stream>>>(p);
+        if (l2) JV_LUT_LAUNCH(8, true); else JV_LUT_LAUNCH(8, false);
     }
+#undef JV_LUT_LAUNCH
     JV_CUDA_TRY(cudaGetLastError());
     return JV_OK;
 }
