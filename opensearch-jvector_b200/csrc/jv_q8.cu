@@ -623,25 +623,23 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
                             asm volatile("" ::"r"(acc));
                             JV_PHASE(9)
                         }
-                        // queue the rows that beat the list's worst entry: one shared-memory atomic per warp and pass
-                        uint64_t ka[NU];
-                        uint32_t bal[NU];
-                        int total = 0;
+                        // queue the rows that beat the list's worst entry.  After the butterfly every lane of a group holds the
+                        // group's sums: lane sl = u takes row u, so one key, one ballot and one shared-memory atomic serve all
+                        // NU rows of the 4 groups
+                        uint32_t my_s = s[0];
+                        int32_t my_nb = nbv[0];
 #pragma unroll
-                        for (int u = 0; u < NU; u++) {
-                            ka[u] = nbv[u] >= 0 ? (qkey_pack(ord_of(s[u], nbv[u]), nbv[u]) >> 1) : 0ull;
-                            bal[u] = __ballot_sync(JV_FULL_MASK, sl == 0 && ka[u] > worst);
-                            total += __popc(bal[u]);
+                        for (int u = 1; u < NU; u++) {
+                            my_s = sl == u ? s[u] : my_s;
+                            my_nb = sl == u ? nbv[u] : my_nb;
                         }
-                        if (total) { // warp-uniform
+                        const uint64_t ka = (sl < NU && my_nb >= 0) ? (qkey_pack(ord_of(my_s, my_nb), my_nb) >> 1) : 0ull;
+                        const uint32_t bal = __ballot_sync(JV_FULL_MASK, ka > worst);
+                        if (bal) { // warp-uniform
                             int slot = 0;
-                            if (lane == 0) slot = atomicAdd(&s_ns[par], total);
+                            if (lane == 0) slot = atomicAdd(&s_ns[par], __popc(bal));
                             slot = __shfl_sync(JV_FULL_MASK, slot, 0);
-#pragma unroll
-                            for (int u = 0; u < NU; u++) {
-                                if ((bal[u] >> lane) & 1u) surv[slot + __popc(bal[u] & ((1u << lane) - 1u))] = ka[u];
-                                slot += __popc(bal[u]);
-                            }
+                            if ((bal >> lane) & 1u) surv[slot + __popc(bal & ((1u << lane) - 1u))] = ka;
                         }
                         JV_PHASE(10)
                     };
