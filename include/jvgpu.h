@@ -108,7 +108,17 @@ typedef struct jv_index_desc {
     const uint8_t *pq_codes;   /* [n * M]                                                       */
     int32_t device;            /* CUDA device ordinal                                           */
     uint32_t flags;            /* JV_INDEX_FLAG_*                                               */
+    /* ---- struct_size >= 128: NVQ-inline segments ("nvq+pq", JVectorWriter.java:436-466).  The graph nodes carry
+     * 8-bit non-uniform-quantised vectors instead of fp32; the reranker (view.rerankerFor, JVectorReader.java:352-358)
+     * scores the dequantised vector: JVectorIndexQuantization.java:316-361.  `vectors` may then be NULL (brute force is
+     * unsupported on such segments, as in the reference: JVectorQuantizedNvqVectorValues.java:33-36). */
+    int32_t nvq_m;             /* number of NVQ sub-vectors (0 = no NVQ); sizes per the PQ split rule */
+    int32_t nvq_reserved;
+    const uint8_t *nvq_bytes;  /* [n * dim] quantised components                                */
+    const float *nvq_params;   /* [n * nvq_m * 4] growthRate, midpoint, minValue, maxValue per sub-vector */
+    const float *nvq_global_mean; /* [dim] NVQuantization.globalMean                            */
 } jv_index_desc;
+#define JV_INDEX_DESC_SIZE_V1 96 /* struct_size of the layout without the NVQ fields: still accepted */
 
 typedef struct jv_index jv_index; /* opaque */
 

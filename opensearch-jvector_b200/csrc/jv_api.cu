@@ -139,15 +139,29 @@ int32_t jv_device_count(int32_t *out_count) {
     return JV_OK;
 }
 
-int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
-    JV_REQUIRE(d != nullptr && out != nullptr, "desc/out is NULL");
+int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
+    JV_REQUIRE(desc != nullptr && out != nullptr, "desc/out is NULL");
     *out = nullptr;
-    JV_REQUIRE(d->struct_size == (int32_t)sizeof(jv_index_desc), "jv_index_desc.struct_size mismatch (%d vs %zu)", d->struct_size,
-               sizeof(jv_index_desc));
+    JV_REQUIRE(desc->struct_size == (int32_t)sizeof(jv_index_desc) || desc->struct_size == JV_INDEX_DESC_SIZE_V1,
+               "jv_index_desc.struct_size mismatch (%d vs %zu or %d)", desc->struct_size, sizeof(jv_index_desc), JV_INDEX_DESC_SIZE_V1);
+    jv_index_desc dcopy; // the V1 layout has no NVQ fields: zero-filled
+    memset(&dcopy, 0, sizeof(dcopy));
+    memcpy(&dcopy, desc, (size_t)desc->struct_size);
+    const jv_index_desc *d = &dcopy;
+    const bool has_nvq = d->nvq_m > 0;
     JV_REQUIRE(d->similarity >= JV_SIM_EUCLIDEAN && d->similarity <= JV_SIM_MIP, "unknown similarity ordinal %d", d->similarity);
     JV_REQUIRE(d->dim >= 1 && d->n >= 0 && d->n < 0x7fffffffLL, "bad dim/n");
     JV_REQUIRE(d->max_degree >= 1 && d->max_degree <= 128, "max_degree must be in [1,128]");
-    JV_REQUIRE(d->n == 0 || (d->adjacency && d->vectors), "adjacency/vectors are NULL");
+    JV_REQUIRE(d->n == 0 || d->adjacency, "adjacency is NULL");
+    JV_REQUIRE(d->n == 0 || d->vectors || (has_nvq && d->pq_m > 0), "vectors are NULL (only an nvq+pq segment may omit them)");
+    if (has_nvq) {
+        JV_REQUIRE(d->nvq_bytes && d->nvq_params && d->nvq_global_mean, "nvq_bytes/nvq_params/nvq_global_mean are NULL");
+        JV_REQUIRE(d->nvq_m <= 32 && d->nvq_m <= d->dim, "nvq_m must be in [1, 32]");
+        if (d->pq_m <= 0) {
+            set_error("NVQ-inline segments without the auxiliary PQ blob (exact traversal scored by the NVQ reranker) are not supported");
+            return JV_ERR_UNSUPPORTED;
+        }
+    }
     JV_REQUIRE(d->n == 0 || (d->entry_node >= 0 && d->entry_node < d->n), "entry_node out of range");
     const bool has_pq = d->pq_m > 0;
     if (has_pq) {
@@ -186,7 +200,7 @@ int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
     cudaMemset(ix->dbg.p, 0, 256);
     const size_t n = (size_t)d->n;
     if ((st = upload(ix->adjacency, d->adjacency, n * d->max_degree * 4, &total)) != JV_OK) return fail(st);
-    if (d->flags & JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE) {
+    if ((d->flags & JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE) && d->vectors) {
         // cfg 5: fp32 rerank vectors stay in pinned, device-mapped host memory
         cudaError_t e = cudaHostAlloc(&ix->vectors_host, n * d->dim * 4 + 16, cudaHostAllocMapped | cudaHostAllocPortable);
         if (e != cudaSuccess) {
@@ -202,13 +216,25 @@ int32_t jv_index_create(const jv_index_desc *d, jv_index **out) {
         }
         ix->vectors_dev = static_cast<float *>(dp);
         ix->vectors_on_host = true;
-    } else {
+    } else if (d->vectors) {
         if ((st = upload(ix->vectors, d->vectors, n * d->dim * 4, &total)) != JV_OK) return fail(st);
         ix->vectors_dev = ix->vectors.as<float>();
     }
+    if (has_nvq) {
+        PqShape sh;
+        sh.init(d->dim, d->nvq_m, 1);
+        std::vector<int32_t> off(sh.off.begin(), sh.off.end());
+        off.push_back(d->dim);
+        if ((st = upload(ix->nvq_bytes, d->nvq_bytes, n * d->dim, &total)) != JV_OK) return fail(st);
+        if ((st = upload(ix->nvq_params, d->nvq_params, n * d->nvq_m * 16, &total)) != JV_OK) return fail(st);
+        if ((st = upload(ix->nvq_gmean, d->nvq_global_mean, (size_t)d->dim * 4, &total)) != JV_OK) return fail(st);
+        if ((st = upload(ix->nvq_off, off.data(), off.size() * 4, &total)) != JV_OK) return fail(st);
+        ix->has_nvq = true;
+        ix->nvq_m = d->nvq_m;
+    }
     if (d->ord_to_doc)
         if ((st = upload(ix->ord_to_doc, d->ord_to_doc, n * 4, &total)) != JV_OK) return fail(st);
-    if (d->similarity == JV_SIM_COSINE && n > 0) {
+    if (d->similarity == JV_SIM_COSINE && n > 0 && ix->vectors_dev) {
         if ((st = ix->vec_norm.alloc(n * 4)) != JV_OK) return fail(st);
         total += (int64_t)n * 4;
         if ((st = launch_vec_norms(nullptr, ix->vectors_dev, d->n, d->dim, ix->vec_norm.as<float>())) != JV_OK) return fail(st);
@@ -517,6 +543,10 @@ int32_t jv_exact_topk_dev(jv_index *ix, const float *d_queries, int32_t nq, int3
     if (nq == 0) return JV_OK;
     JV_REQUIRE(d_queries && d_out_doc && d_out_score && d_out_count, "NULL buffer");
     JV_REQUIRE(ix->n > 0, "index is empty");
+    if (!ix->vectors_dev) {
+        set_error("brute force is not supported on NVQ-inline segments (JVectorQuantizedNvqVectorValues.java:33-36)");
+        return JV_ERR_UNSUPPORTED;
+    }
     DeviceGuard guard(ix->device);
     CtxLease lease(ix);
     JV_REQUIRE(lease.c != nullptr, "could not create a search context: %s", get_error());
@@ -536,6 +566,10 @@ int32_t jv_exact_topk(jv_index *ix, const float *queries, int32_t nq, int32_t k,
         for (int64_t i = 0; i < (int64_t)nq * k; i++) out_doc[i] = -1, out_score[i] = 0.f;
         for (int i = 0; i < nq; i++) out_count[i] = 0;
         return JV_OK;
+    }
+    if (!ix->vectors_dev) {
+        set_error("brute force is not supported on NVQ-inline segments (JVectorQuantizedNvqVectorValues.java:33-36)");
+        return JV_ERR_UNSUPPORTED;
     }
     DeviceGuard guard(ix->device);
     CtxLease lease(ix);

@@ -44,6 +44,10 @@ struct jv_index {
     jv::DevBuf fused; // neighbour-interleaved records (optional)
     // 8-bit table path (JV_INDEX_FLAG_LUT_U8): lane-major permuted codes, bounding balls of the subspace codebooks
     jv::DevBuf codes_q8, ball_ctr, ball_rad;
+    // NVQ-inline vectors (nvq+pq segments): the reranker scores the dequantised vector
+    jv::DevBuf nvq_bytes, nvq_params, nvq_gmean, nvq_off;
+    bool has_nvq = false;
+    int nvq_m = 0;
     bool q8_ok = false;
     int q8_nj = 0; // 32-subspace blocks per code row (M rounded up to 32)
     int fused_stride = 0;

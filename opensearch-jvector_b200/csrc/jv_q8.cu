@@ -921,7 +921,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         // K3 can run as the traversal's epilogue (JVGPU_Q8_FUSED=1).  Measured at cfg2: 2.67 ms fused vs 2.34 ms with the
         // separate rerank kernel — a 4-warp CTA gathers its 50 rows one DRAM round trip after the other while it holds
         // 1/4 of an SM; the stand-alone K3 keeps 16 CTAs per SM in flight (0.31 ms, 0.76 of the HBM roofline) — so off by default.
-        const bool fuse = a.fuse_k > 0 && !ix->vectors_on_host && (size_t)ix->dim * 4 + 16 + (size_t)a.rerank_k * 8 <= (size_t)lutb &&
+        const bool fuse = a.fuse_k > 0 && !ix->vectors_on_host && !ix->has_nvq && (size_t)ix->dim * 4 + 16 + (size_t)a.rerank_k * 8 <= (size_t)lutb &&
                           getenv("JVGPU_Q8_FUSED") != nullptr;
         if (fuse) {
             p.fuse_k = a.fuse_k;

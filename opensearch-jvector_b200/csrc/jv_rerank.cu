@@ -21,15 +21,20 @@ __global__ void __launch_bounds__(kRerankThreads)
 rerank_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_norm, const int32_t *__restrict__ ord_to_doc,
               int dim, int sim, int has_pq, const float *__restrict__ queries, int k, int L, float rerank_floor,
               const uint64_t *__restrict__ approx_keys, const int32_t *__restrict__ approx_count, int32_t *out_doc,
-              float *out_score, int32_t *out_count, jv_query_stats *stats) {
+              float *out_score, int32_t *out_count, jv_query_stats *stats, NvqView nvq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sq = reinterpret_cast<float *>(smem_raw);
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw + ((((size_t)dim * 4) + 15) & ~(size_t)15));
+    const size_t qb = (((size_t)dim * 4) + 15) & ~(size_t)15;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw + qb);
+    if (nvq.bytes != nullptr) { // per-warp decode buffers behind the keys
+        nvq.xbuf = reinterpret_cast<float *>(smem_raw + qb + ((((size_t)L * 8) + 15) & ~(size_t)15)); // 16-B aligned: float4 reads
+        nvq.consts = nvq.xbuf + (size_t)(kRerankThreads / 32) * ((dim + 3) & ~3);
+    }
     const int qi = blockIdx.x;
     const bool vec4 = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
     const int reranked = rerank_query<kRerankThreads>(vectors, vec_norm, ord_to_doc, dim, sim, has_pq, queries + (int64_t)qi * dim, vec4, k,
                                                       approx_count[qi], rerank_floor, approx_keys + (int64_t)qi * L, sq, keys,
-                                                      out_doc + (int64_t)qi * k, out_score + (int64_t)qi * k, out_count + qi);
+                                                      out_doc + (int64_t)qi * k, out_score + (int64_t)qi * k, out_count + qi, nvq);
     if (threadIdx.x == 0 && stats) stats[qi].reranked = reranked;
 }
 
@@ -37,12 +42,21 @@ int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int 
                       const uint64_t *d_approx_keys, const int32_t *d_approx_count, int32_t *d_out_doc, float *d_out_score,
                       int32_t *d_out_count, jv_query_stats *d_stats, int *launches) {
     if (nq <= 0) return JV_OK;
-    const size_t smem = ((((size_t)ix->dim * 4) + 15) & ~(size_t)15) + (size_t)rerank_k * 8;
+    size_t smem = ((((size_t)ix->dim * 4) + 15) & ~(size_t)15) + (size_t)rerank_k * 8;
+    NvqView nvq{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+    if (ix->has_nvq) {
+        nvq.bytes = ix->nvq_bytes.as<uint8_t>();
+        nvq.params = ix->nvq_params.as<float>();
+        nvq.gmean = ix->nvq_gmean.as<float>();
+        nvq.off = ix->nvq_off.as<int32_t>();
+        nvq.m = ix->nvq_m;
+        smem = ((smem + 15) & ~(size_t)15) + (size_t)(kRerankThreads / 32) * (((((size_t)ix->dim * 4) + 15) & ~(size_t)15) + (size_t)ix->nvq_m * 16);
+    }
     JV_REQUIRE(smem <= ix->smem_optin - 1024, "rerank_k %d too large for shared memory", rerank_k);
     JV_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<<<nq, kRerankThreads, smem, ctx->stream>>>(
         ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, ix->has_pq ? 1 : 0,
-        d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats);
+        d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats, nvq);
     JV_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return JV_OK;

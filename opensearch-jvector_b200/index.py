@@ -93,12 +93,20 @@ def merge_topk(docs, scores, k: int, device: int = 0):
 class GpuIndex:
     def __init__(self, similarity: int, vectors, adjacency, entry_node: int, ord_to_doc=None, max_doc: Optional[int] = None,
                  pq_m: int = 0, pq_k: int = 0, pq_codebooks=None, pq_global_centroid=None, pq_codes=None, device: int = 0,
-                 flags: int = 0):
+                 flags: int = 0, nvq_m: int = 0, nvq_bytes=None, nvq_params=None, nvq_global_mean=None):
+        """`vectors` may be None for an nvq+pq segment (NVQ-inline vectors + auxiliary PQ codes): the reranker then scores
+        the dequantised NVQ vectors (JVectorReader.java:352-358) and brute force is unsupported, as in the reference."""
         lib = N.load()
+        nb = None if nvq_bytes is None else np.ascontiguousarray(nvq_bytes, dtype=np.uint8)
         v = _f32(vectors)
-        if v.ndim != 2:
-            raise ValueError("vectors must be [n, dim]")
-        self.n, self.dim = v.shape
+        if v is None:
+            if nb is None:
+                raise ValueError("vectors or nvq_bytes are required")
+            self.n, self.dim = nb.shape
+        else:
+            if v.ndim != 2:
+                raise ValueError("vectors must be [n, dim]")
+            self.n, self.dim = v.shape
         adj = np.ascontiguousarray(adjacency, dtype=np.int32).reshape(self.n, -1) if self.n else np.zeros((0, 1), np.int32)
         o2d = None if ord_to_doc is None else np.ascontiguousarray(ord_to_doc, dtype=np.int32)
         self.max_doc = int(max_doc) if max_doc is not None else (
@@ -119,6 +127,9 @@ class GpuIndex:
         d.pq_m, d.pq_k = self.pq_m, self.pq_k
         d.pq_codebooks, d.pq_global_centroid, d.pq_codes = _ptr(cb), _ptr(g), _ptr(codes)
         d.device, d.flags = device, flags
+        nprm, ngm = _f32(nvq_params), _f32(nvq_global_mean)
+        d.nvq_m = nvq_m if nb is not None else 0
+        d.nvq_bytes, d.nvq_params, d.nvq_global_mean = _ptr(nb), _ptr(nprm), _ptr(ngm)
         h = C.c_void_p()
         N.check(lib.jv_index_create(C.addressof(d), C.addressof(h)))
         self._h = h

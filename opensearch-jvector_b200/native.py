@@ -22,6 +22,8 @@ class IndexDesc(C.Structure):
         ("pq_m", C.c_int32), ("pq_k", C.c_int32),
         ("pq_codebooks", C.c_void_p), ("pq_global_centroid", C.c_void_p), ("pq_codes", C.c_void_p),
         ("device", C.c_int32), ("flags", C.c_uint32),
+        ("nvq_m", C.c_int32), ("nvq_reserved", C.c_int32),
+        ("nvq_bytes", C.c_void_p), ("nvq_params", C.c_void_p), ("nvq_global_mean", C.c_void_p),
     ]
 
 

@@ -484,6 +484,121 @@ static inline float adc_score_q8(int sim, const uint8_t *q8, const float *params
 }
 
 /* ------------------------------------------------------------------------------------------
+ * NVQ (non-uniform vector quantisation) of the inline vectors, "nvq+pq" segments.
+ * Decoder: literal restatement of the IN-TREE code JVectorIndexQuantization.java:316-361
+ * (nvqDequantize, logisticNQT, logitNQT) — Math.fma -> fmaf, Math.round(float) -> floor(x + 1/2)
+ * evaluated exactly, Float.floatToIntBits / intBitsToFloat -> memcpy.
+ * Encoder: FIXTURE ONLY.  jVector trains (growthRate, midpoint) per sub-vector with an optimiser that
+ * is out of tree; any (growthRate, midpoint, minValue, maxValue, bytes) tuple is a valid input of
+ * the decoder, so the fixture uses fixed shape parameters and picks every byte as the best
+ * reconstruction under that decoder.
+ * ------------------------------------------------------------------------------------------ */
+static inline int32_t f2i_bits(float f) {
+    int32_t i;
+    memcpy(&i, &f, 4);
+    return i;
+}
+static inline float i2f_bits(int32_t i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+static inline int java_round_f(float a) { return (int)floor((double)a + 0.5); } /* Math.round(float), exact */
+
+/* JVectorIndexQuantization.java:344-351 */
+static float logistic_nqt(float value, float alpha, float x0) {
+    float temp = fmaf(value, alpha, -alpha * x0);
+    int p = java_round_f(temp + 0.5f);
+    int m = f2i_bits(fmaf(temp - (float)p, 0.5f, 1.0f));
+    temp = i2f_bits(m + (int32_t)((uint32_t)p << 23));
+    return temp / (temp + 1.0f);
+}
+/* JVectorIndexQuantization.java:354-361 */
+static float logit_nqt(float scaled, float inverse_alpha, float x0) {
+    float z = scaled / (1.0f - scaled);
+    int32_t temp = f2i_bits(z);
+    int32_t e = temp & 0x7f800000;
+    float p = (float)((e >> 23) - 128);
+    float m = i2f_bits((temp & 0x007fffff) + 0x3f800000);
+    return (m + p) * inverse_alpha + x0;
+}
+typedef struct {
+    float scale, bias, inv_alpha, mid;
+} nvq_sub_t;
+/* the per-sub-vector constants of nvqDequantize, JVectorIndexQuantization.java:320-326 */
+static nvq_sub_t nvq_sub(const float *prm /* growthRate, midpoint, minValue, maxValue */) {
+    nvq_sub_t r;
+    float delta = prm[3] - prm[2];
+    float sgr = prm[0] / delta;
+    r.mid = prm[1] * delta;
+    r.bias = logistic_nqt(prm[2], sgr, r.mid);
+    r.scale = (logistic_nqt(prm[3], sgr, r.mid) - r.bias) / 255.0f;
+    r.inv_alpha = 1.0f / sgr;
+    return r;
+}
+static inline float nvq_component(const nvq_sub_t *c, int b) { return logit_nqt(fmaf((float)b, c->scale, c->bias), c->inv_alpha, c->mid); }
+
+/* nvqDequantize for one vector: out[dim] = decoded + globalMean */
+static void nvq_dequantize_one(const pq_shape *sh, const uint8_t *bytes, const float *params, const float *gmean, float *out) {
+    for (int m = 0; m < sh->M; m++) {
+        nvq_sub_t c = nvq_sub(params + 4 * m);
+        for (int d = 0; d < sh->size[m]; d++) out[sh->off[m] + d] = nvq_component(&c, bytes[sh->off[m] + d]);
+    }
+    for (int i = 0; i < sh->dim; i++) out[i] = out[i] + gmean[i];
+}
+
+JVO_EXPORT void jvo_nvq_dequantize(int64_t n, int32_t dim, int32_t nvq_m, const uint8_t *bytes, const float *params,
+                                   const float *gmean, float *out) {
+    pq_shape sh;
+    pq_shape_init(&sh, dim, nvq_m, 1);
+    for (int64_t i = 0; i < n; i++) nvq_dequantize_one(&sh, bytes + i * dim, params + i * nvq_m * 4, gmean, out + i * dim);
+    pq_shape_free(&sh);
+}
+
+/* FIXTURE encoder: globalMean = per-dimension mean (double sums); per sub-vector minValue/maxValue = extremes of the
+ * centred components, growthRate/midpoint as given; every byte = the code whose reconstruction is closest. */
+JVO_EXPORT void jvo_nvq_encode(const float *vectors, int64_t n, int32_t dim, int32_t nvq_m, float growth_rate, float midpoint,
+                               uint8_t *out_bytes, float *out_params, float *out_gmean) {
+    pq_shape sh;
+    pq_shape_init(&sh, dim, nvq_m, 1);
+    for (int d = 0; d < dim; d++) {
+        double acc = 0.0;
+        for (int64_t i = 0; i < n; i++) acc += (double)vectors[i * dim + d];
+        out_gmean[d] = n > 0 ? (float)(acc / (double)n) : 0.f;
+    }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        for (int m = 0; m < nvq_m; m++) {
+            float *prm = out_params + (i * nvq_m + m) * 4;
+            float lo = INFINITY, hi = -INFINITY;
+            for (int d = 0; d < sh.size[m]; d++) {
+                float x = vectors[i * dim + sh.off[m] + d] - out_gmean[sh.off[m] + d];
+                if (x < lo) lo = x;
+                if (x > hi) hi = x;
+            }
+            if (!(hi > lo)) hi = lo + 1e-6f;
+            prm[0] = growth_rate, prm[1] = midpoint, prm[2] = lo, prm[3] = hi;
+            nvq_sub_t c = nvq_sub(prm);
+            float table[256];
+            for (int b = 0; b < 256; b++) table[b] = nvq_component(&c, b);
+            for (int d = 0; d < sh.size[m]; d++) {
+                float x = vectors[i * dim + sh.off[m] + d] - out_gmean[sh.off[m] + d];
+                int best = 0;
+                float be = INFINITY;
+                for (int b = 0; b < 256; b++) {
+                    float e = fabsf(table[b] - x);
+                    if (e < be) be = e, best = b;
+                }
+                out_bytes[i * dim + sh.off[m] + d] = (uint8_t)best;
+            }
+        }
+    }
+    pq_shape_free(&sh);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Index view + per-thread search scratch
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -493,12 +608,18 @@ typedef struct {
     int adc_order;    /* see adc_sum */
     float *node_norm; /* cosine + PQ only */
     float *ball_ctr, *ball_rad; /* adc_order -8 only */
+    int has_nvq;
+    pq_shape nvq; /* sub-vector split of the NVQ-inline vectors */
 } jvo_index;
 
 JVO_EXPORT jvo_index *jvo_index_create(const jv_index_desc *desc) {
     jvo_index *ix = (jvo_index *)calloc(1, sizeof(jvo_index));
-    ix->d = *desc;
+    memset(&ix->d, 0, sizeof(ix->d)); /* struct_size 96 = layout without the NVQ fields */
+    memcpy(&ix->d, desc, (desc->struct_size > 0 && (size_t)desc->struct_size < sizeof(ix->d)) ? (size_t)desc->struct_size : sizeof(ix->d));
     ix->has_pq = desc->pq_m > 0 && desc->pq_codes && desc->pq_codebooks;
+    ix->has_nvq = ix->d.nvq_m > 0 && ix->d.nvq_bytes && ix->d.nvq_params && ix->d.nvq_global_mean;
+    if (!ix->has_nvq) ix->d.nvq_m = 0;
+    if (ix->has_nvq) pq_shape_init(&ix->nvq, desc->dim, desc->nvq_m, 1);
     if (ix->has_pq) {
         pq_shape_init(&ix->pq, desc->dim, desc->pq_m, desc->pq_k);
         if (desc->similarity == JV_SIM_COSINE) {
@@ -520,6 +641,7 @@ JVO_EXPORT void jvo_index_set_adc_order(jvo_index *ix, int32_t order) {
 JVO_EXPORT void jvo_index_destroy(jvo_index *ix) {
     if (!ix) return;
     if (ix->has_pq) pq_shape_free(&ix->pq);
+    if (ix->has_nvq) pq_shape_free(&ix->nvq);
     free(ix->node_norm);
     free(ix->ball_ctr);
     free(ix->ball_rad);
@@ -534,6 +656,7 @@ typedef struct {
     float *lut, *qc;
     uint8_t *lut8; /* adc_order -8 */
     float *lo8, q8p[2];
+    float *deq; /* NVQ: dequantised vector of the node being reranked */
     uint64_t *sorted;
 } scratch_t;
 
@@ -548,6 +671,7 @@ static scratch_t *scratch_new(const jvo_index *ix) {
         s->lo8 = (float *)malloc(sizeof(float) * (size_t)ix->d.pq_m);
     }
     s->qc = (float *)malloc(sizeof(float) * (size_t)ix->d.dim);
+    s->deq = (float *)malloc(sizeof(float) * (size_t)ix->d.dim);
     return s;
 }
 static void scratch_free(scratch_t *s) {
@@ -559,6 +683,7 @@ static void scratch_free(scratch_t *s) {
     free(s->lut8);
     free(s->lo8);
     free(s->qc);
+    free(s->deq);
     free(s->sorted);
     free(s);
 }
@@ -673,7 +798,13 @@ static void search_one(const jvo_index *ix, scratch_t *S, const float *q, int k,
             float s = key_score(S->sorted[i]);
             if (use_pq) {
                 if (s < rerank_floor) continue;
-                s = exact_score(sim, q, qnorm, d->vectors + (int64_t)node * dim, dim); /* reranker is NOT x2-wrapped */
+                const float *x = d->vectors + (int64_t)node * dim;
+                if (ix->has_nvq) { /* nvq+pq: view.rerankerFor scores the dequantised inline vector (JVectorReader.java:352-358) */
+                    nvq_dequantize_one(&ix->nvq, d->nvq_bytes + (int64_t)node * dim, d->nvq_params + (int64_t)node * d->nvq_m * 4,
+                                       d->nvq_global_mean, S->deq);
+                    x = S->deq;
+                }
+                s = exact_score(sim, q, qnorm, x, dim); /* reranker is NOT x2-wrapped */
                 reranked++;
             }
             int32_t doc = d->ord_to_doc ? d->ord_to_doc[node] : node;

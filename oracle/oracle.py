@@ -51,6 +51,11 @@ class IndexDesc(C.Structure):
         ("pq_codes", C.c_void_p),
         ("device", C.c_int32),
         ("flags", C.c_uint32),
+        ("nvq_m", C.c_int32),
+        ("nvq_reserved", C.c_int32),
+        ("nvq_bytes", C.c_void_p),
+        ("nvq_params", C.c_void_p),
+        ("nvq_global_mean", C.c_void_p),
     ]
 
 
@@ -142,6 +147,29 @@ def pq_lut(sim: int, dim: int, m: int, k: int, codebooks, gcent, queries) -> np.
     return out
 
 
+def nvq_encode(vectors, nvq_m: int = 2, growth_rate: float = 3.0, midpoint: float = 0.0):
+    """FIXTURE NVQ encoder (see jv_oracle.c): returns (bytes [n, dim] u8, params [n, nvq_m, 4], global_mean [dim])."""
+    v = _f32(vectors)
+    n, dim = v.shape
+    b = np.empty((n, dim), dtype=np.uint8)
+    prm = np.empty((n, nvq_m, 4), dtype=np.float32)
+    g = np.empty(dim, dtype=np.float32)
+    lib().jvo_nvq_encode(_p(v), C.c_int64(n), C.c_int32(dim), C.c_int32(nvq_m), C.c_float(growth_rate), C.c_float(midpoint),
+                         _p(b), _p(prm), _p(g))
+    return b, prm, g
+
+
+def nvq_dequantize(nvq_bytes, nvq_params, global_mean) -> np.ndarray:
+    """nvqDequantize, JVectorIndexQuantization.java:316-341."""
+    b = np.ascontiguousarray(nvq_bytes, dtype=np.uint8)
+    prm = _f32(nvq_params)
+    g = _f32(global_mean)
+    n, dim = b.shape
+    out = np.empty((n, dim), dtype=np.float32)
+    lib().jvo_nvq_dequantize(C.c_int64(n), C.c_int32(dim), C.c_int32(prm.shape[1]), _p(b), _p(prm), _p(g), _p(out))
+    return out
+
+
 def graph_build(vectors, sim: int, max_degree: int = 32, beam_width: int = 100, overflow: float = 1.2,
                 alpha: float = 1.2, max_batch: int = 8192, frac: float = 0.02):
     """Fixture: batched-insert Vamana with exact build scores.  Returns (adjacency[n,R], entry)."""
@@ -160,7 +188,7 @@ class OracleIndex:
 
     def __init__(self, similarity: int, vectors, adjacency, entry_node: int, ord_to_doc=None, max_doc=None,
                  pq_m: int = 0, pq_k: int = 0, pq_codebooks=None, pq_global_centroid=None, pq_codes=None,
-                 adc_order: int = 0):
+                 adc_order: int = 0, nvq_m: int = 0, nvq_bytes=None, nvq_params=None, nvq_global_mean=None):
         self.vectors = _f32(vectors)
         self.n, self.dim = self.vectors.shape
         self.adjacency = np.ascontiguousarray(adjacency, dtype=np.int32)
@@ -187,6 +215,13 @@ class OracleIndex:
         d.pq_codebooks = None if self.codebooks is None else self.codebooks.ctypes.data
         d.pq_global_centroid = None if self.gcent is None else self.gcent.ctypes.data
         d.pq_codes = None if self.codes is None else self.codes.ctypes.data
+        self.nvq_bytes = None if nvq_bytes is None else np.ascontiguousarray(nvq_bytes, dtype=np.uint8)
+        self.nvq_params = _f32(nvq_params)
+        self.nvq_gmean = _f32(nvq_global_mean)
+        d.nvq_m = nvq_m if self.nvq_bytes is not None else 0
+        d.nvq_bytes = None if self.nvq_bytes is None else self.nvq_bytes.ctypes.data
+        d.nvq_params = None if self.nvq_params is None else self.nvq_params.ctypes.data
+        d.nvq_global_mean = None if self.nvq_gmean is None else self.nvq_gmean.ctypes.data
         self.desc = d
         self._h = lib().jvo_index_create(C.byref(d))
         if adc_order:

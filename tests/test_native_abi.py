@@ -40,14 +40,16 @@ def test_struct_layouts_match_header(jv, tmp_path):
         '#include <stdio.h>\n#include <stddef.h>\n#include "jvgpu.h"\n'
         "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(jv_index_desc), sizeof(jv_search_params),"
         " sizeof(jv_query_stats), sizeof(jv_batch_timing), offsetof(jv_index_desc, adjacency), offsetof(jv_index_desc, pq_codes),"
-        " offsetof(jv_search_params, accept_bits), offsetof(jv_index_desc, flags));return 0;}\n")
+        " offsetof(jv_search_params, accept_bits), offsetof(jv_index_desc, flags));"
+        "printf(\"%zu %zu %d\\n\", offsetof(jv_index_desc, nvq_m), offsetof(jv_index_desc, nvq_global_mean), JV_INDEX_DESC_SIZE_V1);return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     n = jv.native
     assert [int(x) for x in out] == [
         C.sizeof(n.IndexDesc), C.sizeof(n.SearchParams), C.sizeof(n.QueryStats), C.sizeof(n.BatchTiming),
-        n.IndexDesc.adjacency.offset, n.IndexDesc.pq_codes.offset, n.SearchParams.accept_bits.offset, n.IndexDesc.flags.offset]
+        n.IndexDesc.adjacency.offset, n.IndexDesc.pq_codes.offset, n.SearchParams.accept_bits.offset, n.IndexDesc.flags.offset,
+        n.IndexDesc.nvq_m.offset, n.IndexDesc.nvq_global_mean.offset, n.IndexDesc.nvq_m.offset]  # V1 layout ends where nvq_m starts
 
 
 def test_oracle_desc_mirror_matches(jv, oracle):

@@ -252,3 +252,79 @@ def test_quantised_adc_table_bounds_and_recall():
         r8 = ix8.search(q, 10, 50)[0]
         r32 = ix.search(q, 10, 50)[0]
         assert recall(r8, gt) >= recall(r32, gt) - 0.01
+
+
+# ---- NVQ-inline vectors (nvq+pq segments): decoder pinned to the in-tree Java code ------------------------------------
+def _java_logistic_nqt(value, alpha, x0):
+    """JVectorIndexQuantization.java:344-351 in numpy float32 (Math.fma evaluated in float64: exact for float operands)."""
+    f = np.float32
+    temp = f(np.float64(value) * np.float64(alpha) + np.float64(f(-(f(alpha) * f(x0)))))
+    p = int(np.floor(np.float64(f(temp + f(0.5))) + 0.5))                      # Math.round
+    m = f(np.float64(f(temp - f(p))) * 0.5 + 1.0).view(np.int32)
+    t = np.int32(int(m) + (p << 23)).view(np.float32)
+    return f(t / f(t + f(1)))
+
+
+def _java_logit_nqt(scaled, inv_alpha, x0):
+    """JVectorIndexQuantization.java:354-361."""
+    f = np.float32
+    z = f(scaled / f(f(1) - scaled))
+    temp = int(z.view(np.int32))
+    e = temp & 0x7F800000
+    p = f((e >> 23) - 128)
+    m = np.int32((temp & 0x007FFFFF) + 0x3F800000).view(np.float32)
+    return f(f(f(m + p) * inv_alpha) + x0)
+
+
+def _java_nvq_dequantize(bytes_row, params_row, gmean, sizes, offs):
+    """nvqDequantize, JVectorIndexQuantization.java:316-341."""
+    f = np.float32
+    out = np.zeros(len(bytes_row), np.float32)
+    for m, (size, off) in enumerate(zip(sizes, offs)):
+        growth, mid, lo, hi = (f(x) for x in params_row[m])
+        delta = f(hi - lo)
+        sgr = f(growth / delta)
+        smid = f(mid * delta)
+        bias = _java_logistic_nqt(lo, sgr, smid)
+        scale = f(f(_java_logistic_nqt(hi, sgr, smid) - bias) / f(255.0))
+        inv = f(f(1.0) / sgr)
+        for d in range(size):
+            b = f(int(bytes_row[off + d]))
+            sv = f(np.float64(b) * np.float64(scale) + np.float64(bias))       # Math.fma
+            out[off + d] = _java_logit_nqt(sv, inv, smid)
+    return (out + gmean).astype(np.float32)
+
+
+def test_nvq_decoder_matches_the_in_tree_java_formulas():
+    x = O.java_random_vectors(40, 30, 73)                                      # dim 30, 4 sub-vectors: sizes 8, 8, 7, 7
+    b, prm, g = O.nvq_encode(x, 4, growth_rate=2.5, midpoint=0.1)
+    deq = O.nvq_dequantize(b, prm, g)
+    sizes, offs = O.pq_subspaces(30, 4)
+    for i in range(40):
+        want = _java_nvq_dequantize(b[i], prm[i], g, sizes, offs)
+        np.testing.assert_array_equal(deq[i].view(np.uint32), want.view(np.uint32))
+    assert np.abs(deq - x).max() < 1.0 / 128                                   # 8 bits over a unit range
+    # the fast logistic is the base-2 sigmoid up to its piecewise-linear mantissa approximation
+    for v, a, x0 in ((0.3, 2.0, 0.1), (-1.5, 0.7, 0.0), (4.0, 1.0, 2.0)):
+        t = v * a - a * x0
+        assert abs(float(_java_logistic_nqt(np.float32(v), np.float32(a), np.float32(x0))) - 2.0 ** t / (1 + 2.0 ** t)) < 0.02
+
+
+def test_nvq_rerank_recall_floor_at_the_reference_seed():
+    """JVectorNVQTests (dimension 128, 2 sub-vectors, seed 73, overquery 10): recall >= 0.85 with NVQ-inline vectors;
+    here the traversal uses the auxiliary PQ codes and the reranker the dequantised vectors (nvq+pq)."""
+    base = O.java_random_vectors(2000, 128, 73)
+    q = O.java_random_vectors(30, 128, 74)
+    fx = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=16, pq_m=O.default_num_subspaces(128))
+    b, prm, g = O.nvq_encode(base, 2)
+    ix = O.OracleIndex(O.SIM_EUCLIDEAN, base, fx.adjacency, fx.entry, pq_m=fx.pq_m, pq_k=fx.pq_k, pq_codebooks=fx.codebooks,
+                       pq_global_centroid=fx.gcent, pq_codes=fx.codes, nvq_m=2, nvq_bytes=b, nvq_params=prm, nvq_global_mean=g)
+    gt = fx.oracle_index().exact_topk(q, 10)[0]
+    docs, scores, _, st = ix.search(q, 10, 100)
+    assert recall(docs, gt) >= 0.85
+    assert (st[:, 3] == 100).all()
+    # scores are the exact similarity of the DEQUANTISED vectors
+    deq = O.nvq_dequantize(b, prm, g)
+    for i in range(5):
+        for d, s in zip(docs[i], scores[i]):
+            assert s == np.float32(O.exact_score(O.SIM_EUCLIDEAN, q[i], deq[d]))
