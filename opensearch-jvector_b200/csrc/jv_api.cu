@@ -484,27 +484,36 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
     JV_CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     if (abytes) JV_CUDA_TRY(cudaMemcpyAsync(c->accept.p, p->accept_bits, abytes, cudaMemcpyHostToDevice, c->stream));
     int launches = 0;
-    // Large staged batches are pipelined: a small first chunk (1/8 of the batch: its copy is the only one that is exposed)
-    // and then chunks of <= 16384 queries travel on a copy stream while the kernels of the previous chunk (table build,
-    // traversal, rerank) run.  Per-query accept bitsets keep the single-shot path (their stride is relative to the batch).
+    // Large staged batches are pipelined: a small first chunk (its copy is the only one that is exposed) and then growing
+    // chunks travel on a copy stream while the kernels of the previous chunks (table build, traversal, rerank) run.  Per-query accept bitsets keep the single-shot path (their stride is relative to the batch).
     int bounds[9] = {0, nq, 0, 0, 0, 0, 0, 0, 0}, nchunks = 1;
     if (!zero_copy && nq >= 4096 && !(p->accept_bits && p->accept_stride_words) && getenv("JVGPU_H2D_SINGLE") == nullptr) {
-        int first = nq / 8;
+        // geometric ramp: 1/8, 1/4, then the rest in parts of <= 16384 queries; consecutive chunks alternate between two
+        // contexts so that a chunk's kernels start as soon as its copy has landed, overlapping the previous chunk's tail
+        const int first = nq / 8, second = first + nq / 4;
         bounds[1] = first;
-        nchunks = 1;
-        int rest = nq - first, parts = (rest + 16383) / 16384;
-        if (parts > 7) parts = 7;
-        for (int i = 1; i <= parts; i++) bounds[1 + i] = first + (int)((int64_t)rest * i / parts);
-        nchunks = 1 + parts;
+        bounds[2] = second;
+        int rest = nq - second, parts = (rest + 16383) / 16384;
+        if (parts > 6) parts = 6;
+        for (int i = 1; i <= parts; i++) bounds[2 + i] = second + (int)((int64_t)rest * i / parts);
+        nchunks = 2 + parts;
     }
     if (nchunks > 1) {
         JV_CUDA_TRY(cudaEventRecord(c->chunk_ev[0], c->stream)); // the copy stream must not overtake earlier work on these buffers
         JV_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));
         int per = 0;
         for (int ci = 0; ci < nchunks; ci++) per = bounds[ci + 1] - bounds[ci] > per ? bounds[ci + 1] - bounds[ci] : per;
+        // Odd chunks run on a second context (own stream + scratch): when the persistent traversal kernel of chunk i drains,
+        // the kernels of chunk i+1 fill the freed SMs instead of waiting for the last query of chunk i.
+        CtxLease lease2(ix);
+        JV_REQUIRE(lease2.c != nullptr, "could not create a search context: %s", get_error());
+        SearchCtx *cc[2] = {c, lease2.c};
         // approximate-list scratch for the largest chunk is allocated once, before anything is enqueued
-        JV_TRY(c->approx_keys.ensure((size_t)per * p->rerank_k * 8));
-        JV_TRY(c->approx_count.ensure((size_t)per * 4));
+        for (SearchCtx *x : cc) {
+            JV_TRY(x->approx_keys.ensure((size_t)per * p->rerank_k * 8));
+            JV_TRY(x->approx_count.ensure((size_t)per * 4));
+        }
+        JV_CUDA_TRY(cudaStreamWaitEvent(cc[1]->stream, c->chunk_ev[0], 0)); // ordered after earlier work on the shared buffers
         for (int ci = 0; ci < nchunks; ci++) {
             const int q0 = bounds[ci], nqc = bounds[ci + 1] - q0;
             JV_CUDA_TRY(cudaMemcpyAsync(c->queries.as<float>() + (size_t)q0 * ix->dim, queries + (size_t)q0 * ix->dim, (size_t)nqc * ix->dim * 4,
@@ -513,11 +522,23 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
         }
         for (int ci = 0; ci < nchunks; ci++) {
             const int q0 = bounds[ci], nqc = bounds[ci + 1] - q0;
-            JV_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ev[ci], 0));
-            JV_TRY(search_core(ix, c, c->queries.as<float>() + (size_t)q0 * ix->dim, nqc, p, d_accept, c->out_doc.as<int32_t>() + (size_t)q0 * p->k,
+            SearchCtx *x = cc[ci & 1];
+            JV_CUDA_TRY(cudaStreamWaitEvent(x->stream, c->chunk_ev[ci], 0));
+            JV_TRY(search_core(ix, x, c->queries.as<float>() + (size_t)q0 * ix->dim, nqc, p, d_accept, c->out_doc.as<int32_t>() + (size_t)q0 * p->k,
                                c->out_score.as<float>() + (size_t)q0 * p->k, c->out_count.as<int32_t>() + q0,
                                c->stats.as<jv_query_stats>() + q0, &launches, ci == 0));
         }
+        JV_CUDA_TRY(cudaEventRecord(cc[1]->chunk_ev[0], cc[1]->stream)); // join: results leave on the first context's stream
+        JV_CUDA_TRY(cudaStreamWaitEvent(c->stream, cc[1]->chunk_ev[0], 0));
+        JV_CUDA_TRY(cudaMemcpyAsync(out_doc, c->out_doc.p, kb, cudaMemcpyDeviceToHost, c->stream));
+        JV_CUDA_TRY(cudaMemcpyAsync(out_score, c->out_score.p, kb, cudaMemcpyDeviceToHost, c->stream));
+        JV_CUDA_TRY(cudaMemcpyAsync(out_count, c->out_count.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (stats)
+            JV_CUDA_TRY(cudaMemcpyAsync(stats, c->stats.p, (size_t)nq * sizeof(jv_query_stats), cudaMemcpyDeviceToHost, c->stream));
+        JV_CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+        JV_CUDA_TRY(cudaStreamSynchronize(c->stream)); // (lease2 must not be released before its work is done)
+        fill_timing(c, timing, launches, true);
+        return JV_OK;
     } else {
         if (!zero_copy) JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
         JV_TRY(search_core(ix, c, d_q, nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
