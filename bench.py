@@ -231,10 +231,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     torch.cuda.set_device(local_rank)
     dist = None
+    saved_stdout = None
     if world > 1 and args.impl == "ours":
-        # NCCL writes its debug output (version banner included) to stdout by default: send it to stderr so that
-        # rank 0's stdout is exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL writes its debug output (version banner included) to stdout: point fd 1 at stderr until the JSON line is
+        # printed, so that rank 0's stdout is exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -439,6 +442,10 @@ def main():
                                 "sample": f"{sample} of the {nq} queries, one query per OpenMP thread, same index (CPU restatement, not the JVM)",
                                 "recall_at_10": recall_at_k(cd, truth[:sample]),
                                 "visited_per_query": float(cst[:, 0].mean())}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line), flush=True)
     gi.close()
