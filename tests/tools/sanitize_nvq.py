@@ -1,4 +1,5 @@
-"""Small NVQ-inline (nvq+pq) run for compute-sanitizer."""
+"""Small NVQ-inline (nvq+pq) run for compute-sanitizer (lives under tests/: it uses the oracle's fixture NVQ encoder).
+usage: compute-sanitizer --tool memcheck python tests/tools/sanitize_nvq.py"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
