@@ -168,3 +168,24 @@ def test_large_host_batches_are_pipelined_in_chunks(jv, fx_dot):
                 np.testing.assert_array_equal(r.scores[t:t + m], small.scores[:m])
                 np.testing.assert_array_equal(r.counts[t:t + m], small.counts[:m])
                 np.testing.assert_array_equal(r.stats[t:t + m, 1:], small.stats[:m, 1:])
+
+
+def test_vectors_in_pinned_host_memory_and_wide_graphs(jv, fx_dot):
+    """cfg 5 flavour: fp32 rerank vectors stay in pinned host memory (K3 gathers them over PCIe) while the 8-bit table
+    traversal runs from HBM; and a graph with R = 64 (two adjacency chunks per candidate, <= 256 queued survivors)."""
+    fx = fx_dot
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as a, \
+            fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8 | jv.native.FLAG_NO_VECTORS_ON_DEVICE) as b:
+        ra, rb = a.search(fx.queries, 10, 50), b.search(fx.queries, 10, 50)
+        np.testing.assert_array_equal(ra.docs, rb.docs)
+        np.testing.assert_array_equal(ra.scores, rb.scores)
+    base, q = clustered(4000, 64, 40, seed=12, normalize=True)
+    wide = make_fixture(O.SIM_DOT, base, q, max_degree=64, pq_m=16)
+    with wide.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        gt, _, _ = gi.exact_topk(q, 10)
+        r = gi.search(q, 10, 50)
+        wd = wide.oracle_index().search(q, 10, 50)[0]
+        assert recall(r.docs, gt) >= recall(wd, gt) - 0.015
+        r1 = gi.search(q, 10, 50, expand_width=1)
+        w1 = wide.oracle_index(adc_order=-8).search(q, 10, 50)[0]
+        assert np.mean([np.array_equal(x, y) for x, y in zip(r1.docs, w1)]) >= 0.9
