@@ -151,10 +151,13 @@ typedef struct jv_search_params {
     float threshold;       /* JVectorKnnCollector.getThreshold(), default 0                      */
     float rerank_floor;    /* JVectorKnnCollector.getRerankFloor(), default 0                    */
     int32_t expand_width;  /* traversal schedule (GPU-side knob, not part of the reference API):
-                            *   0  default: the fast kernel expands the 4 best unexpanded candidates per step
-                            *   1..8 explicit width; 1 = the reference's best-first order (up to exact score ties)
+                            *   0  default: the production kernel expands the 4 best unexpanded candidates per step
+                            *   1..8 explicit width (clamped to what the kernel supports); 1 = the reference's best-first
+                            *      order (up to exact score ties)
                             *  -1  strict kernel: candidate heap + result heap exactly as GraphSearcher;
-                            *      always used when accept_bits or threshold > 0 are given                      */
+                            *      always used when threshold > 0; with accept_bits it is used unless the index was created
+                            *      with JV_INDEX_FLAG_LUT_U8 and 8 * rerank_k <= 1024 (then accepted and rejected nodes share
+                            *      one list of 8 * rerank_k entries in the production kernel)                          */
     /* AcceptDocs by Lucene docId (FixedBitSet words: bit d = word d>>6, bit d&63), NULL = accept all.
      * accept_stride_words == 0: one bitset shared by the batch; else query i uses
      * accept_bits + i*accept_stride_words.  An ordinal is accepted iff ord_to_doc[ord] != -1 and its

@@ -90,7 +90,7 @@ struct SearchLaunch {
 int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked = nullptr);
 
 // K1+K2 with the 8-bit table (jv_q8.cu)
-bool q8_search_supported(const jv_index *ix, int L, int R);
+bool q8_search_supported(const jv_index *ix, int L, int R, bool filtered);
 int q8_lut_bytes(int nj); // table bytes per query in the bank-interleaved layout
 int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked);
 int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, uint8_t *d_lut, float4 *d_qparams);

@@ -351,6 +351,10 @@ struct Q8Params {
     int *dbg;
     int64_t n;
     int nq, L, R, entry, sim, NJ, lutb, hash_log2, E, surv_cap;
+    // filtered queries (FILT instantiation): accept bits by Lucene docId (JVectorReader.java:157-163); Lc = list capacity
+    int Lc;
+    const uint64_t *accept;
+    int64_t accept_stride;
     // fused K3 (exact rerank + top-k as the epilogue of every query; fuse_k = 0: write approx_keys for a separate rerank kernel)
     int fuse_k, dim;
     float rerank_floor;
@@ -367,6 +371,12 @@ __device__ __forceinline__ uint64_t qkey_pack(uint32_t ord, int32_t node) {
     return ((uint64_t)ord << 32) | ((uint64_t)(uint32_t)(0x7fffffff - node) << 1) | 1ull;
 }
 __device__ __forceinline__ int32_t qkey_node(uint64_t k) { return 0x7fffffff - (int32_t)((k >> 1) & 0x7fffffffu); }
+// filtered flavour: 30-bit node field, bit 1 = "accepted by the filter" (the lowest bit of the comparable part key >> 1; it
+// never decides an order because (order word, node) is already unique), bit 0 = unexpanded
+__device__ __forceinline__ uint64_t qkey_pack_f(uint32_t ord, int32_t node, bool acc) {
+    return ((uint64_t)ord << 32) | ((uint64_t)(uint32_t)(0x3fffffff - node) << 2) | (acc ? 2ull : 0ull) | 1ull;
+}
+__device__ __forceinline__ int32_t qkey_node_f(uint64_t k) { return 0x3fffffff - (int32_t)((k >> 2) & 0x3fffffffu); }
 
 // visited filter: true when `nb` was NOT present (and records it).  2 tags of 15 bits + valid bit per word; (set, tag) is
 // a bijection of the ordinal when n <= 2^(set_bits+15), so there are no false positives; evictions only cause re-scoring.
@@ -389,29 +399,33 @@ __device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, 
 
 // NJ_T > 0: code words per lane known at compile time (registers, all loads of U rows in flight before the first lookup).
 // W = warps per CTA (4 row groups each); PROF = per-phase cycle counters (jv_index_debug_counter).
-template <int NJ_T, int W, bool PROF>
-__global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) {
+// FILT = accept bits given: the list also holds rejected nodes (they are traversed, never returned), up to Lc entries; only
+// entries ranked before the L-th ACCEPTED one can still be expanded (the reference stops when the best candidate is worse than
+// the worst of rerankK accepted results), and that entry's key is the admission threshold for new nodes.
+template <int NJ_T, int W, bool PROF, bool FILT>
+__global__ void __launch_bounds__(W * 32, FILT ? 2 : 4) q8_search_kernel(const Q8Params p) {
     constexpr int kQW = W, kQThreads = W * 32, NG = 4 * W;
     constexpr int U = W == 4 ? 3 : 2; // rows in flight per row group and pass: NG * U rows >= the fresh neighbours of a typical step
     constexpr int NJC = NJ_T > 0 ? NJ_T : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.L, E = p.E, H = 1 << p.hash_log2, R = p.R;
+    const int Lc = FILT ? p.Lc : L; // list capacity
     const int NJ = NJ_T > 0 ? NJ_T : p.NJ;
 
     unsigned char *sp = smem_raw;
     const uint8_t *lut = sp;
     sp += p.lutb;
     uint64_t *list0 = reinterpret_cast<uint64_t *>(sp);
-    sp += (size_t)L * 8;
+    sp += (size_t)Lc * 8;
     uint64_t *list1 = reinterpret_cast<uint64_t *>(sp);
-    sp += (size_t)L * 8;
+    sp += (size_t)Lc * 8;
     uint64_t *surv = reinterpret_cast<uint64_t *>(sp); // queued survivors as key >> 1 (always unexpanded); 0 = dropped duplicate
     sp += (size_t)p.surv_cap * 8;
     int32_t *pool = reinterpret_cast<int32_t *>(sp); // fresh neighbour ids of the current step
     sp += (size_t)p.surv_cap * 4;
     int32_t *gapcnt = reinterpret_cast<int32_t *>(sp); // [L + 1] survivors per list gap (merge)
-    sp += (size_t)((L + 2) & ~1) * 4;
+    sp += (size_t)((Lc + 2) & ~1) * 4;
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
 
     __shared__ __align__(8) uint64_t s_bar;
@@ -489,7 +503,7 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             bulk_g2s(smem_raw, p.lut + (int64_t)qi * p.lutb, (uint32_t)p.lutb, &s_bar);
         }
         for (int i = tid; i < H; i += kQThreads) filter[i] = tagged ? 0u : kEmpty;
-        for (int i = tid; i <= L; i += kQThreads) gapcnt[i] = 0;
+        for (int i = tid; i <= Lc; i += kQThreads) gapcnt[i] = 0;
         const float4 qp = __ldg(p.qparams + qi);
         const float delta = qp.x, base = qp.y, qnorm = qp.z;
         auto score_of = [&](uint32_t isum, int32_t nb) -> float {
@@ -501,6 +515,16 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             if (isum_keys) return l2 ? ~isum : isum;
             return jv_f2ord(score_of(isum, nb));
         };
+        const uint64_t *abits = FILT ? p.accept + (int64_t)qi * p.accept_stride : nullptr;
+        auto pack_key = [&](uint32_t isum, int32_t nb) -> uint64_t { // full list key of a freshly scored node (unexpanded)
+            if (FILT) {
+                const int32_t doc = p.ord_to_doc ? __ldg(p.ord_to_doc + nb) : nb; // a9: accept-bits lambda, JVectorReader.java:157-163
+                const bool acc = doc >= 0 && ((__ldg(abits + (doc >> 6)) >> (doc & 63)) & 1ull);
+                return qkey_pack_f(ord_of(isum, nb), nb, acc);
+            }
+            return qkey_pack(ord_of(isum, nb), nb);
+        };
+        auto node_of = [&](uint64_t k) -> int32_t { return FILT ? qkey_node_f(k) : qkey_node(k); };
         __syncthreads(); // filter cleared
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
@@ -510,7 +534,7 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             if (warp == 0) {
                 const uint32_t s = row_sum(g == 0 ? p.entry : -1);
                 if (lane == 0) {
-                    list0[0] = qkey_pack(ord_of(s, p.entry), p.entry);
+                    list0[0] = pack_key(s, p.entry);
                     q_filter_insert(filter, p.hash_log2, tagged, p.entry);
                 }
             }
@@ -525,22 +549,53 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             const int par = step & 1;
             // ---- (a) every warp scans the list flags itself: no serial section, no barrier
             int found = 0;
-            for (int c0 = 0; c0 < n; c0 += 32) {
-                const int i = c0 + lane;
-                const bool un = i < n && (list[i] & 1ull);
-                const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
-                const int rank = found + __popc(ballot & ((1u << lane) - 1u));
-                if (un && rank < 2 * E) { // ranks E..2E-1 are runners-up: their rows are prefetched into L2
-                    w_sel[warp][rank] = qkey_node(list[i]);
-                    w_pos[warp][rank] = i;
+            uint64_t worst;
+            if (!FILT) {
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    const int i = c0 + lane;
+                    const bool un = i < n && (list[i] & 1ull);
+                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                    if (un && rank < 2 * E) { // ranks E..2E-1 are runners-up: their rows are prefetched into L2
+                        w_sel[warp][rank] = qkey_node(list[i]);
+                        w_pos[warp][rank] = i;
+                    }
+                    found += __popc(ballot);
+                    if (found >= 2 * E) break;
                 }
-                found += __popc(ballot);
-                if (found >= 2 * E) break;
+                worst = n >= L ? (list[L - 1] >> 1) : 0ull;
+            } else {
+                // only entries with fewer than L accepted entries in front of them can still be expanded; the L-th accepted
+                // entry's key is the admission threshold (the worst of rerankK accepted results)
+                int nacc = 0;
+                uint64_t thr = 0ull;
+                bool have_thr = false;
+                for (int c0 = 0; c0 < n && !have_thr; c0 += 32) {
+                    const int i = c0 + lane;
+                    const uint64_t k = i < n ? list[i] : 0ull;
+                    const bool acc = (k & 2ull) != 0ull;
+                    const uint32_t aball = __ballot_sync(JV_FULL_MASK, acc);
+                    const int before = nacc + __popc(aball & ((1u << lane) - 1u)); // accepted entries strictly in front of me
+                    const bool un = i < n && (k & 1ull) && before < L;
+                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                    if (un && rank < 2 * E && found < 2 * E) {
+                        w_sel[warp][rank] = qkey_node_f(k);
+                        w_pos[warp][rank] = i;
+                    }
+                    found += __popc(ballot);
+                    const uint32_t lth = __ballot_sync(JV_FULL_MASK, acc && before == L - 1);
+                    if (lth) {
+                        thr = __shfl_sync(JV_FULL_MASK, k, __ffs(lth) - 1) >> 1;
+                        have_thr = true;
+                    }
+                    nacc += __popc(aball);
+                }
+                worst = have_thr ? thr : (n >= Lc ? (list[Lc - 1] >> 1) : 0ull);
             }
             __syncwarp();
             const int nsel = found < E ? found : E;
             if (nsel == 0) break;
-            const uint64_t worst = n >= L ? (list[L - 1] >> 1) : 0ull;
             JV_PHASE(2)
 
             // ---- (b1) warp w expands candidates w, w + 4, ..: adjacency row -> visited filter -> shared pool of fresh ids
@@ -571,7 +626,7 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             {
                 const int gid = warp * 4 + g;
                 auto offer = [&](uint32_t isum, int32_t node) { // re-scored list members are dropped in (c)
-                    const uint64_t a = qkey_pack(ord_of(isum, node), node) >> 1;
+                    const uint64_t a = pack_key(isum, node) >> 1;
                     if (a > worst) surv[atomicAdd(&s_ns[par], 1)] = a;
                 };
                 if (NJ_T > 0) {
@@ -633,7 +688,7 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
                             my_s = sl == u ? s[u] : my_s;
                             my_nb = sl == u ? nbv[u] : my_nb;
                         }
-                        const uint64_t ka = (sl < NU && my_nb >= 0) ? (qkey_pack(ord_of(my_s, my_nb), my_nb) >> 1) : 0ull;
+                        const uint64_t ka = (sl < NU && my_nb >= 0) ? (pack_key(my_s, my_nb) >> 1) : 0ull;
                         const uint32_t bal = __ballot_sync(JV_FULL_MASK, ka > worst);
                         if (bal) { // warp-uniform
                             int slot = 0;
@@ -726,7 +781,7 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
                     if (a != 0ull) {
                         const int t0 = t & ~31; // this warp's survivors start here
                         const int pos = my_pos[c] + count_gt(0, t0, a - 1ull) + count_gt(t0, ns, a) + __popc(same);
-                        if (pos < L) out[pos] = (a << 1) | 1ull;
+                        if (pos < Lc) out[pos] = (a << 1) | 1ull;
                     }
                 }
             }
@@ -753,13 +808,13 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
                     for (int e = 0; e < nsel; e++) selected |= (w_pos[warp][e] == t);
                     if (selected) k &= ~1ull;
                     const int pos = t + offset + v;
-                    if (pos < L) out[pos] = k;
+                    if (pos < Lc) out[pos] = k;
                 }
             }
             __syncthreads(); // B2
             JV_PHASE(5)
-            for (int i = tid; i <= L; i += kQThreads) gapcnt[i] = 0; // consumed above; the next increments come after B1
-            n = n + ns - ndup < L ? n + ns - ndup : L;
+            for (int i = tid; i <= Lc; i += kQThreads) gapcnt[i] = 0; // consumed above; the next increments come after B1
+            n = n + ns - ndup < Lc ? n + ns - ndup : Lc;
             cur ^= 1;
             step++;
         }
@@ -770,7 +825,7 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             uint64_t *akeys = cur ? list0 : list1; // fused rerank: converted keys go to the idle list buffer
             uint64_t *o = p.fuse_k ? akeys : p.approx_keys + (int64_t)qi * L;
             auto key_of = [&](uint64_t k) -> uint64_t {
-                const int32_t node = qkey_node(k);
+                const int32_t node = node_of(k);
                 const uint32_t ord = (uint32_t)(k >> 32);
                 const float sc = isum_keys ? score_of(l2 ? ~ord : ord, node) : jv_ord2f(ord);
                 return jv_mk_key(sc, node);
@@ -778,7 +833,19 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
             int dup = 0; // a node scored twice in one step (see the merge) sits in two adjacent slots
             for (int i = tid + 1; i < n; i += kQThreads) dup |= ((list[i] >> 1) == (list[i - 1] >> 1)) ? 1 : 0;
             int cnt = n;
-            if (!__syncthreads_or(dup)) {
+            if (FILT) { // the best L ACCEPTED entries, in order (serial: <= Lc iterations once per query)
+                if (tid == 0) {
+                    int w = 0;
+                    for (int i = 0; i < n && w < L; i++) {
+                        const uint64_t k = list[i];
+                        if ((k & 2ull) && (i == 0 || (k >> 1) != (list[i - 1] >> 1))) o[w++] = key_of(k);
+                    }
+                    s_nn[0] = w; // broadcast slot (reset at the top of the next query)
+                    for (; !p.fuse_k && w < L; w++) o[w] = 0ull;
+                }
+                __syncthreads();
+                cnt = s_nn[0];
+            } else if (!__syncthreads_or(dup)) {
                 for (int i = tid; i < (p.fuse_k ? n : L); i += kQThreads) o[i] = i < n ? key_of(list[i]) : 0ull;
             } else { // rare: serial compaction
                 if (tid == 0) {
@@ -825,19 +892,22 @@ __global__ void __launch_bounds__(W * 32, 4) q8_search_kernel(const Q8Params p) 
     }
 }
 
-template <int NJ_T, int W, bool PROF>
+template <int NJ_T, int W, bool PROF, bool FILT = false>
 static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
     constexpr int kQThreads = W * 32;
-    auto kern = q8_search_kernel<NJ_T, W, PROF>;
-    const size_t fixed = (size_t)p.lutb + (size_t)p.L * 16 + (size_t)p.surv_cap * 12 + (size_t)((p.L + 2) & ~1) * 4;
+    auto kern = q8_search_kernel<NJ_T, W, PROF, FILT>;
+    const int Lc = FILT ? p.Lc : p.L;
+    const size_t fixed = (size_t)p.lutb + (size_t)Lc * 16 + (size_t)p.surv_cap * 12 + (size_t)((Lc + 2) & ~1) * 4;
     const size_t sm_total = 228 * 1024;
     int64_t want = (int64_t)p.L * p.R; // words; 2 tags each
     if (want < 1024) want = 1024;
+    const int64_t min_words = FILT ? 4096 : 1024; // a filter multiplies the visited nodes by ~1/selectivity
+    if (FILT) want = 8192;
     int best_occ = 0, best_log2 = 0;
     for (int occ = 8; occ >= 1; occ--) {
         const int64_t per = (int64_t)(sm_total / occ) - 1024 - 512 - (int64_t)fixed; // 1 KB system + static __shared__
-        if (per < 1024 * 4) continue;
-        int lg = 10;
+        if (per < min_words * 4) continue;
+        int lg = FILT ? 12 : 10;
         while (lg < 15 && ((int64_t)4 << (lg + 1)) <= per && ((int64_t)1 << lg) < want) lg++;
         best_occ = occ;
         best_log2 = lg;
@@ -868,10 +938,15 @@ static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
     return JV_OK;
 }
 
-bool q8_search_supported(const jv_index *ix, int L, int R) {
+// list capacity with a filter: rejected nodes stay in the list (they are traversed) next to the rerankK accepted ones
+static int q8_filtered_list_cap(int L) { return 8 * L; }
+
+bool q8_search_supported(const jv_index *ix, int L, int R, bool filtered) {
     if (!ix->has_pq || !ix->q8_ok || R > 64) return false; // <= 2 queued survivors per thread and step
-    const size_t fixed = (size_t)q8_lut_bytes(ix->q8_nj) + (size_t)L * 16 + (size_t)kQMaxE * ((R + 31) / 32) * 32 * 12 + (size_t)((L + 2) & ~1) * 4;
-    return fixed + 4096 + 2048 <= 227 * 1024;
+    if (filtered && (q8_filtered_list_cap(L) > 1024 || ix->n >= (1ll << 30))) return false; // strict kernel instead
+    const int Lc = filtered ? q8_filtered_list_cap(L) : L;
+    const size_t fixed = (size_t)q8_lut_bytes(ix->q8_nj) + (size_t)Lc * 16 + (size_t)kQMaxE * ((R + 31) / 32) * 32 * 12 + (size_t)((Lc + 2) & ~1) * 4;
+    return fixed + (filtered ? 16384 : 4096) + 2048 <= 227 * 1024;
 }
 
 // LUT build + traversal for queries [0, nq) in chunks bounded by the table staging buffer
@@ -918,6 +993,12 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         p.lutb = lutb;
         p.E = E;
         p.dim = ix->dim;
+        p.ord_to_doc = ix->ord_to_doc.as<int32_t>();
+        const bool filt = a.d_accept != nullptr;
+        p.Lc = filt ? q8_filtered_list_cap(a.rerank_k) : a.rerank_k;
+        p.accept = a.d_accept;
+        p.accept_stride = a.accept_stride_words; // words per query (0 = one bitset for the batch)
+        if (filt && a.accept_stride_words) p.accept += (int64_t)q0 * a.accept_stride_words;
         // K3 can run as the traversal's epilogue (JVGPU_Q8_FUSED=1).  Measured at cfg2: 2.67 ms fused vs 2.34 ms with the
         // separate rerank kernel — a 4-warp CTA gathers its 50 rows one DRAM round trip after the other while it holds
         // 1/4 of an SM; the stand-alone K3 keeps 16 CTAs per SM in flight (0.31 ms, 0.76 of the HBM roofline) — so off by default.
@@ -941,8 +1022,11 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         const int warps = getenv("JVGPU_Q8_WARPS") ? atoi(getenv("JVGPU_Q8_WARPS")) : 4;
 #define JV_Q8_CASE(NJV)                                                                         \
     case NJV:                                                                                   \
-        st = warps == 8 ? (prof ? launch_q8_typed<NJV, 8, true>(ix, ctx, p) : launch_q8_typed<NJV, 8, false>(ix, ctx, p)) \
-                        : (prof ? launch_q8_typed<NJV, 4, true>(ix, ctx, p) : launch_q8_typed<NJV, 4, false>(ix, ctx, p)); \
+        if (filt)                                                                               \
+            st = launch_q8_typed<NJV, 4, false, true>(ix, ctx, p);                              \
+        else                                                                                    \
+            st = warps == 8 ? (prof ? launch_q8_typed<NJV, 8, true>(ix, ctx, p) : launch_q8_typed<NJV, 8, false>(ix, ctx, p)) \
+                            : (prof ? launch_q8_typed<NJV, 4, true>(ix, ctx, p) : launch_q8_typed<NJV, 4, false>(ix, ctx, p)); \
         break;
         switch (ix->q8_nj) {
             JV_Q8_CASE(1)
@@ -952,7 +1036,8 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
             JV_Q8_CASE(6)
             JV_Q8_CASE(8)
         default:
-            st = prof ? launch_q8_typed<0, 4, true>(ix, ctx, p) : launch_q8_typed<0, 4, false>(ix, ctx, p);
+            st = filt ? launch_q8_typed<0, 4, false, true>(ix, ctx, p)
+                      : (prof ? launch_q8_typed<0, 4, true>(ix, ctx, p) : launch_q8_typed<0, 4, false>(ix, ctx, p));
             break;
         }
 #undef JV_Q8_CASE

@@ -317,7 +317,11 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     // production path: unfiltered, threshold-free queries go to the fast kernel (jv_search_fast.cu); filters and
     // range thresholds need the reference's two-queue semantics and stay on the strict kernel below.
     const bool plain = a.expand_width >= 0 && a.d_accept == nullptr && !(a.threshold > 0.f);
-    if (plain && (ix->flags & JV_INDEX_FLAG_LUT_U8) && a.d_query_ids == nullptr && q8_search_supported(ix, a.rerank_k, ix->R))
+    // filtered queries also take the 8-bit table path (accepted + rejected nodes in one list of 8 * rerankK entries); range
+    // thresholds keep the strict kernel
+    const bool filtered = a.expand_width >= 0 && a.d_accept != nullptr && !(a.threshold > 0.f);
+    if ((plain || filtered) && (ix->flags & JV_INDEX_FLAG_LUT_U8) && a.d_query_ids == nullptr &&
+        q8_search_supported(ix, a.rerank_k, ix->R, filtered))
         return launch_search_q8(ix, ctx, a, launches, reranked);
     if (plain && (!ix->has_pq || (p.M & 3) == 0)) {
         const int32_t fs = launch_search_fast(ix, ctx, p, a.expand_width == 0 ? 4 : a.expand_width, f16);

@@ -18,4 +18,7 @@ for dim, m, sim in ((64, 16, 1), (96, 48, 0), (128, 16, 2)):
         for e in (1, 4):
             r = gi.search(q, 10, 50, expand_width=e)
             print("dim", dim, "E", e, "visited", r.stats[:, 0].mean(), "docs0", r.docs[0][:3])
+        mask = rng.random(n) < 0.2
+        r = gi.search(q, 10, 50, accept_bits=jv.make_accept_bits(mask))  # filtered flavour of the 8-bit path
+        print("dim", dim, "filtered visited", r.stats[:, 0].mean(), "accepted only", bool(mask[r.docs[r.docs >= 0]].all()))
 print("ok")

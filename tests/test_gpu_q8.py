@@ -117,15 +117,18 @@ def test_large_rerank_k_and_chunked_batches(jv, fx_l2, monkeypatch):
         np.testing.assert_array_equal(a.stats[:, 1:], b.stats[:, 1:])
 
 
-def test_filters_and_unsupported_shapes_fall_back(jv, fx_l2):
+def test_thresholds_and_unsupported_shapes_fall_back(jv, fx_l2):
     fx = fx_l2
     ora = fx.oracle_index(adc_order=32)
     bits = O.make_accept_bits(np.random.default_rng(1).random(fx.base.shape[0]) < 0.3)
-    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:  # filtered queries: strict kernel, fp32 table
-        r = gi.search(fx.queries, 10, 50, accept_bits=bits)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:  # explicit strict order: reference kernel, fp32 table
+        r = gi.search(fx.queries, 10, 50, accept_bits=bits, expand_width=-1)
         wd, ws, wc, _ = ora.search(fx.queries, 10, 50, accept_bits=bits)
         np.testing.assert_array_equal(r.docs, wd)
         np.testing.assert_array_equal(r.counts, wc)
+        r = gi.search(fx.queries, 10, 50, threshold=0.05)       # range threshold: strict kernel
+        wd, ws, wc, _ = ora.search(fx.queries, 10, 50, threshold=0.05)
+        np.testing.assert_array_equal(r.docs, wd)
     # non-uniform sub-vectors (dim 30, M = 4 -> sizes 8,8,7,7): no 8-bit path, the flag is ignored
     base, q = clustered(3000, 30, 32, seed=5)
     odd = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=16, pq_m=4)
@@ -135,6 +138,59 @@ def test_filters_and_unsupported_shapes_fall_back(jv, fx_l2):
         np.testing.assert_array_equal(r.docs, wd)
         with pytest.raises(ValueError):
             gi.pq_lut_q8(q)
+
+
+@pytest.mark.parametrize("name", ["fx_dot", "fx_l2", "fx_cos8"])
+@pytest.mark.parametrize("selectivity", [0.1, 0.5])
+def test_filtered_queries_on_the_8bit_path(jv, request, name, selectivity):
+    """Accept bits (a9): rejected nodes are traversed but never returned.  The production path keeps accepted and rejected
+    nodes in one list of 8 * rerankK entries; gate = recall parity with the reference loop at equal rerankK."""
+    fx = request.getfixturevalue(name)
+    n = fx.base.shape[0]
+    rng = np.random.default_rng(7)
+    mask = rng.random(n) < selectivity
+    bits = O.make_accept_bits(mask)
+    ora = fx.oracle_index()
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        gt, _, gc = gi.exact_topk(fx.queries, 10, accept_bits=bits)
+        wd, ws, wc, wst = ora.search(fx.queries, 10, 50, accept_bits=bits)
+        for width in (1, 0):
+            r = gi.search(fx.queries, 10, 50, accept_bits=bits, expand_width=width)
+            assert mask[r.docs[r.docs >= 0]].all()                       # never a rejected doc
+            np.testing.assert_array_equal(r.counts, wc)
+            assert recall(r.docs, gt) >= recall(wd, gt) - 0.02
+            for i in range(len(fx.queries)):                             # exact-rerank scores wherever the doc matches
+                ref = {int(d): s for d, s in zip(wd[i], ws[i]) if d >= 0}
+                for d, s in zip(r.docs[i], r.scores[i]):
+                    if int(d) in ref:
+                        assert s == ref[int(d)]
+        # per-query bitsets: query i keeps only docs with doc % 3 == i % 3
+        per = np.stack([O.make_accept_bits((np.arange(n) % 3) == (i % 3)) for i in range(len(fx.queries))])
+        r = gi.search(fx.queries, 10, 50, accept_bits=per)
+        for i in range(len(fx.queries)):
+            d = r.docs[i][r.docs[i] >= 0]
+            assert (d % 3 == i % 3).all() and len(d) == 10
+
+
+def test_filtered_queries_with_deleted_docs_and_empty_filters(jv):
+    base, q = clustered(3000, 64, 32, seed=21, normalize=True)
+    n = base.shape[0]
+    o2d = np.arange(n, dtype=np.int32) * 2                               # ordinal != docId
+    o2d[::7] = -1                                                        # deleted / no-vector ordinals
+    fx = make_fixture(O.SIM_DOT, base, q, max_degree=16, pq_m=16, ord_to_doc=o2d, max_doc=2 * n)
+    mask = np.zeros(2 * n, bool)
+    mask[::4] = True                                                     # docs 0, 4, 8, .. = ordinals 0, 2, 4, ..
+    bits = O.make_accept_bits(mask)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        r = gi.search(q, 10, 50, accept_bits=bits)
+        wd, ws, wc, _ = fx.oracle_index().search(q, 10, 50, accept_bits=bits)
+        got = r.docs[r.docs >= 0]
+        assert (got % 4 == 0).all() and not np.isin(got // 2, np.arange(0, n, 7)).any()
+        np.testing.assert_array_equal(r.counts, wc)
+        gt, _, _ = gi.exact_topk(q, 10, accept_bits=bits)
+        assert recall(r.docs, gt) >= recall(wd, gt) - 0.02
+        none = gi.search(q, 10, 50, accept_bits=O.make_accept_bits(np.zeros(2 * n, bool)))
+        assert (none.counts == 0).all() and (none.docs == -1).all()
 
 
 def test_single_query_and_tiny_graph(jv, fx_dot):
