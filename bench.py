@@ -39,7 +39,12 @@ WORKLOADS = {
     "cfg2-1Mx768-dot-pq192": dict(n=1_000_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=4096),
     "cfg2-small-100kx768": dict(n=100_000, dim=768, sim=1, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=512),
     "tiny-20kx128": dict(n=20_000, dim=128, sim=1, pq_m=32, R=16, k=10, over=5, nq=2_000, latent=32),
+    # the other BASELINE.json configs at a size that builds in seconds (parity / recall checks at scale, not bench lines)
+    "cfg3-1Mx96-l2-pq48": dict(n=1_000_000, dim=96, sim=0, pq_m=48, R=32, k=10, over=5, nq=10_000, latent=32, clusters=4096),
+    "cfg4-250kx1536-cos-pq192": dict(n=250_000, dim=1536, sim=2, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=1024),
+    "cfg5-1Mx128-dot-pq64-k100": dict(n=1_000_000, dim=128, sim=1, pq_m=64, R=32, k=100, over=5, nq=10_000, latent=32, clusters=4096),
 }
+SIM_NAMES = {0: "l2", 1: "dot", 2: "cosine", 3: "mip"}
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -162,12 +167,16 @@ def build_fixture(torch, jv, w, device, seed, n, log, query_seed=None):
         gs.manual_seed(seed + 2)
         sample = base[torch.randperm(n, generator=gs, device=dev_t)[:128_000].sort().values].contiguous()
     cb = torch.empty(K * dim, device=dev_t)
-    N.check(lib.jv_pq_train_dev(device, sample.data_ptr(), sample.shape[0], dim, m, K, 0, 6, seed, cb.data_ptr(), None))
+    center = w["sim"] == 0  # only EUCLIDEAN is centred (JVectorIndexQuantization.java:127)
+    gcent = torch.zeros(dim, device=dev_t) if center else None
+    N.check(lib.jv_pq_train_dev(device, sample.data_ptr(), sample.shape[0], dim, m, K, int(center), 6, seed, cb.data_ptr(),
+                                gcent.data_ptr() if center else None))
     del sample
     log(f"PQ trained ({m}x{K}) in {time.time() - t0:.1f}s")
     codes = torch.empty(n, m, dtype=torch.uint8, device=dev_t)
     enc_ms = C.c_float(0)
-    N.check(lib.jv_pq_encode_dev(device, base.data_ptr(), n, dim, m, K, cb.data_ptr(), None, codes.data_ptr(), C.addressof(enc_ms)))
+    N.check(lib.jv_pq_encode_dev(device, base.data_ptr(), n, dim, m, K, cb.data_ptr(), gcent.data_ptr() if center else None, codes.data_ptr(),
+                                 C.addressof(enc_ms)))
     log(f"PQ encode kernel {enc_ms.value:.2f} ms ({n / enc_ms.value / 1e3:.2f} M vectors/s)")
     t0 = time.time()
     adj = torch.empty(n, w["R"], dtype=torch.int32, device=dev_t)
@@ -175,7 +184,7 @@ def build_fixture(torch, jv, w, device, seed, n, log, query_seed=None):
     N.check(lib.jv_graph_build_dev(device, base.data_ptr(), n, dim, w["sim"], w["R"], 100, 1.2, 1.2, adj.data_ptr(), C.addressof(entry)))
     log(f"Vamana graph (R={w['R']}, beamWidth=100) built in {time.time() - t0:.1f}s, mean degree {(adj >= 0).sum(1).float().mean().item():.1f}")
     host = dict(base=base.cpu().numpy(), queries=queries.cpu().numpy(), cb=cb.cpu().numpy(), codes=codes.cpu().numpy(),
-                adj=adj.cpu().numpy(), entry=int(entry.value), enc_ms=float(enc_ms.value))
+                adj=adj.cpu().numpy(), entry=int(entry.value), enc_ms=float(enc_ms.value), gcent=gcent.cpu().numpy() if center else None)
     del base, codes, adj, cb
     torch.cuda.empty_cache()
     return host, queries
@@ -263,7 +272,7 @@ def main():
     if args.impl == "reference":
         from oracle import oracle as O
         ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
-                            pq_codes=host["codes"])
+                            pq_global_centroid=host.get("gcent"), pq_codes=host["codes"])
         cores = O.num_threads()
         t0 = time.time()
         ora.search(host["queries"][:256], k, rk)
@@ -279,7 +288,7 @@ def main():
         line = {"impl": "reference", "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "n": n_local, "dim": dim, "similarity": "dot", "pq": f"{m}x256", "k": k,
+                "config": {"workload": args.workload, "n": n_local, "dim": dim, "similarity": SIM_NAMES[w["sim"]], "pq": f"{m}x256", "k": k,
                            "rerank_k": rk, "graph": f"Vamana R={R} beamWidth=100 (fixture built on the GPU, shared with our arm)"},
                 "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                  "sample": f"{sample} queries per step, OpenMP one query per thread (CPU restatement of jVector 4.0.0-rc.9, not the JVM)"},
@@ -290,8 +299,8 @@ def main():
     # ------------------------------------------------------------------------------------------ our arm
     flags = {"u8": N.FLAG_LUT_U8, "fp16": N.FLAG_LUT_F16, "fp32": 0}[args.adc_table]
     t0 = time.time()
-    gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"], pq_codes=host["codes"],
-                     device=local_rank, flags=flags)
+    gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"], pq_global_centroid=host.get("gcent"),
+                     pq_codes=host["codes"], device=local_rank, flags=flags)
     log(f"index resident in HBM: {gi.device_bytes() / 2**30:.2f} GiB ({time.time() - t0:.1f}s)")
     dev_t = torch.device("cuda", local_rank)
     base_doc = rank * n_local if shards else 0
@@ -404,7 +413,7 @@ def main():
         "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "n": w["n"], "dim": dim, "similarity": "dot", "pq": f"{m}x256", "k": k, "rerank_k": rk,
+        "config": {"workload": args.workload, "n": w["n"], "dim": dim, "similarity": SIM_NAMES[w["sim"]], "pq": f"{m}x256", "k": k, "rerank_k": rk,
                    "graph": f"Vamana R={R} beamWidth=100", "query_batch": nq, "layout": args.layout if world > 1 else "single",
                    "adc_table": args.adc_table, "expand_width": args.expand_width or 4,
                    "l2": f"index working set {gi.device_bytes() / 2**30:.2f} GiB >> 126 MB L2, no flush needed"},
@@ -429,7 +438,7 @@ def main():
     if rank == 0 and world == 1:
         from oracle import oracle as O
         ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
-                            pq_codes=host["codes"])
+                            pq_global_centroid=host.get("gcent"), pq_codes=host["codes"])
         cores = O.num_threads()
         t0 = time.time()
         ora.search(host["queries"][:256], k, rk)
