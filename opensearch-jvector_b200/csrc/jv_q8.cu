@@ -61,6 +61,18 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void *dst, const v
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// packed fp32 pairs (FFMA2 on sm_100a): two IEEE fmas per instruction, each lane rounded exactly like a scalar fmaf
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t sat_u8_rn(float x) {
     uint32_t u;
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -206,13 +218,19 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
     const bool full = q0 + QT <= p.nq;
     for (int j = warp; j < p.NJ; j += nw) {
         const int m = j * 32 + lane;
-        float qr[QT][S], inv[QT], nlo[QT];
+        float qr[QT][S];
         load_q(m, qr);
+        // queries are processed in pairs with FFMA2: same fmaf chain per query, half the instructions
+        uint64_t q2[QT / 2][S], inv2[QT / 2], nlo2[QT / 2];
 #pragma unroll
-        for (int t = 0; t < QT; t++) {
-            inv[t] = inv_s[t];
-            nlo[t] = -__fmul_rn(lo_s[t * MP + m], inv[t]);
+        for (int t = 0; t < QT / 2; t++) {
+#pragma unroll
+            for (int jj = 0; jj < S; jj++) q2[t][jj] = pack2(qr[2 * t][jj], qr[2 * t + 1][jj]);
+            const float i0 = inv_s[2 * t], i1 = inv_s[2 * t + 1];
+            inv2[t] = pack2(i0, i1);
+            nlo2[t] = pack2(-__fmul_rn(lo_s[(2 * t) * MP + m], i0), -__fmul_rn(lo_s[(2 * t + 1) * MP + m], i1));
         }
+        const uint64_t neg1 = pack2(-1.0f, -1.0f);
         // a chunk holds, for each of the 32 subspaces, the codes {q*64 + ch*EP + e : q < 4, e < EP}: the 4 codes that
         // share one table word ((c & 63) fixed, byte = c >> 6) sit in the same chunk
         auto issue = [&](int ch, int buf) {
@@ -256,19 +274,25 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
                             cv[4 * h] = v.x, cv[4 * h + 1] = v.y, cv[4 * h + 2] = v.z, cv[4 * h + 3] = v.w;
                         }
                     }
+                    uint64_t cv2[S];
 #pragma unroll
-                    for (int t = 0; t < QT; t++) {
-                        float acc = 0.f;
+                    for (int jj = 0; jj < S; jj++) cv2[jj] = pack2(cv[jj], cv[jj]);
+#pragma unroll
+                    for (int t = 0; t < QT / 2; t++) {
+                        uint64_t acc = 0ull; // (+0.f, +0.f)
 #pragma unroll
                         for (int jj = 0; jj < S; jj++) {
                             if (l2) {
-                                const float d = __fsub_rn(qr[t][jj], cv[jj]);
-                                acc = __fmaf_rn(d, d, acc);
+                                const uint64_t d = ffma2(cv2[jj], neg1, q2[t][jj]); // q - c, rounded once like __fsub_rn
+                                acc = ffma2(d, d, acc);
                             } else {
-                                acc = __fmaf_rn(qr[t][jj], cv[jj], acc);
+                                acc = ffma2(q2[t][jj], cv2[jj], acc);
                             }
                         }
-                        qv[t][quarter] = __float2int_rn(__fmaf_rn(acc, inv[t], nlo[t])); // NaN -> 0; saturated to a byte below
+                        float e0, e1;
+                        unpack2(ffma2(acc, inv2[t], nlo2[t]), e0, e1);
+                        qv[2 * t][quarter] = __float2int_rn(e0); // NaN -> 0; saturated to a byte below
+                        qv[2 * t + 1][quarter] = __float2int_rn(e1);
                     }
                 }
                 const int c6 = ch * EP + e; // = c & 63
