@@ -811,14 +811,15 @@ __global__ void __launch_bounds__(W * 32, FILT ? 2 : 4) q8_search_kernel(const Q
             }
             // list entry t moves down by the number of survivors better than it = survivors in gaps 0..t (inclusive prefix
             // sum of gapcnt): warp-level scan, chunks of 32 entries dealt to the warps from the top (survivors use the low ones)
+            int offset = 0, done_cc = 0; // survivors in the gaps [0, done_cc): carried from chunk to chunk (linear in n)
             for (int c0 = (kQW - 1 - warp) * 32; c0 < n; c0 += kQW * 32) {
-                int offset = 0;
-                for (int cc = 0; cc < c0; cc += 32) { // survivors in the gaps of earlier chunks
+                for (int cc = done_cc; cc < c0; cc += 32) { // the chunks between this warp's previous chunk and this one
                     int v = gapcnt[cc + lane];
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(JV_FULL_MASK, v, o);
                     offset += v;
                 }
+                done_cc = c0;
                 const int t = c0 + lane;
                 int v = t < n ? gapcnt[t] : 0;
 #pragma unroll
