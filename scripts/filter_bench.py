@@ -8,6 +8,7 @@ N = jv.native
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2-1Mx768-dot-pq192"
 sel = float(sys.argv[2]) if len(sys.argv) > 2 else 0.1
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
+width = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 w = dict(bench.WORKLOADS[wl])
 host, d_queries = bench.build_fixture(torch, jv, w, 0, 1234, w["n"], lambda m: None)
 k, rk = w["k"], w["k"] * w["over"]
@@ -19,9 +20,9 @@ bits = jv.make_accept_bits(mask)
 q = host["queries"][:nq]
 gt, _, _ = gi.exact_topk(q, k, accept_bits=bits)
 for _ in range(2):
-    r = gi.search(q, k, rk, accept_bits=bits)
+    r = gi.search(q, k, rk, accept_bits=bits, expand_width=width)
 t0 = time.perf_counter()
-r = gi.search(q, k, rk, accept_bits=bits)
+r = gi.search(q, k, rk, accept_bits=bits, expand_width=width)
 dt = time.perf_counter() - t0
 rec = float(np.mean([len(set(a[a >= 0].tolist()) & set(b.tolist())) / k for a, b in zip(r.docs, gt)]))
 print(f"selectivity {sel}: {nq / dt:,.0f} queries/s (search_ms {r.timing['search_ms']:.2f}, rerank_ms {r.timing['rerank_ms']:.2f}) recall@{k} {rec:.4f} "
