@@ -638,7 +638,16 @@ __global__ void __launch_bounds__(W * 32, FILT ? 2 : 4) q8_search_kernel(const Q
                     int slot = 0;
                     if (lane == 0 && ballot) slot = atomicAdd(&s_nn[par], __popc(ballot));
                     slot = __shfl_sync(JV_FULL_MASK, slot, 0);
-                    if (fresh) pool[slot + __popc(ballot & ((1u << lane) - 1u))] = nb;
+                    if (fresh) {
+                        pool[slot + __popc(ballot & ((1u << lane) - 1u))] = nb;
+                        // the code row is read after the pool barrier by whichever group the row is dealt to: start the
+                        // DRAM -> L2 transfer now (rows are 32-byte aligned and <= 256 bytes here: the lines of the first and
+                        // of the last byte cover them; longer rows get their middle lines with the demand loads)
+                        const char *row = reinterpret_cast<const char *>(p.codes_q8 + (int64_t)nb * (NJ * 32));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                        if (NJ * 32 > 128 || (reinterpret_cast<uintptr_t>(row) & 127) + NJ * 32 > 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + NJ * 32 - 1));
+                    }
                 }
             }
             __syncthreads(); // B0: the pool of fresh neighbours is complete
