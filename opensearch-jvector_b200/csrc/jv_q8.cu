@@ -1058,24 +1058,26 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         int32_t st;
         const bool prof = getenv("JVGPU_PROFILE") != nullptr; // per-phase cycle counters (costs registers): diagnostics only
         const int warps = getenv("JVGPU_Q8_WARPS") ? atoi(getenv("JVGPU_Q8_WARPS")) : 4;
+        // the diagnostic instantiations (8 warps, phase counters) exist for the headline shape (M = 192) only
 #define JV_Q8_CASE(NJV)                                                                         \
     case NJV:                                                                                   \
-        if (filt)                                                                               \
-            st = launch_q8_typed<NJV, 4, false, true>(ix, ctx, p);                              \
-        else                                                                                    \
-            st = warps == 8 ? (prof ? launch_q8_typed<NJV, 8, true>(ix, ctx, p) : launch_q8_typed<NJV, 8, false>(ix, ctx, p)) \
-                            : (prof ? launch_q8_typed<NJV, 4, true>(ix, ctx, p) : launch_q8_typed<NJV, 4, false>(ix, ctx, p)); \
+        st = filt ? launch_q8_typed<NJV, 4, false, true>(ix, ctx, p) : launch_q8_typed<NJV, 4, false>(ix, ctx, p); \
         break;
         switch (ix->q8_nj) {
             JV_Q8_CASE(1)
             JV_Q8_CASE(2)
             JV_Q8_CASE(3)
             JV_Q8_CASE(4)
-            JV_Q8_CASE(6)
             JV_Q8_CASE(8)
+        case 6:
+            if (filt)
+                st = launch_q8_typed<6, 4, false, true>(ix, ctx, p);
+            else
+                st = warps == 8 ? (prof ? launch_q8_typed<6, 8, true>(ix, ctx, p) : launch_q8_typed<6, 8, false>(ix, ctx, p))
+                                : (prof ? launch_q8_typed<6, 4, true>(ix, ctx, p) : launch_q8_typed<6, 4, false>(ix, ctx, p));
+            break;
         default:
-            st = filt ? launch_q8_typed<0, 4, false, true>(ix, ctx, p)
-                      : (prof ? launch_q8_typed<0, 4, true>(ix, ctx, p) : launch_q8_typed<0, 4, false>(ix, ctx, p));
+            st = filt ? launch_q8_typed<0, 4, false, true>(ix, ctx, p) : launch_q8_typed<0, 4, false>(ix, ctx, p);
             break;
         }
 #undef JV_Q8_CASE
