@@ -52,7 +52,8 @@ typedef enum jv_status {
     JV_ERR_CUDA = -2,             /* Java side: IOException (no device / CUDA err) */
     JV_ERR_OUT_OF_MEMORY = -3,    /* Java side: IOException                        */
     JV_ERR_UNSUPPORTED = -4,      /* Java side: UnsupportedOperationException      */
-    JV_ERR_INTERNAL = -5
+    JV_ERR_INTERNAL = -5,
+    JV_ERR_CORRUPT = -6           /* Java side: CorruptIndexException / IOException (segment files) */
 } jv_status;
 
 /* ---- similarity ordinals --------------------------------------------
@@ -246,6 +247,65 @@ JV_API int32_t jv_graph_build(int32_t device, const float *vectors, int64_t n, i
 JV_API int32_t jv_graph_build_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t similarity,
                            int32_t max_degree, int32_t beam_width, float neighbor_overflow, float alpha,
                            int32_t *d_out_adjacency, int32_t *out_entry_node);
+
+/* ---- "next" row SURVEY 8f-1: segment-file loader ------------------------------------------------
+ * Reads the files JVectorWriter persists straight into the decoded arrays of a jv_index_desc, so that
+ * the Java side hands over two paths instead of extracting arrays through jVector's API:
+ *   <seg>_<sfx>.meta-jvector          CodecUtil index header "JVectorVectorsFormatMeta" (JVectorFormat.java:23,31-33,
+ *                                     JVectorWriter.java:134-157) · repeat{ int fieldNumber · VectorIndexFieldMetadata
+ *                                     (JVectorWriter.java:528-540) } · int -1 · CodecUtil footer (:573-577);
+ *                                     parsed like JVectorReader.java:52-81,255-262 incl. the v0 rule for the missing
+ *                                     quantisation-type byte (JVectorWriter.java:551-558) and the doc map
+ *                                     (GraphNodeIdToDocMap.java:39-59)
+ *   <seg>_<sfx>_<field>.data-jvector  CodecUtil index header "JVectorVectorsFormatIndex" · OnDiskGraphIndex bytes at
+ *                                     [indexOffset, +indexLength) · optional PQVectors blob at [pqOffset, +pqLength) ·
+ *                                     footer (JVectorWriter.java:383-433,469-510; read at JVectorReader.java:306-331)
+ * Lucene framing (magic, version, CRC-32) is big-endian, everything that goes through IndexOutput.writeInt/Long is
+ * little-endian (JVectorIndexWriter.java:72-83).  The byte layout INSIDE the two jVector blobs belongs to the un-vendored
+ * jar (jvector 4.0.0-rc.9) and is restated from its published format: it has not been checked
+ * against a file written by the real plugin, hence the flags below for the open questions of SURVEY B.3.
+ * No GPU is needed up to jv_field_data_desc(); jv_segment_index_create() = load + jv_index_create(). */
+#define JV_SEGMENT_FLAG_FLOATS_BIG_ENDIAN 1u /* inline vectors / codebooks were written through a big-endian bulk path
+                                                 (B.3-1); default: little-endian, what JVectorIndexWriter.writeFloat emits */
+#define JV_SEGMENT_FLAG_VERIFY_DATA_CRC 2u   /* also CRC the whole field data file on load (the reference does that only
+                                                 in checkIntegrity, JVectorReader.java:87-99) */
+#define JV_SEGMENT_FLAG_LENIENT_MAGIC 4u     /* do not fail on unexpected jVector blob magic numbers (B.3-2) */
+
+typedef struct jv_field_meta {        /* one VectorIndexFieldMetadata record */
+    int32_t struct_size;              /* = sizeof(jv_field_meta), set by the caller */
+    int32_t field_number;
+    int32_t vector_encoding;          /* Lucene VectorEncoding ordinal: 0 BYTE, 1 FLOAT32 */
+    int32_t similarity;               /* JV_SIM_* (the record's simOrd, JVectorReader.java:389-394) */
+    int32_t dim;
+    int32_t quantization_type;        /* 0 none, 1 PQ, 2 NVQ-inline (JVectorIndexQuantization.QUANTIZATION_TYPE_*) */
+    int64_t index_offset, index_length; /* OnDiskGraphIndex bytes inside the field data file */
+    int64_t pq_offset, pq_length;     /* PQVectors blob, 0/0 when absent */
+    float degree_overflow;
+    int32_t graph_nodes;              /* GraphNodeIdToDocMap size */
+    int32_t max_doc;                  /* GraphNodeIdToDocMap maxDocs */
+    int32_t format_version;           /* version of the meta file's index header (0 or 1) */
+} jv_field_meta;
+
+typedef struct jv_segment jv_segment;       /* parsed meta file */
+typedef struct jv_field_data jv_field_data; /* decoded arrays of one field data file (host memory) */
+
+JV_API int32_t jv_segment_open(const char *meta_path, uint32_t flags, jv_segment **out_segment);
+JV_API int32_t jv_segment_close(jv_segment *segment);
+JV_API int32_t jv_segment_field_count(const jv_segment *segment, int32_t *out_count);
+JV_API int32_t jv_segment_field_meta(const jv_segment *segment, int32_t i, jv_field_meta *out_meta);
+/* ordinal -> Lucene docId, -1 for deleted ordinals; capacity >= graph_nodes */
+JV_API int32_t jv_segment_field_doc_map(const jv_segment *segment, int32_t i, int32_t *out_ord_to_doc, int32_t capacity);
+JV_API int32_t jv_segment_load_field(const jv_segment *segment, int32_t i, const char *field_data_path, uint32_t flags,
+                              jv_field_data **out_data);
+/* fills every array pointer / shape of *out_desc (device = 0, flags = 0: the caller sets those); the pointers stay
+ * valid until jv_field_data_free() */
+JV_API int32_t jv_field_data_desc(const jv_field_data *data, jv_index_desc *out_desc);
+JV_API int32_t jv_field_data_free(jv_field_data *data);
+/* FieldEntry ctor in one call (JVectorReader.java:284-337): load, create the device index, drop the host arrays */
+JV_API int32_t jv_segment_index_create(const jv_segment *segment, int32_t i, const char *field_data_path, int32_t device,
+                                uint32_t index_flags, uint32_t load_flags, jv_index **out_index);
+/* CodecUtil.checksumEntireFile of one file (JVectorReader.checkIntegrity, JVectorReader.java:87-99) */
+JV_API int32_t jv_file_check_integrity(const char *path);
 
 #ifdef __cplusplus
 }

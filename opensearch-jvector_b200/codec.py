@@ -264,6 +264,14 @@ class JVectorWriter:
             seg.fields[name] = fd
         return seg
 
+    @staticmethod
+    def write(segment: Segment, directory, segment_name: str = "_0", segment_suffix: str = "JVector_0",
+              field_numbers: Optional[Dict[str, int]] = None, **kw):
+        """Persist a flushed segment in the reference's file layout (JVectorWriter.java:134-165,383-433,469-510,
+        573-577).  Returns {"meta": path, field name: data path}."""
+        from .segment_files import write_segment
+        return write_segment(segment, directory, segment_name, segment_suffix, field_numbers=field_numbers, **kw)
+
 
 class JVectorReader:
     """JVectorReader.java — per-segment reader; `search` is the drop-in for JVectorReader.java:130-210."""
@@ -278,6 +286,32 @@ class JVectorReader:
                 ord_to_doc=fd.doc_map.graph_node_ids_to_doc_ids, max_doc=segment.max_doc, pq_m=fd.pq_m, pq_k=fd.pq_k,
                 pq_codebooks=fd.pq_codebooks, pq_global_centroid=fd.pq_global_centroid, pq_codes=fd.pq_codes,
                 device=device, flags=flags)
+
+    @classmethod
+    def open(cls, directory, field_infos: Dict[int, str], segment_name: str = "_0", segment_suffix: str = "JVector_0",
+             device: int = 0, flags: int = 0, load_flags: int = 0) -> "JVectorReader":
+        """JVectorReader(SegmentReadState), JVectorReader.java:52-81: read the meta file, then one FieldEntry per record
+        (:255-337) — here a single native call per field (jv_segment_index_create) that parses the field data file and
+        copies graph, vectors, PQ codebooks + codes and doc map to the device.  `field_infos` maps Lucene field numbers to
+        names (FieldInfos lives outside this codec)."""
+        from pathlib import Path as _Path
+
+        from .segment_files import META_EXTENSION, SegmentFiles, field_data_file_name, segment_file_name
+        directory = _Path(directory)
+        self = object.__new__(cls)
+        self._segment, self._entries, self._closed = None, {}, False
+        self._files: Dict[str, tuple] = {}
+        self._seg_files = SegmentFiles(directory / segment_file_name(segment_name, segment_suffix, META_EXTENSION), load_flags)
+        try:
+            for i, m in enumerate(self._seg_files.metas):
+                name = field_infos[m.field_number]
+                path = directory / field_data_file_name(segment_name, segment_suffix, name)
+                self._entries[name] = self._seg_files.index_create(i, path, device, flags, load_flags)
+                self._files[name] = (i, path)
+        except Exception:
+            self.close()
+            raise
+        return self
 
     def field_index(self, field: str) -> GpuIndex:
         return self._entries[field]
@@ -335,12 +369,24 @@ class JVectorReader:
         return [ScoreDoc(float(scores[0, j]), int(docs[0, j])) for j in range(int(counts[0]))]
 
     def get_float_vector_values(self, field: str) -> np.ndarray:
+        if self._segment is None:        # opened from files: decode the inline vectors on demand
+            i, path = self._files[field]
+            return self._seg_files.load_field(i, path)["vectors"]
         return self._segment.fields[field].vectors
+
+    def check_integrity(self) -> None:
+        """JVectorReader.checkIntegrity, JVectorReader.java:87-99 (file-backed readers)."""
+        from .segment_files import check_integrity
+        for _, path in getattr(self, "_files", {}).values():
+            check_integrity(path)
 
     def close(self):
         for ix in self._entries.values():
             ix.close()
         self._entries.clear()
+        if getattr(self, "_seg_files", None) is not None:
+            self._seg_files.close()
+            self._seg_files = None
         self._closed = True
 
 

@@ -134,6 +134,17 @@ class GpuIndex:
         N.check(lib.jv_index_create(C.addressof(d), C.addressof(h)))
         self._h = h
 
+    @classmethod
+    def from_handle(cls, handle, similarity: int, n: int, dim: int, max_doc: int, device: int = 0, has_pq: bool = False,
+                    pq_m: int = 0, pq_k: int = 0, max_degree: int = 0) -> "GpuIndex":
+        """Wrap a jv_index* created natively (jv_segment_index_create); the wrapper owns the handle."""
+        self = object.__new__(cls)
+        self.n, self.dim, self.max_doc = int(n), int(dim), int(max_doc)
+        self.similarity, self.device = int(similarity), int(device)
+        self.has_pq, self.pq_m, self.pq_k, self.max_degree = bool(has_pq), int(pq_m), int(pq_k), int(max_degree)
+        self._h = handle
+        return self
+
     # -- lifetime (FieldEntry.close, JVectorReader.java:367-378)
     def close(self):
         if getattr(self, "_h", None):

@@ -9,7 +9,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libjvgpu.so"
 
 JV_OK = 0
-ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_INTERNAL = -1, -2, -3, -4, -5
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_INTERNAL, ERR_CORRUPT = -1, -2, -3, -4, -5, -6
 SIM_EUCLIDEAN, SIM_DOT, SIM_COSINE, SIM_MIP = 0, 1, 2, 3
 FLAG_FUSED_LAYOUT, FLAG_LUT_F16, FLAG_NO_VECTORS_ON_DEVICE, FLAG_LUT_U8 = 1, 2, 4, 8
 
@@ -24,6 +24,16 @@ class IndexDesc(C.Structure):
         ("device", C.c_int32), ("flags", C.c_uint32),
         ("nvq_m", C.c_int32), ("nvq_reserved", C.c_int32),
         ("nvq_bytes", C.c_void_p), ("nvq_params", C.c_void_p), ("nvq_global_mean", C.c_void_p),
+    ]
+
+
+class FieldMeta(C.Structure):
+    """jv_field_meta: one VectorIndexFieldMetadata record of the meta file (JVectorWriter.java:528-540)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("field_number", C.c_int32), ("vector_encoding", C.c_int32), ("similarity", C.c_int32),
+        ("dim", C.c_int32), ("quantization_type", C.c_int32),
+        ("index_offset", C.c_int64), ("index_length", C.c_int64), ("pq_offset", C.c_int64), ("pq_length", C.c_int64),
+        ("degree_overflow", C.c_float), ("graph_nodes", C.c_int32), ("max_doc", C.c_int32), ("format_version", C.c_int32),
     ]
 
 
@@ -67,6 +77,16 @@ SYMBOLS = {
     "jv_pq_train_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
     "jv_graph_build": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
     "jv_graph_build_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
+    "jv_segment_open": (_I32, [C.c_char_p, C.c_uint32, _P]),
+    "jv_segment_close": (_I32, [_P]),
+    "jv_segment_field_count": (_I32, [_P, _P]),
+    "jv_segment_field_meta": (_I32, [_P, _I32, _P]),
+    "jv_segment_field_doc_map": (_I32, [_P, _I32, _P, _I32]),
+    "jv_segment_load_field": (_I32, [_P, _I32, C.c_char_p, C.c_uint32, _P]),
+    "jv_field_data_desc": (_I32, [_P, _P]),
+    "jv_field_data_free": (_I32, [_P]),
+    "jv_segment_index_create": (_I32, [_P, _I32, C.c_char_p, _I32, C.c_uint32, C.c_uint32, _P]),
+    "jv_file_check_integrity": (_I32, [C.c_char_p]),
 }
 
 
