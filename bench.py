@@ -43,6 +43,10 @@ WORKLOADS = {
     "cfg3-1Mx96-l2-pq48": dict(n=1_000_000, dim=96, sim=0, pq_m=48, R=32, k=10, over=5, nq=10_000, latent=32, clusters=4096),
     "cfg4-250kx1536-cos-pq192": dict(n=250_000, dim=1536, sim=2, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=1024),
     "cfg5-1Mx128-dot-pq64-k100": dict(n=1_000_000, dim=128, sim=1, pq_m=64, R=32, k=100, over=5, nq=10_000, latent=32, clusters=4096),
+    # full-size single-GPU cases: config 3 whole on one GPU (under --layout shards each rank holds n / world of it), and ONE of
+    # config 5's eight shards (100M / 8) with the fp32 rerank vectors in pinned host memory (--host-vectors)
+    "cfg3-10Mx96-l2-pq48": dict(n=10_000_000, dim=96, sim=0, pq_m=48, R=32, k=10, over=5, nq=10_000, latent=32, clusters=40960),
+    "cfg5-shard-12.5Mx128-dot-pq64-k100": dict(n=12_500_000, dim=128, sim=1, pq_m=64, R=32, k=100, over=5, nq=10_000, latent=32, clusters=51200),
 }
 SIM_NAMES = {0: "l2", 1: "dot", 2: "cosine", 3: "mip"}
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -216,6 +220,9 @@ def main():
     ap.add_argument("--overquery", type=int, default=0, help="override the workload's overquery factor (rerankK = k * overquery)")
     ap.add_argument("--latent", type=int, default=0, help="override the intrinsic dimension of the synthetic data")
     ap.add_argument("--clusters", type=int, default=0, help="override the number of mixture components of the synthetic data")
+    ap.add_argument("--host-vectors", action="store_true",
+                    help="keep the fp32 rerank vectors in pinned host memory (JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE, config 5); the exact "
+                         "ground truth is computed first on a device-resident copy of the same index")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
@@ -314,6 +321,13 @@ def main():
     t0 = time.time()
     gi.exact_topk_dev(d_queries.data_ptr(), nq, k, gt_doc.data_ptr(), gt_score.data_ptr(), gt_cnt.data_ptr())  # ground truth (K5)
     log(f"exact ground truth for {nq} queries in {time.time() - t0:.2f}s")
+    if args.host_vectors:  # same index, rerank vectors read over PCIe from pinned host memory
+        torch.cuda.synchronize(local_rank)
+        gi.close()
+        gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
+                         pq_global_centroid=host.get("gcent"), pq_codes=host["codes"], device=local_rank,
+                         flags=flags | N.FLAG_NO_VECTORS_ON_DEVICE)
+        log(f"re-created with the fp32 vectors in pinned host memory: {gi.device_bytes() / 2**30:.2f} GiB on the device")
 
     def merge_shards(docs_t, scores_t):
         """K7: all-gather the per-GPU lists over NCCL and merge them on the device."""
@@ -418,6 +432,7 @@ def main():
         "config": {"workload": args.workload, "n": w["n"], "dim": dim, "similarity": SIM_NAMES[w["sim"]], "pq": f"{m}x256", "k": k, "rerank_k": rk,
                    "graph": f"Vamana R={R} beamWidth=100", "query_batch": nq, "layout": args.layout if world > 1 else "single",
                    "adc_table": args.adc_table, "expand_width": args.expand_width or 4,
+                   "rerank_vectors": "pinned host memory" if args.host_vectors else "HBM",
                    "l2": f"index working set {gi.device_bytes() / 2**30:.2f} GiB >> 126 MB L2, no flush needed"},
         "recall_at_10": rec, "wall_ms_per_step": t_wall / args.steps * 1e3,
         "visited_per_query": float(st[:, 0].mean()), "expanded_per_query": float(st[:, 1].mean()),
