@@ -426,8 +426,16 @@ __device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, 
 // FILT = accept bits given: the list also holds rejected nodes (they are traversed, never returned), up to Lc entries; only
 // entries ranked before the L-th ACCEPTED one can still be expanded (the reference stops when the best candidate is worse than
 // the worst of rerankK accepted results), and that entry's key is the admission threshold for new nodes.
+// CTAs per SM the register allocation must allow.  The kernel is latency-bound and its throughput follows the queries in
+// flight per SM, which shared memory caps at 227 KB / (table + lists + filter): 4 at M = 192 (48 KB tables),
+// but 8 / 6 / 5 with the 16 / 24 / 32 KB tables of M <= 64 / 96 / 128 — there the register file must not be the limit
+// (65536 / (128 threads * CTAs) registers per thread).
+constexpr int q8_min_ctas(int nj, int warps, bool filt) {
+    return filt ? 2 : warps != 4 ? 4 : (nj == 1 || nj == 2) ? 8 : nj == 3 ? 6 : nj == 4 ? 5 : 4;
+}
+
 template <int NJ_T, int W, bool PROF, bool FILT>
-__global__ void __launch_bounds__(W * 32, FILT ? 2 : 4) q8_search_kernel(const Q8Params p) {
+__global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_kernel(const Q8Params p) {
     constexpr int kQW = W, kQThreads = W * 32, NG = 4 * W;
     constexpr int U = W == 4 ? 3 : 2; // rows in flight per row group and pass: NG * U rows >= the fresh neighbours of a typical step
     constexpr int NJC = NJ_T > 0 ? NJ_T : 1;
