@@ -285,3 +285,37 @@ def test_gpu_reader_from_files_matches_in_memory_reader(jv, oracle, tmp_path, si
         finally:
             mem.close()
             disk.close()
+
+
+def test_committed_golden_segment(jv, tmp_path):
+    """tests/golden/segment/ (written by tests/golden/make_golden_segment.py): the loader parses the committed bytes, and the
+    writer mirror still produces exactly those bytes — neither side can drift alone."""
+    import importlib.util
+    from pathlib import Path
+    from opensearch_jvector_b200 import segment_files as SF
+    gdir = Path(__file__).resolve().parent / "golden" / "segment"
+    spec = importlib.util.spec_from_file_location("make_golden_segment", gdir.parent / "make_golden_segment.py")
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    meta, data = gdir / "_g_JVector_0.meta-jvector", gdir / "_g_JVector_0_vec.data-jvector"
+    # known bytes of the committed meta file: CodecUtil header, first record, end marker, footer
+    b = meta.read_bytes()
+    assert len(b) == 159 and b[:4] == bytes.fromhex("3fd76c17") and b[5:29] == b"JVectorVectorsFormatMeta"
+    assert b[29:33] == bytes.fromhex("00000001") and b[33:49] == bytes(range(0xA0, 0xB0)) and b[49:59] == b"\x09JVector_0"
+    assert b[59:63] == struct.pack("<i", 2) and b[63:75] == struct.pack("<iii", 2, 1, 0)      # fieldNumber x2, FLOAT32, EUCLIDEAN
+    assert b[75] == 6 and b[76] == 60                                                            # vint dim, vlong indexOffset
+    assert b[-20:-16] == struct.pack("<i", -1) and b[-16:-8] == bytes.fromhex("c02893e800000000")
+    assert struct.unpack(">Q", b[-8:])[0] == zlib.crc32(b[:-8])
+    vec, adj, docs, cb, gcent, codes = mk.arrays()
+    with SF.SegmentFiles(meta) as s:
+        m = s.metas[0]
+        assert (m.field_number, m.similarity, m.dim, m.quantization_type, m.graph_nodes, m.max_doc) == (2, 0, 6, 1, 40, 130)
+        assert np.array_equal(s.doc_map(0), docs) and s.doc_map(0)[7] == -1
+        out = s.load_field(0, data, SF.FLAG_VERIFY_DATA_CRC)
+    assert np.array_equal(out["vectors"], vec) and np.array_equal(out["adjacency"], adj) and out["entry_node"] == 11
+    assert (out["pq_m"], out["pq_k"]) == (3, 16) and np.array_equal(out["pq_codes"], codes)
+    assert np.array_equal(out["pq_codebooks"], cb) and np.array_equal(out["pq_global_centroid"], gcent)
+    fresh = mk.write(tmp_path)
+    for name in ("_g_JVector_0.meta-jvector", "_g_JVector_0.data-jvector", "_g_JVector_0_vec.data-jvector"):
+        assert (tmp_path / name).read_bytes() == (gdir / name).read_bytes(), name
+    assert set(p.name for p in fresh.values()) == {"_g_JVector_0.meta-jvector", "_g_JVector_0_vec.data-jvector"}
