@@ -434,7 +434,9 @@ constexpr int q8_min_ctas(int nj, int warps, bool filt) {
     return filt ? 2 : warps != 4 ? 4 : (nj == 1 || nj == 2) ? 8 : nj == 3 ? 6 : nj == 4 ? 5 : 4;
 }
 
-template <int NJ_T, int W, bool PROF, bool FILT>
+// FUSE = K3 as the epilogue (diagnostic, JVGPU_Q8_FUSED): a separate instantiation so that the production kernel does not
+// carry the rerank code (the step loop alone is larger than the 32 KB L1.5 instruction cache).
+template <int NJ_T, int W, bool PROF, bool FILT, bool FUSE>
 __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_kernel(const Q8Params p) {
     constexpr int kQW = W, kQThreads = W * 32, NG = 4 * W;
     constexpr int U = W == 4 ? 3 : 2; // rows in flight per row group and pass: NG * U rows >= the fresh neighbours of a typical step
@@ -765,9 +767,10 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
 
             // ---- (c) merge.  Phase 1: position of every survivor in the list (binary search); a survivor equal to a list
             //          entry is a re-scored member (evicted from the visited filter earlier) and is dropped.
-            int my_pos[2] = {0, 0}; // survivors tid and tid + 128 (E * R <= 256)
-#pragma unroll
+            int my_pos0 = 0, my_pos1 = 0; // survivors tid and tid + 128 (E * R <= 256)
+#pragma unroll 1
             for (int c = 0; c < 2; c++) {
+                if (c * kQThreads >= ns) break; // (uniform) the second round exists only when a step queues > 128 survivors
                 const int t = tid + c * kQThreads;
                 if (t < ns) {
                     const uint64_t a = surv[t];
@@ -785,7 +788,7 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                     } else {
                         atomicAdd(&gapcnt[lo], 1); // lo list entries are better than this survivor
                     }
-                    my_pos[c] = lo;
+                    if (c == 0) my_pos0 = lo; else my_pos1 = lo;
                 }
             }
             __syncthreads(); // B1.5: duplicates are zeroed
@@ -801,19 +804,25 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
             //          Two survivors can carry the SAME key: when the visited filter evicts an entry that was inserted in
             //          this very step, the node is scored twice.  Equal keys are ordered by queue index, so every element
             //          still gets its own slot (no holes); the copy is removed when the list is emitted.
-            auto count_gt = [&](int j0, int j1, uint64_t thr) -> int { // survivors j0..j1-1 with key > thr
-                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = j0;
-                for (; j + 4 <= j1; j += 4) {
+            // survivors queued before this warp's 32 count when >= a (earlier queue index wins ties), the others when > a:
+            // one loop, threshold a - 1 in front of t0
+            auto count_better = [&](int t0, uint64_t a) -> int {
+                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = 0;
+#pragma unroll 1
+                for (; j + 4 <= ns; j += 4) {
+                    const uint64_t thr = a - (j < t0 ? 1ull : 0ull); // t0 is a multiple of 32: the 4 entries are on one side
                     c0 += (surv[j] > thr) ? 1 : 0;
                     c1 += (surv[j + 1] > thr) ? 1 : 0;
                     c2 += (surv[j + 2] > thr) ? 1 : 0;
                     c3 += (surv[j + 3] > thr) ? 1 : 0;
                 }
-                for (; j < j1; j++) c0 += (surv[j] > thr) ? 1 : 0;
+#pragma unroll 1
+                for (; j < ns; j++) c0 += (surv[j] > a - (j < t0 ? 1ull : 0ull)) ? 1 : 0;
                 return (c0 + c1) + (c2 + c3);
             };
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 2; c++) {
+                if (c * kQThreads >= ns) break;
                 const int t = tid + c * kQThreads;
                 if (t < ns) {
                     const uint64_t a = surv[t];
@@ -821,7 +830,7 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                     const uint32_t same = __match_any_sync(__activemask(), a) & ((1u << lane) - 1u);
                     if (a != 0ull) {
                         const int t0 = t & ~31; // this warp's survivors start here
-                        const int pos = my_pos[c] + count_gt(0, t0, a - 1ull) + count_gt(t0, ns, a) + __popc(same);
+                        const int pos = (c == 0 ? my_pos0 : my_pos1) + count_better(t0, a) + __popc(same);
                         if (pos < Lc) out[pos] = (a << 1) | 1ull;
                     }
                 }
@@ -865,7 +874,7 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
         {
             const uint64_t *list = cur ? list1 : list0;
             uint64_t *akeys = cur ? list0 : list1; // fused rerank: converted keys go to the idle list buffer
-            uint64_t *o = p.fuse_k ? akeys : p.approx_keys + (int64_t)qi * L;
+            uint64_t *o = FUSE ? akeys : p.approx_keys + (int64_t)qi * L;
             auto key_of = [&](uint64_t k) -> uint64_t {
                 const int32_t node = node_of(k);
                 const uint32_t ord = (uint32_t)(k >> 32);
@@ -883,25 +892,25 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                         if ((k & 2ull) && (i == 0 || (k >> 1) != (list[i - 1] >> 1))) o[w++] = key_of(k);
                     }
                     s_nn[0] = w; // broadcast slot (reset at the top of the next query)
-                    for (; !p.fuse_k && w < L; w++) o[w] = 0ull;
+                    for (; !FUSE && w < L; w++) o[w] = 0ull;
                 }
                 __syncthreads();
                 cnt = s_nn[0];
             } else if (!__syncthreads_or(dup)) {
-                for (int i = tid; i < (p.fuse_k ? n : L); i += kQThreads) o[i] = i < n ? key_of(list[i]) : 0ull;
+                for (int i = tid; i < (FUSE ? n : L); i += kQThreads) o[i] = i < n ? key_of(list[i]) : 0ull;
             } else { // rare: serial compaction
                 if (tid == 0) {
                     int w = 0;
                     for (int i = 0; i < n; i++)
                         if (i == 0 || (list[i] >> 1) != (list[i - 1] >> 1)) o[w++] = key_of(list[i]);
                     s_nn[0] = w; // broadcast slot (reset at the top of the next query)
-                    for (; !p.fuse_k && w < L; w++) o[w] = 0ull;
+                    for (; !FUSE && w < L; w++) o[w] = 0ull;
                 }
                 __syncthreads();
                 cnt = s_nn[0];
             }
             int reranked = 0;
-            if (p.fuse_k) {
+            if (FUSE) {
                 // ---- K3 as the epilogue: the table is no longer needed, its shared memory holds the fp32 query and the keys
                 __syncthreads();
                 float *sq = reinterpret_cast<float *>(smem_raw);
@@ -934,10 +943,10 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
     }
 }
 
-template <int NJ_T, int W, bool PROF, bool FILT = false>
+template <int NJ_T, int W, bool PROF, bool FILT = false, bool FUSE = false>
 static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
     constexpr int kQThreads = W * 32;
-    auto kern = q8_search_kernel<NJ_T, W, PROF, FILT>;
+    auto kern = q8_search_kernel<NJ_T, W, PROF, FILT, FUSE>;
     const int Lc = FILT ? p.Lc : p.L;
     const size_t fixed = (size_t)p.lutb + (size_t)Lc * 16 + (size_t)p.surv_cap * 12 + (size_t)((Lc + 2) & ~1) * 4;
     const size_t sm_total = 228 * 1024;
@@ -1019,6 +1028,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         }
         Q8Params p;
         memset(&p, 0, sizeof(p));
+        const bool filt = a.d_accept != nullptr;
         p.adjacency = ix->adjacency.as<int32_t>();
         p.codes_q8 = ix->codes_q8.as<uint8_t>();
         p.node_norm = ix->node_norm.as<float>();
@@ -1040,7 +1050,6 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         p.E = E;
         p.dim = ix->dim;
         p.ord_to_doc = ix->ord_to_doc.as<int32_t>();
-        const bool filt = a.d_accept != nullptr;
         p.Lc = filt ? q8_filtered_list_cap(a.rerank_k) : a.rerank_k;
         p.accept = a.d_accept;
         p.accept_stride = a.accept_stride_words; // words per query (0 = one bitset for the batch)
@@ -1049,7 +1058,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         // separate rerank kernel — a 4-warp CTA gathers its 50 rows one DRAM round trip after the other while it holds
         // 1/4 of an SM; the stand-alone K3 keeps 16 CTAs per SM in flight (0.31 ms, 0.76 of the HBM roofline) — so off by default.
         const bool fuse = a.fuse_k > 0 && !ix->vectors_on_host && !ix->has_nvq && (size_t)ix->dim * 4 + 16 + (size_t)a.rerank_k * 8 <= (size_t)lutb &&
-                          getenv("JVGPU_Q8_FUSED") != nullptr;
+                          ix->q8_nj == 6 && !filt && getenv("JVGPU_Q8_FUSED") != nullptr; // instantiated for the headline shape only
         if (fuse) {
             p.fuse_k = a.fuse_k;
             p.rerank_floor = a.rerank_floor;
@@ -1081,8 +1090,9 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
             if (filt)
                 st = launch_q8_typed<6, 4, false, true>(ix, ctx, p);
             else
-                st = warps == 8 ? (prof ? launch_q8_typed<6, 8, true>(ix, ctx, p) : launch_q8_typed<6, 8, false>(ix, ctx, p))
-                                : (prof ? launch_q8_typed<6, 4, true>(ix, ctx, p) : launch_q8_typed<6, 4, false>(ix, ctx, p));
+                st = fuse         ? launch_q8_typed<6, 4, false, false, true>(ix, ctx, p)
+                     : warps == 8 ? (prof ? launch_q8_typed<6, 8, true>(ix, ctx, p) : launch_q8_typed<6, 8, false>(ix, ctx, p))
+                                  : (prof ? launch_q8_typed<6, 4, true>(ix, ctx, p) : launch_q8_typed<6, 4, false>(ix, ctx, p));
             break;
         default:
             st = filt ? launch_q8_typed<0, 4, false, true>(ix, ctx, p) : launch_q8_typed<0, 4, false>(ix, ctx, p);
