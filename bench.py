@@ -412,6 +412,44 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - e0
 
+    # ---- the same call from TWO host threads at once (Lucene searches the leaves of a shard from a thread pool, and the
+    # reference reader is shared between threads: KNNJVectorTests.java:982-1028): the copies of one caller overlap the kernels
+    # of the other.  Reported next to the single-caller number, never instead of it.
+    e2e_conc = None
+    if world == 1:
+        bufs = []
+        for _ in range(2):
+            bufs.append((hq.clone().pin_memory(), torch.empty(nq, k, dtype=torch.int32).pin_memory(), torch.empty(nq, k, dtype=torch.float32).pin_memory(),
+                         torch.empty(nq, dtype=torch.int32).pin_memory(), torch.empty(nq, 4, dtype=torch.int32).pin_memory()))
+        per_thread = max(1, args.steps // 2)
+        errs = []
+
+        def caller(b):
+            try:
+                torch.cuda.set_device(local_rank)
+                for _ in range(per_thread):
+                    N.check(lib.jv_search_batch(gi.handle, b[0].data_ptr(), nq, C.addressof(p), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
+                                                b[4].data_ptr(), None))
+            except Exception as e:  # surfaced below
+                errs.append(e)
+
+        for b in bufs:  # warm both contexts
+            N.check(lib.jv_search_batch(gi.handle, b[0].data_ptr(), nq, C.addressof(p), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(), b[4].data_ptr(), None))
+        barrier()
+        c0 = time.perf_counter()
+        ths = [threading.Thread(target=caller, args=(b,)) for b in bufs]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        barrier()
+        conc_wall = time.perf_counter() - c0
+        if errs:
+            raise errs[0]
+        same = bool((bufs[0][1] == h_doc).all() and (bufs[1][1] == h_doc).all())
+        e2e_conc = {"value": 2 * per_thread * nq / conc_wall, "unit": "queries/s", "callers": 2, "batches": 2 * per_thread,
+                    "results_identical_to_single_caller": same}
+
     # max over ranks
     t_dev, t_wall, t_e2e = dev_ms / 1e3, wall, e2e_wall
     if dist is not None:
@@ -456,6 +494,7 @@ def main():
         "pq_encode": {"kernel_ms": host["enc_ms"], "vectors_per_s": n_local / (host["enc_ms"] * 1e-3)},
         "e2e": {"value": units / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                 "d2h_bytes_per_step": nq * k * 8 + nq * 4 + nq * 16},
+        "e2e_two_callers": e2e_conc,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
