@@ -248,6 +248,19 @@ JV_API int32_t jv_graph_build_dev(int32_t device, const float *d_vectors, int64_
                            int32_t max_degree, int32_t beam_width, float neighbor_overflow, float alpha,
                            int32_t *d_out_adjacency, int32_t *out_entry_node);
 
+/* Leading-segment merge, insert-only part (JVectorWriter.tryLeadingSegmentMerge, JVectorWriter.java:1166-1341): the first n0
+ * ordinals keep the leading segment's graph (seed_adjacency [n0*max_degree], -1 padded at the end of each row; its entry node
+ * stays the entry), the cached neighbour scores are recomputed (exact pair scores, what the neighbours-score-cache file holds),
+ * and vectors n0..n-1 are inserted like builder.addGraphNode with the batched schedule of jv_graph_build.  A leading segment
+ * with deleted documents needs markNodeDeleted + cleanup, which is not modelled: rebuild with jv_graph_build (the reference's
+ * own fallback when leading-segment merge is skipped, :1166-1230).  out_adjacency [n*max_degree]. */
+JV_API int32_t jv_graph_extend(int32_t device, const float *vectors, int64_t n, int64_t n0, const int32_t *seed_adjacency,
+                        int32_t seed_entry, int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width,
+                        float neighbor_overflow, float alpha, int32_t *out_adjacency);
+JV_API int32_t jv_graph_extend_dev(int32_t device, const float *d_vectors, int64_t n, int64_t n0, const int32_t *d_seed_adjacency,
+                            int32_t seed_entry, int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width,
+                            float neighbor_overflow, float alpha, int32_t *d_out_adjacency);
+
 /* ---- "next" row SURVEY 8f-1: segment-file loader ------------------------------------------------
  * Reads the files JVectorWriter persists straight into the decoded arrays of a jv_index_desc, so that
  * the Java side hands over two paths instead of extracting arrays through jVector's API:

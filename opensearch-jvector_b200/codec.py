@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import native as N
-from .index import GpuIndex, graph_build, make_accept_bits, pq_encode, pq_train
+from .index import GpuIndex, graph_build, graph_extend, make_accept_bits, pq_encode, pq_train
 
 # ---- constants (KNNConstants.java:83-114, JVectorFormat.java:22-35) -------------------------------
 DEFAULT_MAX_CONN = 32
@@ -263,6 +263,62 @@ class JVectorWriter:
                     JVectorIndexQuantization.compute_pq_vectors(vecs, sim, m, self.device)
             seg.fields[name] = fd
         return seg
+
+    def merge(self, segments: Sequence[Segment], live_docs: Optional[Sequence[Optional[np.ndarray]]] = None) -> Segment:
+        """mergeOneField over whole segments (JVectorWriter.java:1040-1160): the merged segment holds the live documents of
+        `segments` in order (docIds re-based like Lucene's MergeState doc maps: segment i starts after the live docs of the
+        segments before it).  The first segment is the LEADING one: when none of its documents is deleted its graph is kept and
+        the other segments' vectors are inserted into it (tryLeadingSegmentMerge, :1166-1341 -> jv_graph_extend); otherwise the
+        graph is rebuilt from the live vectors (the reference's fallback, :1390-1422).  PQ is recomputed over the merged vectors
+        when there are enough of them (mergePQ, :1095-1124; the reference refines the leading codebooks, this mirror retrains).
+        `live_docs[i]`: bool mask over segment i's docIds (None = all live)."""
+        live_docs = list(live_docs) if live_docs is not None else [None] * len(segments)
+        merged = Segment(max_doc=0)
+        bases, base = [], 0
+        remap = []                                   # per segment: old docId -> new docId (-1 = deleted)
+        for seg, live in zip(segments, live_docs):
+            mask = np.ones(seg.max_doc, bool) if live is None else np.asarray(live, bool)
+            new_ids = np.full(seg.max_doc, -1, np.int64)
+            new_ids[mask] = base + np.arange(int(mask.sum()))
+            remap.append(new_ids)
+            bases.append(base)
+            base += int(mask.sum())
+        merged.max_doc = base
+        for name, lead in segments[0].fields.items():
+            vec_parts, doc_parts = [], []
+            lead_all_live = True
+            for si, seg in enumerate(segments):
+                fd = seg.fields.get(name)
+                if fd is None:
+                    continue
+                ords = fd.doc_map.graph_node_ids_to_doc_ids
+                new_docs = np.where(ords >= 0, remap[si][np.maximum(ords, 0)], -1)
+                keep = new_docs >= 0
+                if si == 0:
+                    lead_all_live = bool(keep.all())
+                vec_parts.append(fd.vectors[keep])
+                doc_parts.append(new_docs[keep])
+            vecs = np.concatenate(vec_parts).astype(np.float32)
+            docs = np.concatenate(doc_parts).astype(np.int32)
+            n = vecs.shape[0]
+            out = FieldData(lead.similarity, vecs, np.zeros((n, self.max_conn), np.int32), 0, GraphNodeIdToDocMap(docs, merged.max_doc))
+            n0 = lead.vectors.shape[0]
+            if n > 0:
+                if lead_all_live and 0 < n0 < n and lead.adjacency.shape[1] == self.max_conn:
+                    out.adjacency = graph_extend(vecs, lead.adjacency, lead.entry_node, lead.similarity.jvector_ord, self.beam_width,
+                                                 self.neighbor_overflow, self.alpha, self.device)
+                    out.entry_node = lead.entry_node
+                elif lead_all_live and n0 == n:
+                    out.adjacency, out.entry_node = lead.adjacency, lead.entry_node
+                else:
+                    out.adjacency, out.entry_node = graph_build(vecs, lead.similarity.jvector_ord, self.max_conn, self.beam_width,
+                                                                self.neighbor_overflow, self.alpha, self.device)
+            if n >= self.min_batch:
+                m = self.num_pq_subspaces(vecs.shape[1])
+                out.pq_m, out.pq_k, out.pq_codebooks, out.pq_global_centroid, out.pq_codes = \
+                    JVectorIndexQuantization.compute_pq_vectors(vecs, lead.similarity, m, self.device)
+            merged.fields[name] = out
+        return merged
 
     @staticmethod
     def write(segment: Segment, directory, segment_name: str = "_0", segment_suffix: str = "JVector_0",

@@ -444,6 +444,32 @@ backlink_kernel(const BuildParams p, int mode, int64_t done, const uint64_t *__r
     }
 }
 
+// leading-segment merge (JVectorWriter.java:1166-1341, insert-only part): the first n0 ordinals keep their graph.  One warp per
+// seed node copies its row (stride R -> Rb) and recomputes the cached neighbour scores (exact pair scores: what the reference
+// reads back from the neighbours-score-cache file).  *bad is raised when a neighbour id lies outside [0, n0).
+__global__ void seed_kernel(const BuildParams p, const int32_t *__restrict__ seed_adj, int64_t n0, int *bad) {
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= n0) return;
+    const bool vec4 = (p.dim & 3) == 0;
+    int du = 0;
+    for (int j = 0; j < p.R; j++) {
+        const int32_t nb = __ldg(seed_adj + u * p.R + j);
+        if (nb < 0) break;
+        if (nb >= n0) {
+            if (lane == 0) atomicExch(bad, 1);
+            break;
+        }
+        const float s = pair_score(p, (int32_t)u, nb, lane, vec4);
+        if (lane == 0) {
+            p.adj[u * p.Rb + j] = nb;
+            p.ads[u * p.Rb + j] = s;
+        }
+        du++;
+    }
+    if (lane == 0) p.deg[u] = du;
+}
+
 __global__ void order_kernel(int32_t *order, int64_t n, int32_t entry) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -465,9 +491,13 @@ __global__ void export_adj_kernel(const int32_t *__restrict__ adj, const int32_t
     out[i] = j < deg[u] ? adj[u * Rb + j] : -1;
 }
 
+// n0 > 0: seeded build (jv_graph_extend): ordinals [0, n0) keep the graph d_seed_adj [n0][R] and its entry node
 static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t n, int dim, int sim, int R, int beam,
-                                    float overflow, float alpha, int32_t *d_out_adj, int32_t *out_entry) {
+                                    float overflow, float alpha, int32_t *d_out_adj, int32_t *out_entry, int64_t n0 = 0,
+                                    const int32_t *d_seed_adj = nullptr, int32_t seed_entry = 0) {
     JV_REQUIRE(n >= 1 && n < 0x7fffffffLL && dim >= 1, "bad n/dim");
+    JV_REQUIRE(n0 >= 0 && n0 <= n && (n0 == 0 || (d_seed_adj != nullptr && seed_entry >= 0 && seed_entry < n0)),
+               "seed graph: n0 must be in [0, n], seed_entry in [0, n0)");
     JV_REQUIRE(R >= 1 && R <= 96 && beam >= 1 && beam <= 1024, "max_degree must be in [1,96], beam_width in [1,1024]");
     JV_REQUIRE(sim >= JV_SIM_EUCLIDEAN && sim <= JV_SIM_MIP, "unknown similarity");
     JV_REQUIRE(overflow >= 1.0f && overflow <= 1.3f && alpha >= 1.0f, "neighbor_overflow must be in [1,1.3], alpha >= 1");
@@ -515,19 +545,24 @@ static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t 
     JV_CUDA_TRY(cudaMemsetAsync(deg.p, 0, (size_t)n * 4, st));
     JV_CUDA_TRY(cudaMemsetAsync(ads.p, 0, (size_t)n * Rb * 4, st));
 
-    // entry = medoid: best exact score against the mean vector (ties -> lower ordinal) = brute force with nq = 1, k = 1
-    mean_kernel<<<(dim + 127) / 128, 128, 0, st>>>(d_vectors, n, dim, mean.as<float>());
-    JV_CUDA_TRY(cudaGetLastError());
     int launches = 0;
-    JV_TRY(launch_exact_topk(&ix, &ctx, mean.as<float>(), 1, 1, nullptr, 0, e_doc.as<int32_t>(), e_score.as<float>(),
-                             e_cnt.as<int32_t>(), &launches));
     int32_t entry = 0;
-    JV_CUDA_TRY(cudaMemcpyAsync(&entry, e_doc.p, 4, cudaMemcpyDeviceToHost, st));
-    JV_CUDA_TRY(cudaStreamSynchronize(st));
-    JV_REQUIRE(entry >= 0 && entry < n, "medoid search failed");
+    if (n0 > 0) {
+        entry = seed_entry; // the leading graph keeps its entry node; insertion order = ordinal order
+        order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order.as<int32_t>(), n, 0);
+    } else {
+        // entry = medoid: best exact score against the mean vector (ties -> lower ordinal) = brute force with nq = 1, k = 1
+        mean_kernel<<<(dim + 127) / 128, 128, 0, st>>>(d_vectors, n, dim, mean.as<float>());
+        JV_CUDA_TRY(cudaGetLastError());
+        JV_TRY(launch_exact_topk(&ix, &ctx, mean.as<float>(), 1, 1, nullptr, 0, e_doc.as<int32_t>(), e_score.as<float>(),
+                                 e_cnt.as<int32_t>(), &launches));
+        JV_CUDA_TRY(cudaMemcpyAsync(&entry, e_doc.p, 4, cudaMemcpyDeviceToHost, st));
+        JV_CUDA_TRY(cudaStreamSynchronize(st));
+        JV_REQUIRE(entry >= 0 && entry < n, "medoid search failed");
+        order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order.as<int32_t>(), n, entry);
+    }
     *out_entry = entry;
     ix.entry = entry;
-    order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order.as<int32_t>(), n, entry);
 
     BuildParams bp;
     bp.vectors = d_vectors;
@@ -569,6 +604,16 @@ static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t 
     const int grid_back = ix.sm_count * (occ_back > 0 ? occ_back : 1);
 
     int64_t done = 1;
+    if (n0 > 0) {
+        JV_CUDA_TRY(cudaMemsetAsync(counters.p, 0, 8, st));
+        seed_kernel<<<(unsigned)((n0 * 32 + 255) / 256), 256, 0, st>>>(bp, d_seed_adj, n0, counters.as<int>());
+        JV_CUDA_TRY(cudaGetLastError());
+        int bad = 0;
+        JV_CUDA_TRY(cudaMemcpyAsync(&bad, counters.p, 4, cudaMemcpyDeviceToHost, st));
+        JV_CUDA_TRY(cudaStreamSynchronize(st));
+        JV_REQUIRE(bad == 0, "seed graph: a neighbour id lies outside [0, n0)");
+        done = n0;
+    }
     while (done < n) {
         int64_t bs = done < bcap ? done : bcap;
         if (bs > n - done) bs = n - done;
@@ -683,6 +728,44 @@ int32_t jv_graph_build(int32_t device, const float *vectors, int64_t n, int32_t 
     JV_CUDA_TRY(cudaMemcpy(dx.p, vectors, (size_t)n * dim * 4, cudaMemcpyHostToDevice));
     JV_TRY(graph_build_dev_impl(device, dx.as<float>(), n, dim, similarity, max_degree, beam_width, neighbor_overflow, alpha,
                                 dadj.as<int32_t>(), out_entry_node));
+    JV_CUDA_TRY(cudaMemcpy(out_adjacency, dadj.p, (size_t)n * max_degree * 4, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
+int32_t jv_graph_extend_dev(int32_t device, const float *d_vectors, int64_t n, int64_t n0, const int32_t *d_seed_adjacency,
+                            int32_t seed_entry, int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width,
+                            float neighbor_overflow, float alpha, int32_t *d_out_adjacency) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) {
+        set_error("no usable CUDA device %d; libjvgpu has no CPU fallback", device);
+        return JV_ERR_CUDA;
+    }
+    JV_REQUIRE(n0 >= 1, "n0 must be >= 1 (use jv_graph_build for an empty seed)");
+    DeviceGuard guard(device);
+    int32_t entry = 0;
+    return graph_build_dev_impl(device, d_vectors, n, dim, similarity, max_degree, beam_width, neighbor_overflow, alpha,
+                                d_out_adjacency, &entry, n0, d_seed_adjacency, seed_entry);
+}
+
+int32_t jv_graph_extend(int32_t device, const float *vectors, int64_t n, int64_t n0, const int32_t *seed_adjacency, int32_t seed_entry,
+                        int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width, float neighbor_overflow, float alpha,
+                        int32_t *out_adjacency) {
+    JV_REQUIRE(vectors && seed_adjacency && out_adjacency && n >= 1 && n0 >= 1 && n0 <= n && dim >= 1 && max_degree >= 1, "bad arguments");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) {
+        set_error("no usable CUDA device %d; libjvgpu has no CPU fallback", device);
+        return JV_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    DevBuf dx, dadj, dseed;
+    JV_TRY(dx.alloc((size_t)n * dim * 4));
+    JV_TRY(dadj.alloc((size_t)n * max_degree * 4));
+    JV_TRY(dseed.alloc((size_t)n0 * max_degree * 4));
+    JV_CUDA_TRY(cudaMemcpy(dx.p, vectors, (size_t)n * dim * 4, cudaMemcpyHostToDevice));
+    JV_CUDA_TRY(cudaMemcpy(dseed.p, seed_adjacency, (size_t)n0 * max_degree * 4, cudaMemcpyHostToDevice));
+    int32_t entry = 0;
+    JV_TRY(graph_build_dev_impl(device, dx.as<float>(), n, dim, similarity, max_degree, beam_width, neighbor_overflow, alpha,
+                                dadj.as<int32_t>(), &entry, n0, dseed.as<int32_t>(), seed_entry));
     JV_CUDA_TRY(cudaMemcpy(out_adjacency, dadj.p, (size_t)n * max_degree * 4, cudaMemcpyDeviceToHost));
     return JV_OK;
 }

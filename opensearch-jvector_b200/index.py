@@ -76,6 +76,20 @@ def graph_build(vectors, similarity: int, max_degree: int = 32, beam_width: int 
     return adj, int(entry.value)
 
 
+def graph_extend(vectors, seed_adjacency, seed_entry: int, similarity: int, beam_width: int = 100, neighbor_overflow: float = 1.2,
+                 alpha: float = 1.2, device: int = 0):
+    """Leading-segment merge, insert-only (JVectorWriter.java:1166-1341): ordinals [0, len(seed_adjacency)) keep their graph
+    and entry node, the remaining vectors are inserted.  Returns adjacency[n, R] int32."""
+    v = _f32(vectors)
+    n, dim = v.shape
+    seed = np.ascontiguousarray(seed_adjacency, dtype=np.int32)
+    n0, r = seed.shape
+    adj = np.empty((n, r), dtype=np.int32)
+    N.check(N.load().jv_graph_extend(device, _ptr(v), n, n0, _ptr(seed), seed_entry, dim, similarity, r, beam_width, neighbor_overflow,
+                                     alpha, _ptr(adj)))
+    return adj
+
+
 def merge_topk(docs, scores, k: int, device: int = 0):
     """[g, nq, k] per-shard lists -> merged [nq, k] (K7)."""
     d = np.ascontiguousarray(docs, dtype=np.int32)

@@ -77,6 +77,8 @@ SYMBOLS = {
     "jv_pq_train_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
     "jv_graph_build": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
     "jv_graph_build_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
+    "jv_graph_extend": (_I32, [_I32, _P, _I64, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _P]),
+    "jv_graph_extend_dev": (_I32, [_I32, _P, _I64, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _P]),
     "jv_segment_open": (_I32, [C.c_char_p, C.c_uint32, _P]),
     "jv_segment_close": (_I32, [_P]),
     "jv_segment_field_count": (_I32, [_P, _P]),

@@ -1139,9 +1139,13 @@ static void sort_by_key_desc(int32_t *nodes, float *scores, int n) {
     free(k);
 }
 
-JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim, int32_t sim, int32_t R, int32_t beam,
-                                   float overflow, float alpha, int32_t max_batch, float frac, int32_t *out_adj,
-                                   int32_t *out_entry) {
+/* n0 > 0: the first n0 ordinals already form a graph (seed_adj [n0][R], -1 padded at the end of each row; seed_entry):
+ * "leading segment merge", JVectorWriter.java:1166-1341 (insert-only part) — the leading segment's graph is loaded with its
+ * cached neighbour scores (here: recomputed, they are exact pair scores) and the other segments' vectors are added with
+ * builder.addGraphNode; the entry node stays the leading graph's.  n0 == 0: build from scratch (medoid entry). */
+static int32_t graph_build_impl(const float *vectors, int64_t n, int32_t dim, int32_t sim, int32_t R, int32_t beam,
+                                float overflow, float alpha, int32_t max_batch, float frac, int64_t n0, const int32_t *seed_adj,
+                                int32_t seed_entry, int32_t *out_adj, int32_t *out_entry) {
     const int bsim = sim == JV_SIM_MIP ? JV_SIM_DOT : sim;
     const int cap = (int)ceilf((float)R * overflow) + 1; /* list capacity incl. one overflow slot */
     /* medoid */
@@ -1162,13 +1166,18 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
         }
     }
     free(mean);
+    if (n0 > 0) entry = seed_entry; /* the leading graph keeps its entry node */
     *out_entry = entry;
 
-    /* insertion order: entry first, then ordinals ascending */
+    /* insertion order: entry first, then ordinals ascending (seeded: ordinals n0.. in order) */
     int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
-    order[0] = entry;
-    for (int64_t i = 0, j = 1; i < n; i++)
-        if (i != entry) order[j++] = (int32_t)i;
+    if (n0 > 0) {
+        for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
+    } else {
+        order[0] = entry;
+        for (int64_t i = 0, j = 1; i < n; i++)
+            if (i != entry) order[j++] = (int32_t)i;
+    }
 
     /* dynamic adjacency with scores (score of neighbour w.r.t. owner) */
     int32_t **adj = (int32_t **)calloc((size_t)n, sizeof(int32_t *));
@@ -1195,6 +1204,25 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
 
     inserted[entry] = 1;
     int64_t done = 1;
+    if (n0 > 0) { /* seed: lists of the leading graph, scores = exact pair scores (the neighbours-score cache) */
+        for (int64_t u = 0; u < n0; u++) {
+            int du = 0;
+            while (du < R && seed_adj[u * R + du] >= 0) du++;
+            acap[u] = cap + 8;
+            adj[u] = (int32_t *)malloc(sizeof(int32_t) * (size_t)acap[u]);
+            ads[u] = (float *)malloc(sizeof(float) * (size_t)acap[u]);
+            const float *uv = vectors + u * dim;
+            const float unorm = canon_dot(uv, uv, dim);
+            for (int j = 0; j < du; j++) {
+                adj[u][j] = seed_adj[u * R + j];
+                ads[u][j] = exact_score(bsim, uv, unorm, vectors + (int64_t)adj[u][j] * dim, dim);
+            }
+            deg[u] = du;
+            inserted[u] = 1;
+            for (int j = 0; j < Rb; j++) flat[u * Rb + j] = j < du ? adj[u][j] : -1;
+        }
+        done = n0;
+    }
     /* prefix doubling, capped at n/divisor (integer: the device builder must compute the same cap) and max_batch */
     const int64_t divisor = frac > 0.f ? (int64_t)(1.0f / frac + 0.5f) : 50;
     int64_t bcap = n / (divisor > 0 ? divisor : 50);
@@ -1331,6 +1359,20 @@ JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim,
     free(order);
     jvo_index_destroy(ix);
     return 0;
+}
+
+JVO_EXPORT int32_t jvo_graph_build(const float *vectors, int64_t n, int32_t dim, int32_t sim, int32_t R, int32_t beam,
+                                   float overflow, float alpha, int32_t max_batch, float frac, int32_t *out_adj,
+                                   int32_t *out_entry) {
+    return graph_build_impl(vectors, n, dim, sim, R, beam, overflow, alpha, max_batch, frac, 0, NULL, 0, out_adj, out_entry);
+}
+
+JVO_EXPORT int32_t jvo_graph_extend(const float *vectors, int64_t n, int64_t n0, const int32_t *seed_adj, int32_t seed_entry,
+                                    int32_t dim, int32_t sim, int32_t R, int32_t beam, float overflow, float alpha,
+                                    int32_t max_batch, float frac, int32_t *out_adj) {
+    int32_t entry = 0;
+    if (n0 < 1 || n0 > n || seed_entry < 0 || seed_entry >= n0) return -1;
+    return graph_build_impl(vectors, n, dim, sim, R, beam, overflow, alpha, max_batch, frac, n0, seed_adj, seed_entry, out_adj, &entry);
 }
 
 JVO_EXPORT int32_t jvo_num_threads(void) {

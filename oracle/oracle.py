@@ -183,6 +183,23 @@ def graph_build(vectors, sim: int, max_degree: int = 32, beam_width: int = 100, 
     return adj, int(entry.value)
 
 
+def graph_extend(vectors, seed_adjacency, seed_entry: int, sim: int, beam_width: int = 100, overflow: float = 1.2,
+                 alpha: float = 1.2, max_batch: int = 8192, frac: float = 0.02):
+    """Fixture: leading-segment merge, insert-only (JVectorWriter.java:1166-1341): the first len(seed_adjacency) ordinals
+    keep their graph, the remaining vectors are added with the same batched-insert schedule.  Returns adjacency[n, R]."""
+    v = _f32(vectors)
+    n, dim = v.shape
+    seed = np.ascontiguousarray(seed_adjacency, dtype=np.int32)
+    n0, r = seed.shape
+    adj = np.empty((n, r), dtype=np.int32)
+    st = lib().jvo_graph_extend(_p(v), C.c_int64(n), C.c_int64(n0), _p(seed), C.c_int32(seed_entry), C.c_int32(dim), C.c_int32(sim),
+                                C.c_int32(r), C.c_int32(beam_width), C.c_float(overflow), C.c_float(alpha), C.c_int32(max_batch),
+                                C.c_float(frac), _p(adj))
+    if st != 0:
+        raise ValueError("bad seed graph")
+    return adj
+
+
 class OracleIndex:
     """One field of one segment, as decoded arrays (what FieldEntry holds, JVectorReader.java:284-337)."""
 
