@@ -261,6 +261,19 @@ JV_API int32_t jv_graph_extend_dev(int32_t device, const float *d_vectors, int64
                             int32_t seed_entry, int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width,
                             float neighbor_overflow, float alpha, int32_t *d_out_adjacency);
 
+/* Delete consolidation: builder.markNodeDeleted(...) + builder.cleanup() of a merge (JVectorWriter.java:1318-1327), i.e.
+ * jVector's GraphIndexBuilder.removeDeletedNodes = FreshDiskANN section 4.2: every live node with a deleted out-neighbour j gets
+ * j's live out-neighbours as candidates next to its own live ones, scored exactly, sorted best first and re-pruned with
+ * retainDiverse(max_degree, alpha).  deleted [n] (0/1 bytes).  Same ordinal space in and out (rows of deleted nodes come back
+ * empty; the writer compacts ordinals afterwards).  A deleted entry node is replaced by the best-scoring live candidate around
+ * it, else the lowest live ordinal, else -1 (jVector picks an approximate medoid: documented deviation). */
+JV_API int32_t jv_graph_remove_deleted(int32_t device, const float *vectors, int64_t n, int32_t dim, int32_t similarity,
+                                int32_t max_degree, float alpha, const int32_t *adjacency, const uint8_t *deleted,
+                                int32_t entry_node, int32_t *out_adjacency, int32_t *out_entry_node);
+JV_API int32_t jv_graph_remove_deleted_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t similarity,
+                                    int32_t max_degree, float alpha, const int32_t *d_adjacency, const uint8_t *d_deleted,
+                                    int32_t entry_node, int32_t *d_out_adjacency, int32_t *out_entry_node);
+
 /* ---- "next" row SURVEY 8f-1: segment-file loader ------------------------------------------------
  * Reads the files JVectorWriter persists straight into the decoded arrays of a jv_index_desc, so that
  * the Java side hands over two paths instead of extracting arrays through jVector's API:

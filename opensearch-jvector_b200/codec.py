@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import native as N
-from .index import GpuIndex, graph_build, graph_extend, make_accept_bits, pq_encode, pq_train
+from .index import GpuIndex, graph_build, graph_extend, graph_remove_deleted, make_accept_bits, pq_encode, pq_train
 
 # ---- constants (KNNConstants.java:83-114, JVectorFormat.java:22-35) -------------------------------
 DEFAULT_MAX_CONN = 32
@@ -267,9 +267,9 @@ class JVectorWriter:
     def merge(self, segments: Sequence[Segment], live_docs: Optional[Sequence[Optional[np.ndarray]]] = None) -> Segment:
         """mergeOneField over whole segments (JVectorWriter.java:1040-1160): the merged segment holds the live documents of
         `segments` in order (docIds re-based like Lucene's MergeState doc maps: segment i starts after the live docs of the
-        segments before it).  The first segment is the LEADING one: when none of its documents is deleted its graph is kept and
-        the other segments' vectors are inserted into it (tryLeadingSegmentMerge, :1166-1341 -> jv_graph_extend); otherwise the
-        graph is rebuilt from the live vectors (the reference's fallback, :1390-1422).  PQ is recomputed over the merged vectors
+        segments before it).  The first segment is the LEADING one: its graph is kept, the other segments' live vectors are
+        inserted into it (tryLeadingSegmentMerge, :1166-1341 -> jv_graph_extend), its deleted nodes are consolidated away
+        (markNodeDeleted + cleanup -> jv_graph_remove_deleted) and the ordinals are compacted as the on-disk writer does.  PQ is recomputed over the merged vectors
         when there are enough of them (mergePQ, :1095-1124; the reference refines the leading codebooks, this mirror retrains).
         `live_docs[i]`: bool mask over segment i's docIds (None = all live)."""
         live_docs = list(live_docs) if live_docs is not None else [None] * len(segments)
@@ -286,7 +286,7 @@ class JVectorWriter:
         merged.max_doc = base
         for name, lead in segments[0].fields.items():
             vec_parts, doc_parts = [], []
-            lead_all_live = True
+            lead_keep = None
             for si, seg in enumerate(segments):
                 fd = seg.fields.get(name)
                 if fd is None:
@@ -295,7 +295,7 @@ class JVectorWriter:
                 new_docs = np.where(ords >= 0, remap[si][np.maximum(ords, 0)], -1)
                 keep = new_docs >= 0
                 if si == 0:
-                    lead_all_live = bool(keep.all())
+                    lead_keep = keep
                 vec_parts.append(fd.vectors[keep])
                 doc_parts.append(new_docs[keep])
             vecs = np.concatenate(vec_parts).astype(np.float32)
@@ -303,15 +303,26 @@ class JVectorWriter:
             n = vecs.shape[0]
             out = FieldData(lead.similarity, vecs, np.zeros((n, self.max_conn), np.int32), 0, GraphNodeIdToDocMap(docs, merged.max_doc))
             n0 = lead.vectors.shape[0]
+            sim_ord = lead.similarity.jvector_ord
             if n > 0:
-                if lead_all_live and 0 < n0 < n and lead.adjacency.shape[1] == self.max_conn:
-                    out.adjacency = graph_extend(vecs, lead.adjacency, lead.entry_node, lead.similarity.jvector_ord, self.beam_width,
-                                                 self.neighbor_overflow, self.alpha, self.device)
-                    out.entry_node = lead.entry_node
-                elif lead_all_live and n0 == n:
-                    out.adjacency, out.entry_node = lead.adjacency, lead.entry_node
+                if n0 > 0 and lead_keep.any() and lead.adjacency.shape[1] == self.max_conn:
+                    # heap ordinal space of the reference (:1240-1262): every leading node, deleted ones included, then the others
+                    heap_vecs = np.concatenate([lead.vectors] + vec_parts[1:]).astype(np.float32)
+                    adj, entry = lead.adjacency, lead.entry_node
+                    if heap_vecs.shape[0] > n0:                       # builder.addGraphNode for the other segments' vectors
+                        adj = graph_extend(heap_vecs, adj, entry, sim_ord, self.beam_width, self.neighbor_overflow, self.alpha, self.device)
+                    if not lead_keep.all():                           # builder.markNodeDeleted + cleanup (:1318-1327)
+                        dead = np.zeros(heap_vecs.shape[0], bool)
+                        dead[:n0] = ~lead_keep
+                        adj, entry = graph_remove_deleted(heap_vecs, adj, entry, dead, sim_ord, self.alpha, self.device)
+                        live = ~dead                                  # the on-disk writer compacts ordinals, order preserved
+                        to_final = np.full(heap_vecs.shape[0], -1, np.int64)
+                        to_final[live] = np.arange(int(live.sum()))
+                        adj = np.where(adj[live] >= 0, to_final[np.maximum(adj[live], 0)], -1).astype(np.int32)
+                        entry = int(to_final[entry])
+                    out.adjacency, out.entry_node = np.ascontiguousarray(adj, np.int32), entry
                 else:
-                    out.adjacency, out.entry_node = graph_build(vecs, lead.similarity.jvector_ord, self.max_conn, self.beam_width,
+                    out.adjacency, out.entry_node = graph_build(vecs, sim_ord, self.max_conn, self.beam_width,
                                                                 self.neighbor_overflow, self.alpha, self.device)
             if n >= self.min_batch:
                 m = self.num_pq_subspaces(vecs.shape[1])

@@ -663,6 +663,192 @@ static int32_t graph_build_dev_impl(int device, const float *d_vectors, int64_t 
     return JV_OK;
 }
 
+
+// ================================================================================================
+// Delete consolidation (GraphIndexBuilder.removeDeletedNodes behind markNodeDeleted + cleanup, JVectorWriter.java:1318-1327;
+// FreshDiskANN section 4.2): same definition as the oracle's jvo_graph_remove_deleted.
+// ================================================================================================
+// pass 1, one warp per node: deleted rows are emptied, rows without a deleted neighbour are copied, the rest is queued
+__global__ void consolidate_scan_kernel(const int32_t *__restrict__ adj, const uint8_t *__restrict__ deleted, int64_t n, int R,
+                                        int32_t *__restrict__ out_adj, int32_t *todo, int *n_todo) {
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= n) return;
+    const bool dead = deleted[u] != 0;
+    bool hit = false;
+    for (int r0 = 0; r0 < R; r0 += 32) {
+        const int j = r0 + lane;
+        const int32_t nb = j < R ? __ldg(adj + u * R + j) : -1;
+        if (j < R) out_adj[u * R + j] = dead ? -1 : nb;
+        hit |= nb >= 0 && deleted[nb] != 0;
+    }
+    hit = __any_sync(0xffffffffu, hit);
+    if (!dead && hit && lane == 0) todo[atomicAdd(n_todo, 1)] = (int32_t)u;
+}
+
+// ordered compaction of one chunk of kPruneThreads flags: returns this thread's output position (base + rank) and advances base
+__device__ __forceinline__ int block_rank(bool flag, int &base, int *warp_tot) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kPruneWarps; w++) {
+        const int c = warp_tot[w];
+        before += w < warp ? c : 0;
+        total += c;
+    }
+    const int pos = base + before + __popc(bal & ((1u << lane) - 1u));
+    base += total;
+    __syncthreads();
+    return pos;
+}
+
+// pass 2, one block per queued node (entry_mode: the deleted entry node; only the best live candidate is reported)
+__global__ void __launch_bounds__(kPruneThreads)
+consolidate_kernel(const BuildParams p, const int32_t *__restrict__ adj, const uint8_t *__restrict__ deleted,
+                   const int32_t *__restrict__ todo, int entry_mode, int32_t entry, int32_t *__restrict__ out_adj, int32_t *out_entry) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);              // [kAppendCap]
+    int32_t *ids = reinterpret_cast<int32_t *>(keys + kAppendCap);        // [kAppendCap]
+    int32_t *cn = ids + kAppendCap;                                       // [kPruneMaxCands]
+    float *cs = reinterpret_cast<float *>(cn + kPruneMaxCands);           // [kPruneMaxCands]
+    int32_t *sel = reinterpret_cast<int32_t *>(cs + kPruneMaxCands);      // [R]
+    float *sels = reinterpret_cast<float *>(sel + p.R);                   // [R]
+    int32_t *nbr = reinterpret_cast<int32_t *>(sels + p.R);               // [R]
+    uint8_t *taken = reinterpret_cast<uint8_t *>(nbr + p.R);              // [kPruneMaxCands]
+    __shared__ int warp_tot[kPruneWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, R = p.R;
+    const int32_t u = entry_mode ? entry : todo[blockIdx.x];
+    for (int j = tid; j < R; j += kPruneThreads) nbr[j] = __ldg(adj + (int64_t)u * R + j);
+    __syncthreads();
+    // candidates in slot order: segment 0 = live neighbours of u, segment 1 + j = live neighbours k != u of deleted neighbour j
+    int m = 0;
+    for (int s0 = 0; s0 < (R + 1) * R; s0 += kPruneThreads) {
+        const int s = s0 + tid;
+        int32_t cand = -1;
+        if (s < (R + 1) * R) {
+            const int seg = s / R, idx = s - seg * R;
+            if (seg == 0) {
+                cand = nbr[idx];
+                if (cand >= 0 && deleted[cand]) cand = -1;
+            } else {
+                const int32_t j = nbr[seg - 1];
+                if (j >= 0 && deleted[j]) {
+                    cand = __ldg(adj + (int64_t)j * R + idx);
+                    if (cand == u || (cand >= 0 && deleted[cand])) cand = -1;
+                }
+            }
+        }
+        const int pos = block_rank(cand >= 0, m, warp_tot);
+        if (cand >= 0 && pos < kAppendCap) ids[pos] = cand;
+    }
+    if (m > kAppendCap) m = kAppendCap;
+    __syncthreads();
+    const bool vec4 = (p.dim & 3) == 0;
+    for (int i = warp; i < m; i += kPruneWarps) {
+        const float sc = pair_score(p, u, ids[i], lane, vec4);
+        if (lane == 0) keys[i] = jv_mk_key(sc, ids[i]);
+    }
+    int n2 = 1;
+    while (n2 < m) n2 <<= 1;
+    for (int i = m + tid; i < n2; i += kPruneThreads) keys[i] = 0ull;
+    __syncthreads();
+    block_sort_desc(keys, n2);
+    // duplicates (a node reachable through several deleted neighbours) carry equal keys and are adjacent
+    int w = 0;
+    for (int i0 = 0; i0 < m; i0 += kPruneThreads) {
+        const int i = i0 + tid;
+        const bool uniq = i < m && (i == 0 || keys[i] != keys[i - 1]);
+        const int pos = block_rank(uniq, w, warp_tot);
+        if (uniq && pos < kPruneMaxCands) {
+            cn[pos] = jv_key_id(keys[i]);
+            cs[pos] = jv_key_score(keys[i]);
+        }
+    }
+    const int nc = w < kPruneMaxCands ? w : kPruneMaxCands;
+    __syncthreads();
+    if (entry_mode) {
+        if (tid == 0) *out_entry = nc > 0 ? cn[0] : -1;
+        return;
+    }
+    const int nsel = retain_diverse_block(p, cn, cs, nc, taken, sel, sels);
+    for (int j = tid; j < R; j += kPruneThreads) out_adj[(int64_t)u * R + j] = j < nsel ? sel[j] : -1;
+}
+
+__global__ void first_live_kernel(const uint8_t *__restrict__ deleted, int64_t n, int *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !deleted[i]) atomicMin(out, (int)i);
+}
+
+static int32_t graph_remove_deleted_dev_impl(int device, const float *d_vectors, int64_t n, int dim, int sim, int R, float alpha,
+                                             const int32_t *d_adj, const uint8_t *d_deleted, int32_t entry, int32_t *d_out_adj,
+                                             int32_t *out_entry) {
+    JV_REQUIRE(n >= 1 && n < 0x7fffffffLL && dim >= 1, "bad n/dim");
+    JV_REQUIRE(R >= 1 && R <= 96 && alpha >= 1.0f, "max_degree must be in [1,96], alpha >= 1");
+    JV_REQUIRE(sim >= JV_SIM_EUCLIDEAN && sim <= JV_SIM_MIP, "unknown similarity");
+    JV_REQUIRE(d_vectors && d_adj && d_deleted && d_out_adj && out_entry, "NULL buffer");
+    JV_REQUIRE(entry >= 0 && entry < n, "entry node outside [0, n)");
+    const int bsim = sim == JV_SIM_MIP ? JV_SIM_DOT : sim;
+    cudaStream_t st = nullptr;
+    JV_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamDestroy(s); }
+    } sg{st};
+    DevBuf norms, todo, counters;
+    BuildParams bp;
+    memset(&bp, 0, sizeof(bp));
+    if (bsim == JV_SIM_COSINE) {
+        JV_TRY(norms.alloc((size_t)n * 4));
+        JV_TRY(launch_vec_norms(st, d_vectors, n, dim, norms.as<float>()));
+    }
+    bp.vectors = d_vectors;
+    bp.vec_norm = norms.as<float>();
+    bp.n = n;
+    bp.dim = dim;
+    bp.sim = bsim;
+    bp.R = R;
+    bp.Rb = R;
+    bp.alpha = alpha;
+    JV_TRY(todo.alloc((size_t)n * 4));
+    JV_TRY(counters.alloc(8));
+    JV_CUDA_TRY(cudaMemsetAsync(counters.p, 0, 8, st));
+    consolidate_scan_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_adj, d_deleted, n, R, d_out_adj, todo.as<int32_t>(),
+                                                                              counters.as<int>());
+    JV_CUDA_TRY(cudaGetLastError());
+    int n_todo = 0;
+    uint8_t entry_dead = 0;
+    JV_CUDA_TRY(cudaMemcpyAsync(&n_todo, counters.p, 4, cudaMemcpyDeviceToHost, st));
+    JV_CUDA_TRY(cudaMemcpyAsync(&entry_dead, d_deleted + entry, 1, cudaMemcpyDeviceToHost, st));
+    JV_CUDA_TRY(cudaStreamSynchronize(st));
+    const size_t smem = (size_t)kAppendCap * 12 + (size_t)kPruneMaxCands * 9 + (size_t)R * 12 + 16;
+    JV_CUDA_TRY(cudaFuncSetAttribute(consolidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_todo > 0) {
+        consolidate_kernel<<<(unsigned)n_todo, kPruneThreads, smem, st>>>(bp, d_adj, d_deleted, todo.as<int32_t>(), 0, 0, d_out_adj, nullptr);
+        JV_CUDA_TRY(cudaGetLastError());
+    }
+    int32_t e = entry;
+    if (entry_dead) {
+        int32_t *d_e = counters.as<int32_t>() + 1;
+        consolidate_kernel<<<1, kPruneThreads, smem, st>>>(bp, d_adj, d_deleted, nullptr, 1, entry, nullptr, d_e);
+        JV_CUDA_TRY(cudaGetLastError());
+        JV_CUDA_TRY(cudaMemcpyAsync(&e, d_e, 4, cudaMemcpyDeviceToHost, st));
+        JV_CUDA_TRY(cudaStreamSynchronize(st));
+        if (e < 0) { // no live node around the old entry: the lowest live ordinal
+            const int big = 0x7fffffff;
+            JV_CUDA_TRY(cudaMemcpyAsync(d_e, &big, 4, cudaMemcpyHostToDevice, st));
+            first_live_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_deleted, n, d_e);
+            JV_CUDA_TRY(cudaMemcpyAsync(&e, d_e, 4, cudaMemcpyDeviceToHost, st));
+            JV_CUDA_TRY(cudaStreamSynchronize(st));
+            if (e == big) e = -1;
+        }
+    }
+    JV_CUDA_TRY(cudaStreamSynchronize(st));
+    *out_entry = e;
+    return JV_OK;
+}
+
 }  // namespace jv
 
 using namespace jv;
@@ -767,6 +953,43 @@ int32_t jv_graph_extend(int32_t device, const float *vectors, int64_t n, int64_t
     JV_TRY(graph_build_dev_impl(device, dx.as<float>(), n, dim, similarity, max_degree, beam_width, neighbor_overflow, alpha,
                                 dadj.as<int32_t>(), &entry, n0, dseed.as<int32_t>(), seed_entry));
     JV_CUDA_TRY(cudaMemcpy(out_adjacency, dadj.p, (size_t)n * max_degree * 4, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
+int32_t jv_graph_remove_deleted_dev(int32_t device, const float *d_vectors, int64_t n, int32_t dim, int32_t similarity,
+                                    int32_t max_degree, float alpha, const int32_t *d_adjacency, const uint8_t *d_deleted,
+                                    int32_t entry_node, int32_t *d_out_adjacency, int32_t *out_entry_node) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) {
+        set_error("no usable CUDA device %d; libjvgpu has no CPU fallback", device);
+        return JV_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    return graph_remove_deleted_dev_impl(device, d_vectors, n, dim, similarity, max_degree, alpha, d_adjacency, d_deleted, entry_node,
+                                         d_out_adjacency, out_entry_node);
+}
+
+int32_t jv_graph_remove_deleted(int32_t device, const float *vectors, int64_t n, int32_t dim, int32_t similarity, int32_t max_degree,
+                                float alpha, const int32_t *adjacency, const uint8_t *deleted, int32_t entry_node,
+                                int32_t *out_adjacency, int32_t *out_entry_node) {
+    JV_REQUIRE(vectors && adjacency && deleted && out_adjacency && out_entry_node && n >= 1 && dim >= 1 && max_degree >= 1, "bad arguments");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) {
+        set_error("no usable CUDA device %d; libjvgpu has no CPU fallback", device);
+        return JV_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    DevBuf dx, dadj, dout, ddel;
+    JV_TRY(dx.alloc((size_t)n * dim * 4));
+    JV_TRY(dadj.alloc((size_t)n * max_degree * 4));
+    JV_TRY(dout.alloc((size_t)n * max_degree * 4));
+    JV_TRY(ddel.alloc((size_t)n));
+    JV_CUDA_TRY(cudaMemcpy(dx.p, vectors, (size_t)n * dim * 4, cudaMemcpyHostToDevice));
+    JV_CUDA_TRY(cudaMemcpy(dadj.p, adjacency, (size_t)n * max_degree * 4, cudaMemcpyHostToDevice));
+    JV_CUDA_TRY(cudaMemcpy(ddel.p, deleted, (size_t)n, cudaMemcpyHostToDevice));
+    JV_TRY(graph_remove_deleted_dev_impl(device, dx.as<float>(), n, dim, similarity, max_degree, alpha, dadj.as<int32_t>(),
+                                         ddel.as<uint8_t>(), entry_node, dout.as<int32_t>(), out_entry_node));
+    JV_CUDA_TRY(cudaMemcpy(out_adjacency, dout.p, (size_t)n * max_degree * 4, cudaMemcpyDeviceToHost));
     return JV_OK;
 }
 

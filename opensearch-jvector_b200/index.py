@@ -90,6 +90,20 @@ def graph_extend(vectors, seed_adjacency, seed_entry: int, similarity: int, beam
     return adj
 
 
+def graph_remove_deleted(vectors, adjacency, entry_node: int, deleted, similarity: int, alpha: float = 1.2, device: int = 0):
+    """markNodeDeleted + cleanup of a merge (JVectorWriter.java:1318-1327): FreshDiskANN-style delete consolidation on the GPU.
+    Same ordinal space in and out.  Returns (adjacency[n, R], entry_node)."""
+    v = _f32(vectors)
+    n, dim = v.shape
+    a = np.ascontiguousarray(adjacency, dtype=np.int32)
+    d = np.ascontiguousarray(np.asarray(deleted, dtype=bool).astype(np.uint8))
+    out = np.empty_like(a)
+    e = C.c_int32(0)
+    N.check(N.load().jv_graph_remove_deleted(device, _ptr(v), n, dim, similarity, a.shape[1], alpha, _ptr(a), _ptr(d), entry_node,
+                                             _ptr(out), C.addressof(e)))
+    return out, int(e.value)
+
+
 def merge_topk(docs, scores, k: int, device: int = 0):
     """[g, nq, k] per-shard lists -> merged [nq, k] (K7)."""
     d = np.ascontiguousarray(docs, dtype=np.int32)

@@ -79,6 +79,8 @@ SYMBOLS = {
     "jv_graph_build_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
     "jv_graph_extend": (_I32, [_I32, _P, _I64, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _P]),
     "jv_graph_extend_dev": (_I32, [_I32, _P, _I64, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _P]),
+    "jv_graph_remove_deleted": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _I32, _P, _P]),
+    "jv_graph_remove_deleted_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _I32, _P, _P]),
     "jv_segment_open": (_I32, [C.c_char_p, C.c_uint32, _P]),
     "jv_segment_close": (_I32, [_P]),
     "jv_segment_field_count": (_I32, [_P, _P]),

@@ -1375,6 +1375,99 @@ JVO_EXPORT int32_t jvo_graph_extend(const float *vectors, int64_t n, int64_t n0,
     return graph_build_impl(vectors, n, dim, sim, R, beam, overflow, alpha, max_batch, frac, n0, seed_adj, seed_entry, out_adj, &entry);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * FIXTURE: delete consolidation (GraphIndexBuilder.removeDeletedNodes behind builder.markNodeDeleted + cleanup,
+ * JVectorWriter.java:1318-1327; the algorithm is FreshDiskANN section 4.2 / Algorithm 4 [M]):
+ *   for every live node u with at least one deleted out-neighbour:
+ *     C = live out-neighbours of u, then for every deleted out-neighbour j (row order) the live out-neighbours k != u of j
+ *         (row order); the list is cut at 2048 entries
+ *     scored with the exact build score against u, sorted best first (ties -> lower ordinal), duplicates dropped,
+ *     cut at 1024, re-pruned with retainDiverse(R, alpha)
+ *   rows of deleted nodes are emptied.  Ordinals are NOT compacted here (the writer does that).
+ *   entry deleted -> the best-scoring live candidate of the same construction around the old entry, else the lowest
+ *   live ordinal (jVector picks an approximate medoid; documented deviation).
+ * ------------------------------------------------------------------------------------------ */
+static int consolidate_candidates(const float *vectors, int dim, int bsim, const int32_t *adj, int R, const uint8_t *deleted,
+                                  int32_t u, uint64_t *keys /* [JVO_APPEND_CAP] */) {
+    int32_t ids[JVO_APPEND_CAP];
+    int m = 0;
+    const int32_t *row = adj + (int64_t)u * R;
+    for (int j = 0; j < R && m < JVO_APPEND_CAP; j++)
+        if (row[j] >= 0 && !deleted[row[j]]) ids[m++] = row[j];
+    for (int j = 0; j < R; j++) {
+        if (row[j] < 0 || !deleted[row[j]]) continue;
+        const int32_t *r2 = adj + (int64_t)row[j] * R;
+        for (int t = 0; t < R && m < JVO_APPEND_CAP; t++)
+            if (r2[t] >= 0 && r2[t] != u && !deleted[r2[t]]) ids[m++] = r2[t];
+    }
+    const float *uv = vectors + (int64_t)u * dim;
+    const float unorm = canon_dot(uv, uv, dim);
+    for (int i = 0; i < m; i++) keys[i] = mk_key(exact_score(bsim, uv, unorm, vectors + (int64_t)ids[i] * dim, dim), ids[i]);
+    qsort(keys, (size_t)m, sizeof(uint64_t), cmp_u64_desc);
+    int w = 0;
+    for (int i = 0; i < m; i++)
+        if (i == 0 || keys[i] != keys[i - 1]) keys[w++] = keys[i];
+    return w < JVO_PRUNE_MAX_CANDS ? w : JVO_PRUNE_MAX_CANDS;
+}
+
+JVO_EXPORT int32_t jvo_graph_remove_deleted(const float *vectors, int64_t n, int32_t dim, int32_t sim, int32_t R, float alpha,
+                                            const int32_t *adj, const uint8_t *deleted, int32_t entry, int32_t *out_adj,
+                                            int32_t *out_entry) {
+    const int bsim = sim == JV_SIM_MIP ? JV_SIM_DOT : sim;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * JVO_APPEND_CAP);
+        int32_t *cn = (int32_t *)malloc(sizeof(int32_t) * JVO_PRUNE_MAX_CANDS);
+        float *cs = (float *)malloc(sizeof(float) * JVO_PRUNE_MAX_CANDS);
+        int32_t *tn = (int32_t *)malloc(sizeof(int32_t) * (size_t)R);
+        float *ts = (float *)malloc(sizeof(float) * (size_t)R);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 64)
+#endif
+        for (int64_t u = 0; u < n; u++) {
+            int32_t *o = out_adj + u * R;
+            const int32_t *row = adj + u * R;
+            if (deleted[u]) {
+                for (int j = 0; j < R; j++) o[j] = -1;
+                continue;
+            }
+            int hit = 0;
+            for (int j = 0; j < R; j++)
+                if (row[j] >= 0 && deleted[row[j]]) hit = 1;
+            if (!hit) {
+                for (int j = 0; j < R; j++) o[j] = row[j];
+                continue;
+            }
+            int nc = consolidate_candidates(vectors, dim, bsim, adj, R, deleted, (int32_t)u, keys);
+            for (int i = 0; i < nc; i++) {
+                cn[i] = key_node(keys[i]);
+                cs[i] = key_score(keys[i]);
+            }
+            int c = retain_diverse(vectors, dim, bsim, cn, cs, nc, R, alpha, tn, ts);
+            for (int j = 0; j < R; j++) o[j] = j < c ? tn[j] : -1;
+        }
+        free(keys);
+        free(cn);
+        free(cs);
+        free(tn);
+        free(ts);
+    }
+    int32_t e = entry;
+    if (entry >= 0 && entry < n && deleted[entry]) {
+        uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * JVO_APPEND_CAP);
+        int nc = consolidate_candidates(vectors, dim, bsim, adj, R, deleted, entry, keys);
+        e = -1;
+        if (nc > 0) e = key_node(keys[0]);
+        for (int64_t i = 0; e < 0 && i < n; i++)
+            if (!deleted[i]) e = (int32_t)i;
+        free(keys);
+    }
+    *out_entry = e;
+    return 0;
+}
+
 JVO_EXPORT int32_t jvo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

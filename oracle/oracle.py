@@ -200,6 +200,20 @@ def graph_extend(vectors, seed_adjacency, seed_entry: int, sim: int, beam_width:
     return adj
 
 
+def graph_remove_deleted(vectors, adjacency, entry: int, deleted, sim: int, alpha: float = 1.2):
+    """Fixture: delete consolidation (markNodeDeleted + cleanup, JVectorWriter.java:1318-1327; FreshDiskANN 4.2).  Same ordinal
+    space in and out: rows of deleted nodes come back empty.  Returns (adjacency[n, R], entry) — entry = -1 when nothing is live."""
+    v = _f32(vectors)
+    n, dim = v.shape
+    a = np.ascontiguousarray(adjacency, dtype=np.int32)
+    d = np.ascontiguousarray(np.asarray(deleted, dtype=bool).astype(np.uint8))
+    out = np.empty_like(a)
+    e = C.c_int32(0)
+    lib().jvo_graph_remove_deleted(_p(v), C.c_int64(n), C.c_int32(dim), C.c_int32(sim), C.c_int32(a.shape[1]), C.c_float(alpha),
+                                   _p(a), _p(d), C.c_int32(entry), _p(out), C.byref(e))
+    return out, int(e.value)
+
+
 class OracleIndex:
     """One field of one segment, as decoded arrays (what FieldEntry holds, JVectorReader.java:284-337)."""
 

@@ -81,14 +81,83 @@ def test_gpu_codec_merge_uses_leading_graph(jv, oracle):
         assert recall(res.docs, gd) >= 0.95
     finally:
         r.close()
-    # a leading segment with deleted documents: rebuilt from the live vectors (the reference's fallback)
+    # a leading segment with deleted documents: extend, then markNodeDeleted + cleanup, then compact the ordinals
     live0 = np.ones(2500, bool)
-    live0[[3, 77]] = False
+    live0[[3, 77, lead.entry_node]] = False
     m2 = w.merge(segs, live_docs=[live0, None, None])
     f2 = m2.fields["vec"]
-    assert m2.max_doc == 3998 and f2.vectors.shape[0] == 3998
     keep = np.ones(4000, bool)
-    keep[[3, 77]] = False
-    assert np.array_equal(f2.vectors, base[keep])
-    want_adj, want_entry = oracle.graph_build(base[keep], oracle.SIM_EUCLIDEAN, 16, 100)
-    assert f2.entry_node == want_entry and np.array_equal(f2.adjacency, want_adj)
+    keep[[3, 77, lead.entry_node]] = False
+    assert m2.max_doc == 3997 and np.array_equal(f2.vectors, base[keep])
+    assert np.array_equal(f2.doc_map.graph_node_ids_to_doc_ids, np.arange(3997))
+    ext = oracle.graph_extend(base, lead.adjacency, lead.entry_node, oracle.SIM_EUCLIDEAN)
+    cons, e2 = oracle.graph_remove_deleted(base, ext, lead.entry_node, ~keep, oracle.SIM_EUCLIDEAN)
+    to_final = np.full(4000, -1)
+    to_final[keep] = np.arange(3997)
+    want = np.where(cons[keep] >= 0, to_final[np.maximum(cons[keep], 0)], -1)
+    assert keep[e2] and f2.entry_node == to_final[e2] and np.array_equal(f2.adjacency, want)
+    r = jv.JVectorReader(m2)
+    try:
+        ix = r.field_index("vec")
+        res = ix.search(queries, 10, 50)
+        gd, _, _ = ix.exact_topk(queries, 10)
+        assert recall(res.docs, gd) >= 0.95
+    finally:
+        r.close()
+
+
+def _compact(adj, entry, dead):
+    live = ~dead
+    to_final = np.full(len(dead), -1)
+    to_final[live] = np.arange(int(live.sum()))
+    out = np.where(adj[live] >= 0, to_final[np.maximum(adj[live], 0)], -1).astype(np.int32)
+    order = np.argsort(out < 0, axis=1, kind="stable")
+    return np.take_along_axis(out, order, 1), int(to_final[entry])
+
+
+@pytest.mark.parametrize("frac", [0.02, 0.3])
+def test_oracle_remove_deleted_keeps_graph_searchable(oracle, frac):
+    """simpleDeletionTest / merge-with-deletes scenarios (JVectorWriterMergeTests.java:293-462): after consolidation no live row
+    points at a deleted node, deleted rows are empty, and the compacted graph keeps the recall floor."""
+    base, queries = clustered(3000, 32, 50, seed=9)
+    adj, entry = oracle.graph_build(base, oracle.SIM_EUCLIDEAN, 16, 100)
+    dead = np.random.default_rng(2).random(3000) < frac
+    dead[entry] = True                                             # the entry node goes too
+    out, e2 = oracle.graph_remove_deleted(base, adj, entry, dead, oracle.SIM_EUCLIDEAN)
+    assert (out[dead] == -1).all() and not dead[e2]
+    rows = out[~dead]
+    assert not dead[rows[rows >= 0]].any()
+    untouched = ~dead & ~np.isin(adj, np.nonzero(dead)[0]).any(1)
+    assert np.array_equal(out[untouched], adj[untouched])          # rows without a deleted neighbour are not rewritten
+    cadj, ce = _compact(out, e2, dead)
+    ix = oracle.OracleIndex(oracle.SIM_EUCLIDEAN, base[~dead], cadj, ce)
+    d, _, _, _ = ix.search(queries, 10, 50)
+    gd, _, _ = ix.exact_topk(queries, 10)
+    assert recall(d, gd) >= 0.98
+    # nothing deleted: identity; everything deleted: empty graph, entry -1
+    same, e3 = oracle.graph_remove_deleted(base, adj, entry, np.zeros(3000, bool), oracle.SIM_EUCLIDEAN)
+    assert np.array_equal(same, adj) and e3 == entry
+    none, e4 = oracle.graph_remove_deleted(base, adj, entry, np.ones(3000, bool), oracle.SIM_EUCLIDEAN)
+    assert (none == -1).all() and e4 == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sim_name,frac", [("SIM_EUCLIDEAN", 0.02), ("SIM_DOT", 0.3), ("SIM_COSINE", 0.6)])
+def test_gpu_remove_deleted_matches_oracle_bit_for_bit(jv, oracle, sim_name, frac):
+    sim = getattr(oracle, sim_name)
+    base, _ = clustered(4000, 40, 8, seed=13, normalize=sim_name != "SIM_EUCLIDEAN")
+    adj, entry = oracle.graph_build(base, sim, 16, 100)
+    dead = np.random.default_rng(4).random(4000) < frac
+    dead[entry] = True
+    want, we = oracle.graph_remove_deleted(base, adj, entry, dead, sim)
+    got, ge = jv.graph_remove_deleted(base, adj, entry, dead, sim)
+    assert ge == we and np.array_equal(got, want)
+    g0, e0 = jv.graph_remove_deleted(base, adj, entry, np.zeros(4000, bool), sim)
+    assert e0 == entry and np.array_equal(g0, adj)
+    g1, e1 = jv.graph_remove_deleted(base, adj, entry, np.ones(4000, bool), sim)
+    assert e1 == -1 and (g1 == -1).all()
+    only = np.ones(4000, bool)
+    only[[17, 3000]] = False                                       # two live nodes far from the entry
+    g2, e2 = jv.graph_remove_deleted(base, adj, entry, only, sim)
+    w2, we2 = oracle.graph_remove_deleted(base, adj, entry, only, sim)
+    assert e2 == we2 and np.array_equal(g2, w2)
