@@ -41,6 +41,17 @@ def build():
                     f"{name}_docs8": d8, f"{name}_scores8": s8})
         if g is not None:
             out[f"{name}_gcent"] = g
+    # merge path: leading graph over the first 1000 ordinals extended by the rest, then 10 % of the leading nodes (entry
+    # included) consolidated away — inputs regenerable from the seeds, outputs stored
+    for name, sim in (("l2", O.SIM_EUCLIDEAN), ("cos", O.SIM_COSINE)):
+        seed_adj, seed_entry = O.graph_build(base[:1000], sim, R, 100)
+        ext = O.graph_extend(base, seed_adj, seed_entry, sim)
+        dead = np.zeros(N, bool)
+        dead[np.random.default_rng(99).choice(1000, 100, replace=False)] = True
+        dead[seed_entry] = True
+        cons, cons_entry = O.graph_remove_deleted(base, ext, seed_entry, dead, sim)
+        out.update({f"{name}_merge_seed_entry": seed_entry, f"{name}_merge_ext": ext, f"{name}_merge_dead": dead,
+                    f"{name}_merge_cons": cons, f"{name}_merge_cons_entry": cons_entry})
     b, prm, gm = O.nvq_encode(base[:64], 2)
     out.update({"nvq_bytes": b, "nvq_params": prm, "nvq_gmean": gm, "nvq_deq": O.nvq_dequantize(b, prm, gm)})
     return out

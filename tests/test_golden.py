@@ -58,3 +58,17 @@ def test_oracle_reproduces_the_golden_outputs(gold, name, sim):
 def test_nvq_decoder_reproduces_the_golden_vectors(gold):
     deq = O.nvq_dequantize(gold["nvq_bytes"], gold["nvq_params"], gold["nvq_gmean"])
     np.testing.assert_array_equal(deq.view(np.uint32), gold["nvq_deq"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,sim", (("l2", O.SIM_EUCLIDEAN), ("cos", O.SIM_COSINE)))
+def test_oracle_reproduces_the_golden_merge(gold, name, sim):
+    """Leading-segment merge: seeded build over the first 1000 ordinals + the rest, then delete consolidation."""
+    base, _ = _inputs(gold)
+    r = int(gold["r"])
+    seed_adj, seed_entry = O.graph_build(base[:1000], sim, r, 100)
+    assert seed_entry == int(gold[f"{name}_merge_seed_entry"])
+    ext = O.graph_extend(base, seed_adj, seed_entry, sim)
+    np.testing.assert_array_equal(ext, gold[f"{name}_merge_ext"])
+    cons, e = O.graph_remove_deleted(base, ext, seed_entry, gold[f"{name}_merge_dead"], sim)
+    np.testing.assert_array_equal(cons, gold[f"{name}_merge_cons"])
+    assert e == int(gold[f"{name}_merge_cons_entry"])

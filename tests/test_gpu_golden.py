@@ -76,3 +76,17 @@ def test_device_nvq_rerank_scores_the_golden_decoded_vectors(jv, gold):
             top = np.argsort(-want, kind="stable")[:5]
             assert set(r.docs[i].tolist()) == set(top.tolist())
             np.testing.assert_allclose(r.scores[i], np.sort(want)[::-1][:5], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name,sim", (("l2", 0), ("cos", 2)))
+def test_device_reproduces_the_golden_merge(jv, gold, name, sim):
+    """Merge path against the committed file (no oracle call): leading graph over the first 1000 ordinals extended by the rest
+    (jv_graph_extend), then delete consolidation (jv_graph_remove_deleted)."""
+    base, r = gold["base"], int(gold["r"])
+    seed_adj, seed_entry = jv.graph_build(base[:1000], sim, r, 100, 1.2, 1.2)
+    assert seed_entry == int(gold[f"{name}_merge_seed_entry"])
+    ext = jv.graph_extend(base, seed_adj, seed_entry, sim, 100)
+    np.testing.assert_array_equal(ext, gold[f"{name}_merge_ext"])
+    cons, e = jv.graph_remove_deleted(base, gold[f"{name}_merge_ext"], seed_entry, gold[f"{name}_merge_dead"], sim)
+    np.testing.assert_array_equal(cons, gold[f"{name}_merge_cons"])
+    assert e == int(gold[f"{name}_merge_cons_entry"])
