@@ -269,8 +269,8 @@ class JVectorWriter:
         `segments` in order (docIds re-based like Lucene's MergeState doc maps: segment i starts after the live docs of the
         segments before it).  The first segment is the LEADING one: its graph is kept, the other segments' live vectors are
         inserted into it (tryLeadingSegmentMerge, :1166-1341 -> jv_graph_extend), its deleted nodes are consolidated away
-        (markNodeDeleted + cleanup -> jv_graph_remove_deleted) and the ordinals are compacted as the on-disk writer does.  PQ is recomputed over the merged vectors
-        when there are enough of them (mergePQ, :1095-1124; the reference refines the leading codebooks, this mirror retrains).
+        (markNodeDeleted + cleanup -> jv_graph_remove_deleted) and the ordinals are compacted as the on-disk writer does.  PQ: the
+        leading segment's codebooks are reused and all merged vectors re-encoded (mergePQ, :1072-1124), or trained when it has none.
         `live_docs[i]`: bool mask over segment i's docIds (None = all live)."""
         live_docs = list(live_docs) if live_docs is not None else [None] * len(segments)
         merged = Segment(max_doc=0)
@@ -324,7 +324,12 @@ class JVectorWriter:
                 else:
                     out.adjacency, out.entry_node = graph_build(vecs, sim_ord, self.max_conn, self.beam_width,
                                                                 self.neighbor_overflow, self.alpha, self.device)
-            if n >= self.min_batch:
+            if n > 0 and lead.pq_codes is not None:
+                # mergePQ, :1072-1124: the leading reader's codebooks are kept as they are ("We are not refining PQ codes on
+                # merge presently") and every merged vector is re-encoded with them: PQVectors.encodeAndBuild = K6
+                out.pq_m, out.pq_k, out.pq_codebooks, out.pq_global_centroid = lead.pq_m, lead.pq_k, lead.pq_codebooks, lead.pq_global_centroid
+                out.pq_codes = pq_encode(vecs, lead.pq_m, lead.pq_k, lead.pq_codebooks, lead.pq_global_centroid, self.device)
+            elif n >= self.min_batch:                                  # no codebooks yet: computePqVectors over the merged vectors
                 m = self.num_pq_subspaces(vecs.shape[1])
                 out.pq_m, out.pq_k, out.pq_codebooks, out.pq_global_centroid, out.pq_codes = \
                     JVectorIndexQuantization.compute_pq_vectors(vecs, lead.similarity, m, self.device)

@@ -34,3 +34,14 @@ for name, a, e in (("extended", adj, entry.value), ("rebuilt", full, e2.value)):
     gd, _, _ = gi.exact_topk(q, 10)
     print(f"  {name}: recall@10 {bench.recall_at_k(res.docs, gd):.4f} (exact traversal, no PQ), visited/query {res.stats[:, 0].mean():.0f}, mean degree {(a >= 0).sum(1).float().mean().item():.1f}")
     gi.close()
+# delete consolidation at scale: 10 % of the nodes deleted
+dead = torch.rand(n, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) < 0.10
+dead_u8 = dead.to(torch.uint8).contiguous()
+cons = torch.empty(n, R, dtype=torch.int32, device=dev)
+e3 = C.c_int32(0)
+t0 = time.time()
+N.check(lib.jv_graph_remove_deleted_dev(0, base.data_ptr(), n, w["dim"], w["sim"], R, 1.2, full.data_ptr(), dead_u8.data_ptr(), e2.value,
+                                        cons.data_ptr(), C.addressof(e3)))
+torch.cuda.synchronize(); t_cons = time.time() - t0
+touched = int(((cons != full).any(1) & ~dead).sum().item())
+print(f"delete consolidation: {int(dead.sum().item())} of {n} nodes deleted, {touched} live rows repaired in {t_cons:.2f}s")

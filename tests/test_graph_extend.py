@@ -73,6 +73,9 @@ def test_gpu_codec_merge_uses_leading_graph(jv, oracle):
     assert fd.entry_node == lead.entry_node                       # the leading graph was extended, not rebuilt
     assert np.array_equal(fd.adjacency, oracle.graph_extend(base, lead.adjacency, lead.entry_node, oracle.SIM_EUCLIDEAN))
     assert fd.pq_codes is not None and fd.pq_codes.shape[0] == 4000
+    assert np.array_equal(fd.pq_codebooks, lead.pq_codebooks)      # mergePQ keeps the leading codebooks and re-encodes everything
+    assert np.array_equal(fd.pq_codes, oracle.pq_encode(base, fd.pq_m, fd.pq_k, lead.pq_codebooks, lead.pq_global_centroid))
+    assert np.array_equal(fd.pq_codes[:2500], lead.pq_codes)
     r = jv.JVectorReader(merged)
     try:
         ix = r.field_index("vec")
