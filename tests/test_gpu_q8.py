@@ -245,3 +245,29 @@ def test_vectors_in_pinned_host_memory_and_wide_graphs(jv, fx_dot):
         r1 = gi.search(q, 10, 50, expand_width=1)
         w1 = wide.oracle_index(adc_order=-8).search(q, 10, 50)[0]
         assert np.mean([np.array_equal(x, y) for x, y in zip(r1.docs, w1)]) >= 0.9
+
+
+@pytest.mark.parametrize("m,sub", [(96, 2), (128, 2), (160, 2), (256, 2), (64, 4), (96, 8)])
+def test_every_table_size_instantiation(jv, m, sub):
+    """One shape per traversal instantiation that the named fixtures do not reach — NJ = ceil(M / 32) in {3, 4, 5 (generic
+    code path), 8} and the M <= 64 shape the full-size workloads use — each compiled for its own CTAs-per-SM budget
+    (q8_min_ctas): tables bit-exact, width 1 follows the oracle's order, default width keeps the recall."""
+    sim = O.SIM_DOT if m != 128 else O.SIM_EUCLIDEAN
+    base, q = clustered(2500, m * sub, 48, seed=100 + m, normalize=sim == O.SIM_DOT)
+    fx = make_fixture(sim, base, q, max_degree=16, pq_m=m)
+    ora = fx.oracle_index(adc_order=-8)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        q8, prm = gi.pq_lut_q8(q[:9])
+        w8, wprm = ora.lut_q8(q[:9])
+        np.testing.assert_array_equal(q8, w8)
+        np.testing.assert_array_equal(prm.view(np.uint32), wprm.view(np.uint32))
+        gt, _, _ = gi.exact_topk(q, 10)
+        wd = ora.search(q, 10, 50)[0]
+        r1 = gi.search(q, 10, 50, expand_width=1)
+        assert np.mean([np.array_equal(a, b) for a, b in zip(r1.docs, wd)]) >= 0.9
+        r4 = gi.search(q, 10, 50)
+        assert recall(r4.docs, gt) >= recall(wd, gt) - 0.01
+        bits = jv.make_accept_bits(np.random.default_rng(m).random(2500) < 0.5)      # FILT instantiation of the same shape
+        rf = gi.search(q, 10, 50, accept_bits=bits)
+        gf, _, _ = gi.exact_topk(q, 10, bits)
+        assert recall(rf.docs, gf) >= 0.95
