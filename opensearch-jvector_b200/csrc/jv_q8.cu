@@ -116,7 +116,7 @@ struct LutQ8Params {
 };
 
 template <int S, bool L2>
-__global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
+__global__ void __launch_bounds__(256, 2) lut_q8_kernel(const LutQ8Params p) {
     constexpr int QT = S == 2 ? 8 : 32 / S;     // queries per CTA (QT * S <= 32 query registers per thread)
     constexpr int CH = 32 / S;                 // codes per staged chunk: 128 B per subspace
     constexpr int PB = S == 2 ? 8 : 16;        // cp.async piece
@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
         for (int t = 0; t < QT / 2; t++) {
 #pragma unroll
             for (int jj = 0; jj < S; jj++) q2[t][jj] = pack2(qr[2 * t][jj], qr[2 * t + 1][jj]);
-            const float i0 = inv_s[2 * t], i1 = inv_s[2 * t + 1];
+            // lanes past the last subspace (M not a multiple of 32) get scale 0: their entries round to 0 (NaN -> 0 as well),
+            // so the padding bytes of the table need no select at the store
+            const float i0 = m < p.M ? inv_s[2 * t] : 0.f, i1 = m < p.M ? inv_s[2 * t + 1] : 0.f;
             inv2[t] = pack2(i0, i1);
             nlo2[t] = pack2(-__fmul_rn(lo_s[(2 * t) * MP + m], i0), -__fmul_rn(lo_s[(2 * t + 1) * MP + m], i1));
         }
@@ -297,13 +299,15 @@ __global__ void __launch_bounds__(256) lut_q8_kernel(const LutQ8Params p) {
                 }
                 const int c6 = ch * EP + e; // = c & 63
                 const uint32_t word = (uint32_t)((j >> 1) * 16384 + c6 * 256 + (j & 1) * 128) / 4u;
+                uint32_t *ow = obase + word; // query t of the tile: + t * tstride words (one pointer bump per store)
 #pragma unroll
                 for (int t = 0; t < QT; t++) {
                     // two cvt.pack.sat.u8.s32: bytes (q0, q1, q2, q3) = clamp(entry, 0, 255)
                     uint32_t hi, w;
                     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(qv[t][3]), "r"(qv[t][2]), "r"(0));
                     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(qv[t][1]), "r"(qv[t][0]), "r"(hi));
-                    if (full || q0 + t < p.nq) obase[(uint32_t)t * tstride + word] = m < p.M ? w : 0u;
+                    if (full || q0 + t < p.nq) *ow = w;
+                    ow += tstride;
                 }
             }
             __syncwarp(); // the buffer is refilled two iterations from now
