@@ -167,6 +167,18 @@ class KNNCounter:
     KNN_QUERY_RERANKED_COUNT = 0
     KNN_QUERY_EXPANDED_NODES = 0
     KNN_QUERY_EXPANDED_BASE_LAYER_NODES = 0
+    KNN_QUERY_GRAPH_SEARCH_TIME = 0.0   # milliseconds (:192; here the device time of the batch, added once per batch)
+    KNN_QUANTIZATION_TRAINING_TIME = 0.0  # milliseconds (JVectorIndexQuantization.java:132)
+
+    @classmethod
+    def add_search_time(cls, millis: float):
+        with cls._lock:
+            cls.KNN_QUERY_GRAPH_SEARCH_TIME += float(millis)
+
+    @classmethod
+    def add_training_time(cls, millis: float):
+        with cls._lock:
+            cls.KNN_QUANTIZATION_TRAINING_TIME += float(millis)
 
     @classmethod
     def add(cls, visited, reranked, expanded, expanded_base):
@@ -214,7 +226,10 @@ class JVectorIndexQuantization:
         if n > PQ_TRAINING_SAMPLE_LIMIT:
             rng = np.random.default_rng(seed)
             sample = vectors[np.sort(rng.choice(n, PQ_TRAINING_SAMPLE_LIMIT, replace=False))]
+        import time as _time
+        t0 = _time.perf_counter()
         codebooks, gcent = pq_train(sample, num_subspaces, clusters, center, PQ_LLOYD_ITERATIONS, seed, device)
+        KNNCounter.add_training_time((_time.perf_counter() - t0) * 1e3)                   # :132
         codes = pq_encode(vectors, num_subspaces, clusters, codebooks, gcent, device)     # :133
         return num_subspaces, clusters, codebooks, gcent, codes
 
@@ -420,6 +435,7 @@ class JVectorReader:
             return
         res = ix.search(np.asarray(targets, dtype=np.float32), k, k * c0.over_query_factor, c0.threshold, c0.rerank_floor,
                         bits)
+        KNNCounter.add_search_time(res.timing.get("total_ms", 0.0))                       # :192
         for i, col in enumerate(cols):
             for j in range(int(res.counts[i])):
                 col.collect(int(res.docs[i, j]), float(res.scores[i, j]))            # :175-177
