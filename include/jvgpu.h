@@ -179,7 +179,8 @@ JV_API int32_t jv_index_device_bytes(const jv_index *index, int64_t *out_bytes);
 /* diagnostics since index creation: which = 0 -> queries whose shared-memory visited set filled up in the strict
  * kernel (those searches stop admitting new nodes early; results stay valid but recall may drop);
  * which = 8..15 -> SM cycles the fast kernel spent per phase (setup, table build, select, neighbour rows, scoring,
- * merge, emit, steps), summed over CTAs; which = 100 resets all counters */
+ * merge, emit, steps), summed over CTAs; which = 100 resets all counters; which = 200 re-reads the JVGPU_* diagnostic
+ * environment knobs, which are otherwise read once per process */
 JV_API int32_t jv_index_debug_counter(jv_index *index, int32_t which, int64_t *out_value);
 
 /* ---- K1+K2(+K4)+K3: replaces the body of JVectorReader.search, JVectorReader.java:130-210 ----

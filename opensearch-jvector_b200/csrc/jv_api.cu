@@ -333,7 +333,12 @@ int32_t jv_index_device_bytes(const jv_index *ix, int64_t *out_bytes) {
 }
 
 int32_t jv_index_debug_counter(jv_index *ix, int32_t which, int64_t *out_value) {
-    JV_REQUIRE(ix && out_value && ((which >= 0 && which < 4) || (which >= 8 && which < 24) || which == 100), "bad arguments");
+    JV_REQUIRE(ix && out_value && ((which >= 0 && which < 4) || (which >= 8 && which < 24) || which == 100 || which == 200), "bad arguments");
+    if (which == 200) { // re-read the diagnostic environment knobs (they are cached: never a getenv on the search path)
+        q8_knobs_refresh();
+        *out_value = 0;
+        return JV_OK;
+    }
     DeviceGuard guard(ix->device);
     if (which == 100) { // reset
         JV_CUDA_TRY(cudaMemset(ix->dbg.p, 0, 256));
@@ -487,7 +492,7 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
     // Large staged batches are pipelined: a small first chunk (its copy is the only one that is exposed) and then growing
     // chunks travel on a copy stream while the kernels of the previous chunks (table build, traversal, rerank) run.  Per-query accept bitsets keep the single-shot path (their stride is relative to the batch).
     int bounds[9] = {0, nq, 0, 0, 0, 0, 0, 0, 0}, nchunks = 1;
-    if (!zero_copy && nq >= 4096 && !(p->accept_bits && p->accept_stride_words) && getenv("JVGPU_H2D_SINGLE") == nullptr) {
+    if (!zero_copy && nq >= 4096 && !(p->accept_bits && p->accept_stride_words) && !q8_knobs().h2d_single) {
         // geometric ramp: 1/8, 1/4, then the rest in parts of <= 16384 queries; consecutive chunks alternate between two
         // contexts so that a chunk's kernels start as soon as its copy has landed, overlapping the previous chunk's tail
         const int first = nq / 8, second = first + nq / 4;

@@ -62,6 +62,19 @@ struct jv_index {
 
 namespace jv {
 
+// diagnostic environment knobs, read once per process (never on the search path)
+struct Q8Knobs {
+    int occ = 0;        // JVGPU_Q8_OCC: cap the CTAs per SM
+    int chunk = 0;      // JVGPU_Q8_CHUNK: table staging buffer of n queries
+    int warps = 0;      // JVGPU_Q8_WARPS: warps per CTA (4 or 8)
+    bool prof = false;  // JVGPU_PROFILE: per-phase cycle counters (synchronous kernel)
+    bool fused = false; // JVGPU_Q8_FUSED: K3 as the epilogue of the synchronous kernel
+    bool pipe = false;  // JVGPU_Q8_PIPE: experimental token-passing pipelined kernel (jv_q8_pipe.cu) instead of the round-synchronous one
+    bool h2d_single = false; // JVGPU_H2D_SINGLE: no chunked H2D pipeline in jv_search_batch
+};
+const Q8Knobs &q8_knobs();   // the environment is read once per process ...
+void q8_knobs_refresh();     // ... and again on jv_index_debug_counter(which = 200) (tests and sweeps change the knobs)
+
 // ---- kernel launchers (each returns a jv_status; all work is enqueued on `stream`) ----
 
 // K1+K2 / K4: graph traversal with ADC (PQ) or exact scoring; writes the approximate result list.

@@ -22,45 +22,33 @@
 // cw >> 6, byte 1 from cw) + one LOP3 ((v & 0x3F03) | lane base) per lookup.  Code rows are stored permuted (codes_q8):
 // lane sl of a row group owns subspaces m = 8t + sl, its 4*NJ bytes contiguous, so at lookup t the 8 lanes of a group hit
 // 8 different banks and the 4 groups of a warp are rotated onto the 4 different bank quarters.
-#include <stdlib.h>
-
 #include <type_traits>
 
+#include "jv_q8.cuh"
 #include "jv_rerank_body.cuh"
-#include "jv_search_common.cuh"
 
 namespace jv {
 
-// ---------------------------------------------------------------------------------------------------------------
-// small PTX wrappers
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+static Q8Knobs g_knobs;
+static std::once_flag g_knobs_once;
+
+void q8_knobs_refresh() {
+    Q8Knobs v;
+    if (const char *e = getenv("JVGPU_Q8_OCC")) v.occ = atoi(e);
+    if (const char *e = getenv("JVGPU_Q8_CHUNK")) v.chunk = atoi(e);
+    if (const char *e = getenv("JVGPU_Q8_WARPS")) v.warps = atoi(e);
+    v.prof = getenv("JVGPU_PROFILE") != nullptr;
+    v.fused = getenv("JVGPU_Q8_FUSED") != nullptr;
+    v.pipe = getenv("JVGPU_Q8_PIPE") != nullptr;
+    v.h2d_single = getenv("JVGPU_H2D_SINGLE") != nullptr;
+    g_knobs = v;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+
+const Q8Knobs &q8_knobs() {
+    std::call_once(g_knobs_once, q8_knobs_refresh);
+    return g_knobs;
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-template <int BYTES> __device__ __forceinline__ void cp_async(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // packed fp32 pairs (FFMA2 on sm_100a): two IEEE fmas per instruction, each lane rounded exactly like a scalar fmaf
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
     uint64_t r;
@@ -90,7 +78,7 @@ __global__ void permute_codes_kernel(const uint8_t *__restrict__ codes, int64_t 
         const int o = (int)(i - row * MP);
         const int sl = o / seg, t = o - sl * seg;
         const int m = 8 * t + sl;
-        out[i] = m < M ? codes[row * stride + m] : (uint8_t)0;
+        out[row * MP + q8_word_offset(NJ, sl, t >> 2) + (t & 3)] = m < M ? codes[row * stride + m] : (uint8_t)0;
     }
 }
 
@@ -364,67 +352,6 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
 // ---------------------------------------------------------------------------------------------------------------
 // K2: traversal
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kQMaxE = 8;          // candidates per step (warp w expands candidates w, w + W, ..)
-
-struct Q8Params {
-    const int32_t *adjacency;
-    const uint8_t *codes_q8;
-    const float *node_norm;
-    const uint8_t *lut;      // [nq][lutb]
-    const float4 *qparams;   // [nq]
-    uint64_t *approx_keys;   // [nq][L]
-    int32_t *approx_count;
-    jv_query_stats *stats;
-    int *work_counter;
-    int *dbg;
-    int64_t n;
-    int nq, L, R, entry, sim, NJ, lutb, hash_log2, E, surv_cap;
-    // filtered queries (FILT instantiation): accept bits by Lucene docId (JVectorReader.java:157-163); Lc = list capacity
-    int Lc;
-    const uint64_t *accept;
-    int64_t accept_stride;
-    // fused K3 (exact rerank + top-k as the epilogue of every query; fuse_k = 0: write approx_keys for a separate rerank kernel)
-    int fuse_k, dim;
-    float rerank_floor;
-    const float *queries, *vectors, *vec_norm;
-    const int32_t *ord_to_doc;
-    int32_t *out_doc, *out_count;
-    float *out_score;
-};
-
-// list key: order word (32 bits) | (0x7fffffff - node) << 1 | unexpanded.  The order word is the integer ADC sum itself
-// for DOT/MIP (larger = better), its complement for EUCLIDEAN, and the ordered-float score for COSINE (the cosine
-// decoder divides by the node norm, so its order is not the order of the sums).
-__device__ __forceinline__ uint64_t qkey_pack(uint32_t ord, int32_t node) {
-    return ((uint64_t)ord << 32) | ((uint64_t)(uint32_t)(0x7fffffff - node) << 1) | 1ull;
-}
-__device__ __forceinline__ int32_t qkey_node(uint64_t k) { return 0x7fffffff - (int32_t)((k >> 1) & 0x7fffffffu); }
-// filtered flavour: 30-bit node field, bit 1 = "accepted by the filter" (the lowest bit of the comparable part key >> 1; it
-// never decides an order because (order word, node) is already unique), bit 0 = unexpanded
-__device__ __forceinline__ uint64_t qkey_pack_f(uint32_t ord, int32_t node, bool acc) {
-    return ((uint64_t)ord << 32) | ((uint64_t)(uint32_t)(0x3fffffff - node) << 2) | (acc ? 2ull : 0ull) | 1ull;
-}
-__device__ __forceinline__ int32_t qkey_node_f(uint64_t k) { return 0x3fffffff - (int32_t)((k >> 2) & 0x3fffffffu); }
-
-// visited filter: true when `nb` was NOT present (and records it).  2 tags of 15 bits + valid bit per word; (set, tag) is
-// a bijection of the ordinal when n <= 2^(set_bits+15), so there are no false positives; evictions only cause re-scoring.
-__device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, bool tagged, int32_t nb) {
-    if (tagged) {
-        const uint32_t x = ((uint32_t)nb * 0x9E3779B1u) & ((1u << (set_bits + 15)) - 1u);
-        const uint32_t set = x >> 15, tag = (x & 0x7fffu) | 0x8000u;
-        uint32_t old = filter[set];
-        for (;;) {
-            if ((old & 0xffffu) == tag || (old >> 16) == tag) return false;
-            const uint32_t seen = atomicCAS(&filter[set], old, (old << 16) | tag);
-            if (seen == old) return true;
-            old = seen;
-        }
-    } else {
-        const uint32_t h = ((uint32_t)nb * 2654435761u) >> (32 - set_bits);
-        return atomicExch(&filter[h], (uint32_t)nb) != (uint32_t)nb;
-    }
-}
-
 // NJ_T > 0: code words per lane known at compile time (registers, all loads of U rows in flight before the first lookup).
 // W = warps per CTA (4 row groups each); PROF = per-phase cycle counters (jv_index_debug_counter).
 // FILT = accept bits given: the list also holds rejected nodes (they are traversed, never returned), up to Lc entries; only
@@ -482,7 +409,6 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
         sel[i] = 0x4400u | (qd << 4) | (4u + qd); // byte 0 <- (cw >> 6).byte[qd], byte 1 <- cw.byte[qd]
         lb[i] = qd * 32u + (uint32_t)sl * 4u;
     }
-    const int seg = NJ * 4; // bytes of a code row owned by one lane
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -511,8 +437,8 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
     auto row_sum = [&](int32_t nb) -> uint32_t { // one row per group, loads interleaved with lookups (entry node, generic NJ)
         uint32_t s = 0;
         if (nb >= 0) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(p.codes_q8 + (int64_t)nb * (NJ * 32) + sl * seg);
-            for (int j = 0; j < NJ; j++) s += lookup4(__ldg(row + j), j);
+            const unsigned char *row = p.codes_q8 + (int64_t)nb * (NJ * 32);
+            for (int j = 0; j < NJ; j++) s += lookup4(__ldg(reinterpret_cast<const uint32_t *>(row + q8_word_offset(NJ, sl, j))), j);
         }
         return reduce8(s);
     };
@@ -688,15 +614,7 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                             nbv[u] = idx < nn ? pool[idx] : -1;
                             s[u] = 0u;
                             if (nbv[u] >= 0) {
-                                const unsigned char *row = p.codes_q8 + (int64_t)nbv[u] * (NJ * 32) + sl * seg;
-                                if (NJC % 2 == 0) { // 8-byte aligned lane segments
-#pragma unroll
-                                    for (int j = 0; j < NJC / 2; j++)
-                                        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(cw[u][2 * j]), "=r"(cw[u][2 * j + 1]) : "l"(row + 8 * j));
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < NJC; j++) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cw[u][j]) : "l"(row + 4 * j));
-                                }
+                                q8_load_row<NJC>(p.codes_q8 + (int64_t)nbv[u] * (NJ * 32), sl, cw[u]); // 16-byte vector loads
                             } else {
 #pragma unroll
                                 for (int j = 0; j < NJC; j++) cw[u][j] = 0u;
@@ -981,10 +899,7 @@ static int32_t launch_q8_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p) {
         set_error("search (8-bit table): kernel does not fit on an SM (smem %zu)", smem);
         return JV_ERR_UNSUPPORTED;
     }
-    if (const char *e = getenv("JVGPU_Q8_OCC")) { // diagnostics: cap the CTAs per SM
-        const int v = atoi(e);
-        if (v >= 1 && v < occ) occ = v;
-    }
+    if (q8_knobs().occ >= 1 && q8_knobs().occ < occ) occ = q8_knobs().occ; // diagnostics: cap the CTAs per SM
     int grid = ix->sm_count * occ;
     if (grid > p.nq) grid = p.nq;
     JV_CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(int), ctx->stream));
@@ -1009,10 +924,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
     const int lutb = q8_lut_bytes(ix->q8_nj);
     // staging buffer: <= 512 MB of tables per chunk (10 922 queries at M = 192)
     int chunk = (int)((size_t)512 * 1024 * 1024 / (size_t)lutb);
-    if (const char *e = getenv("JVGPU_Q8_CHUNK")) { // test knob: force small chunks
-        const int v = atoi(e);
-        if (v > 0 && v < chunk) chunk = v;
-    }
+    if (q8_knobs().chunk > 0 && q8_knobs().chunk < chunk) chunk = q8_knobs().chunk; // test knob: force small chunks
     if (chunk > a.nq) chunk = a.nq;
     if (chunk < 1) chunk = 1;
     JV_TRY(ctx->lut8.ensure((size_t)chunk * lutb));
@@ -1062,7 +974,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         // separate rerank kernel — a 4-warp CTA gathers its 50 rows one DRAM round trip after the other while it holds
         // 1/4 of an SM; the stand-alone K3 keeps 16 CTAs per SM in flight (0.31 ms, 0.76 of the HBM roofline) — so off by default.
         const bool fuse = a.fuse_k > 0 && !ix->vectors_on_host && !ix->has_nvq && (size_t)ix->dim * 4 + 16 + (size_t)a.rerank_k * 8 <= (size_t)lutb &&
-                          ix->q8_nj == 6 && !filt && getenv("JVGPU_Q8_FUSED") != nullptr; // instantiated for the headline shape only
+                          ix->q8_nj == 6 && !filt && q8_knobs().fused; // instantiated for the headline shape only
         if (fuse) {
             p.fuse_k = a.fuse_k;
             p.rerank_floor = a.rerank_floor;
@@ -1077,8 +989,15 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         if (reranked) *reranked = fuse;
         p.surv_cap = E * ((ix->R + 31) / 32) * 32;
         int32_t st;
-        const bool prof = getenv("JVGPU_PROFILE") != nullptr; // per-phase cycle counters (costs registers): diagnostics only
-        const int warps = getenv("JVGPU_Q8_WARPS") ? atoi(getenv("JVGPU_Q8_WARPS")) : 4;
+        const bool prof = q8_knobs().prof; // per-phase cycle counters (costs registers): diagnostics only
+        const int warps = q8_knobs().warps ? q8_knobs().warps : 4;
+        // experimental (JVGPU_Q8_PIPE=1): the token-passing pipelined kernel of jv_q8_pipe.cu.  Measured at cfg2: 1.75 ms against
+        // 1.55 ms for the round-synchronous kernel below, so it is not the default.
+        if (q8_knobs().pipe && !filt && !fuse && q8_pipe_supported(ix, a.rerank_k, ix->R)) {
+            JV_TRY(launch_q8_pipe(ix, ctx, p, warps));
+            if (launches) *launches += 2;
+            continue;
+        }
         // the diagnostic instantiations (8 warps, phase counters) exist for the headline shape (M = 192) only
 #define JV_Q8_CASE(NJV)                                                                         \
     case NJV:                                                                                   \

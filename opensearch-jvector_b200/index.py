@@ -208,6 +208,11 @@ class GpuIndex:
         N.check(N.load().jv_index_debug_counter(self.handle, 0, C.addressof(b)))
         return int(b.value)
 
+    def refresh_knobs(self):
+        """Re-read the JVGPU_* diagnostic environment knobs (they are cached by the library)."""
+        b = C.c_int64(0)
+        N.check(N.load().jv_index_debug_counter(self.handle, 200, C.addressof(b)))
+
     PHASES = ("setup", "table_build", "select", "neighbour_rows", "scoring", "merge", "emit", "steps",
               "sub_code_words", "sub_lookups", "sub_offers", "sub_spare")
 

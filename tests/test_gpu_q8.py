@@ -110,8 +110,10 @@ def test_large_rerank_k_and_chunked_batches(jv, fx_l2, monkeypatch):
         assert (r.counts == 100).all()
         a = gi.search(fx.queries, 10, 50)
         monkeypatch.setenv("JVGPU_Q8_CHUNK", "7")  # table staging buffer of 7 queries: 10 chunks for 64 queries
+        gi.refresh_knobs()
         b = gi.search(fx.queries, 10, 50)
         monkeypatch.delenv("JVGPU_Q8_CHUNK")
+        gi.refresh_knobs()
         np.testing.assert_array_equal(a.docs, b.docs)
         np.testing.assert_array_equal(a.scores, b.scores)
         np.testing.assert_array_equal(a.stats[:, 1:], b.stats[:, 1:])
