@@ -222,6 +222,160 @@ def algorithmic_bytes(stats, m, R, dim):
     return int((visited * per_node + expanded * 4 * (1 + R)).sum()), int((reranked * dim * 4).sum())
 
 
+def cpu_arm(host, w, k, rk, nq, budget_s, steps, warmup, truth=None):
+    """The reference's CPU path on this box's host cores: the tuned SIMD restatement (oracle/jv_cpu_simd.c; AVX-512 / AVX2 picked at
+    run time), one query per thread like JVectorReader.search, on ALL the cores this process may use — torchrun exports
+    OMP_NUM_THREADS=1, which must not cripple a baseline.  Each step is a bounded sample of the workload (~budget_s of CPU work)."""
+    from oracle import oracle as O
+    m = w["pq_m"]
+    ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256 if m else 0, pq_codebooks=host["cb"],
+                        pq_global_centroid=host.get("gcent"), pq_codes=host["codes"])
+    fast = O.SimdIndex(ora)
+    cores = O.host_cores()
+    q = host["queries"]
+    t0 = time.time()
+    fast.search(q[:256], k, rk, threads=cores)
+    per_q = (time.time() - t0) / 256
+    sample = int(min(nq, max(256, budget_s / per_q)))
+    for _ in range(warmup):
+        fast.search(q[:sample], k, rk, threads=cores)
+    t0 = time.time()
+    for _ in range(steps):
+        cd, _, _, cst = fast.search(q[:sample], k, rk, threads=cores)
+    el = time.time() - t0
+    one = min(64, sample)  # single-thread latency next to the README's JMH avgt rows (/root/reference/README.md:90-98)
+    t0 = time.time()
+    fast.search(q[:one], k, rk, threads=1)
+    one_ms = (time.time() - t0) / one * 1e3
+    chk = min(sample, max(256, int(0.1 * sample)))  # the bit-exact checker on the same cores, for scale
+    t0 = time.time()
+    ora.search(q[:chk], k, rk, threads=cores)
+    chk_qps = chk / (time.time() - t0)
+    out = {"value": sample * steps / el, "unit": "queries/s", "cores": cores, "kind": "port", "ms_per_step": el / steps * 1e3,
+           "sample": f"{sample} of the {nq} queries per step, one query per OpenMP thread, same index; tuned CPU restatement of jVector "
+                     f"4.0.0-rc.9 ({fast.isa} gathers + FMAs, free summation order) — not the JVM",
+           "cpu_model": O.cpu_model(), "isa": fast.isa, "one_thread_ms_per_query": one_ms, "checker_value": chk_qps,
+           "visited_per_query": float(cst[:, 0].mean())}
+    if truth is not None:
+        out["recall_at_10"] = recall_at_k(cd, truth[:sample])
+    return out
+
+
+def shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="cfg3-10Mx96-l2-pq48"):
+    """BASELINE.json configs[2]: the index partitioned across the ranks (disjoint doc ranges, one Vamana graph + codes per rank), the
+    query batch broadcast, every rank searches its shard, per-rank top-k lists all-gathered over NCCL/NVLink and merged on the device
+    (K7).  The exchange + merge of batch i runs on a side stream while the search of batch i+1 runs (double-buffered results)."""
+    N = jv.native
+    lib = N.load()
+    w = dict(WORKLOADS[workload])
+    k, rk, nq, dim, m, R = w["k"], w["k"] * w["over"], w["nq"], w["dim"], w["pq_m"], w["R"]
+    n_local = w["n"] // world
+    dev_t = torch.device("cuda", local_rank)
+    host, dq = build_fixture(torch, jv, w, local_rank, 4321 + rank * 17, n_local, log)
+    if world > 1:
+        dist.broadcast(dq, src=0)
+    torch.cuda.synchronize(local_rank)  # the library searches on its own stream: the broadcast must have landed
+    gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
+                     pq_global_centroid=host.get("gcent"), pq_codes=host["codes"], device=local_rank, flags=N.FLAG_LUT_U8)
+    base_doc = rank * n_local
+    i32, f32 = torch.int32, torch.float32
+    od = [torch.empty(nq, k, dtype=i32, device=dev_t) for _ in range(2)]
+    os_ = [torch.empty(nq, k, dtype=f32, device=dev_t) for _ in range(2)]
+    oc = torch.empty(nq, dtype=i32, device=dev_t)
+    st = torch.empty(nq, 4, dtype=i32, device=dev_t)
+    gd = [torch.empty(world, nq, k, dtype=i32, device=dev_t) for _ in range(2)]
+    gs = [torch.empty(world, nq, k, dtype=f32, device=dev_t) for _ in range(2)]
+    md = [torch.empty(nq, k, dtype=i32, device=dev_t) for _ in range(2)]
+    ms = [torch.empty(nq, k, dtype=f32, device=dev_t) for _ in range(2)]
+    mc = torch.empty(nq, dtype=i32, device=dev_t)
+    side = torch.cuda.Stream(device=dev_t)
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def exchange(b, docs, scores):  # enqueued on `side`: global docIds -> all-gather -> K7
+        if world == 1:
+            md[b].copy_(docs)
+            ms[b].copy_(scores)
+            return
+        dist.all_gather_into_tensor(gd[b].view(world * nq, k), torch.where(docs >= 0, docs + base_doc, docs))
+        dist.all_gather_into_tensor(gs[b].view(world * nq, k), scores)
+        N.check(lib.jv_merge_topk_stream(local_rank, world, nq, k, gd[b].data_ptr(), gs[b].data_ptr(), md[b].data_ptr(), ms[b].data_ptr(),
+                                         mc.data_ptr(), side.cuda_stream))
+
+    def barrier():
+        torch.cuda.synchronize(local_rank)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(local_rank)
+
+    # merged exact ground truth
+    gtd = torch.empty(nq, k, dtype=i32, device=dev_t)
+    gts = torch.empty(nq, k, dtype=f32, device=dev_t)
+    gi.exact_topk_dev(dq.data_ptr(), nq, k, gtd.data_ptr(), gts.data_ptr(), oc.data_ptr())
+    with torch.cuda.stream(side):
+        exchange(0, gtd, gts)
+    barrier()
+    truth = md[0].cpu().numpy().copy()
+
+    def run(steps, overlap):
+        timings = []
+        for i in range(steps):
+            b = i & 1
+            done[b].synchronize()  # the exchange that last read these result buffers has finished
+            timings.append(gi.search_dev(dq.data_ptr(), nq, k, rk, od[b].data_ptr(), os_[b].data_ptr(), oc.data_ptr(), st.data_ptr()))
+            with torch.cuda.stream(side):  # search_dev returns when the shard's results are complete
+                exchange(b, od[b], os_[b])
+                done[b].record(side)
+            if not overlap:
+                side.synchronize()
+        return timings
+
+    run(max(args.warmup, 3), True)
+    barrier()
+    out = {}
+    for name, overlap in (("serial", False), ("overlapped", True)):
+        t0 = time.perf_counter()
+        timings = run(args.steps, overlap)
+        barrier()
+        out[name] = (time.perf_counter() - t0, timings)
+    # gather + merge alone, CUDA events on the side stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(side):
+        e0.record(side)
+        for _ in range(10):
+            exchange(0, od[0], os_[0])
+        e1.record(side)
+    barrier()
+    xchg_ms = e0.elapsed_time(e1) / 10
+    found = md[(args.steps - 1) & 1].cpu().numpy()
+    rec = recall_at_k(found, truth)
+    tt = torch.tensor([out["serial"][0], out["overlapped"][0], xchg_ms, -rec], dtype=torch.float64, device=dev_t)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_serial, t_over, xchg_ms, neg_rec = tt.tolist()
+    tm = out["overlapped"][1]
+    search_ms = sum(t["search_ms"] for t in tm) / len(tm)
+    lut_ms = sum(t.get("lut_ms", 0.0) for t in tm) / len(tm)
+    rerank_ms = sum(t["rerank_ms"] for t in tm) / len(tm)
+    s = st.cpu().numpy()
+    adc_bytes, rr_bytes = algorithmic_bytes(s, m, R, dim)
+    peak, _ = measured_peak()
+    res = {"workload": workload, "layout": "shards", "n_total": w["n"], "n_per_gpu": n_local, "query_batch": nq, "k": k, "rerank_k": rk,
+           "value": nq * args.steps / t_over, "unit": "queries/s", "ms_per_step": t_over / args.steps * 1e3,
+           "value_serial": nq * args.steps / t_serial, "ms_per_step_serial": t_serial / args.steps * 1e3,
+           "gather_merge_ms": xchg_ms if world > 1 else 0.0, "recall_at_10": -neg_rec, "scaling": "strong",
+           "collective": (f"2 x ncclAllGather of [nq, k] x 4 B per rank ({2 * nq * k * 4} B sent, {2 * world * nq * k * 4} B received per GPU and "
+                          "batch) + K7 merge on a side stream, overlapped with the next batch's search") if world > 1 else "none (one shard)",
+           "per_shard": {"k1_k2_ms": search_ms, "k2_ms": search_ms - lut_ms, "rerank_ms": rerank_ms, "visited_per_query": float(s[:, 0].mean()),
+                         "roofline_frac_k2": adc_bytes / ((search_ms - lut_ms) * 1e-3) / 1e9 / peak,
+                         "index_gib": gi.device_bytes() / 2**30},
+           "limit": "every query visits every shard and a best-first search of a graph N times smaller visits as many nodes, so shards add "
+                    "capacity (an index N times larger at the same QPS), not throughput; the exchange is latency-bound and hidden"}
+    gi.close()
+    del host
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -294,29 +448,15 @@ def main():
 
     # ------------------------------------------------------------------------------------------ CPU arm
     if args.impl == "reference":
-        from oracle import oracle as O
-        ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256 if m else 0, pq_codebooks=host["cb"],
-                            pq_global_centroid=host.get("gcent"), pq_codes=host["codes"])
-        cores = O.num_threads()
-        t0 = time.time()
-        ora.search(host["queries"][:256], k, rk)
-        per_q = (time.time() - t0) / 256
-        sample = int(min(nq, max(256, 1.5 / per_q)))  # ~1.5 s of CPU work per step
-        for _ in range(args.warmup):
-            ora.search(host["queries"][:sample], k, rk)
-        t0 = time.time()
-        for _ in range(args.steps):
-            docs, _, _, _ = ora.search(host["queries"][:sample], k, rk)
-        el = time.time() - t0
-        qps = sample * args.steps / el
-        line = {"impl": "reference", "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        base = cpu_arm(host, w, k, rk, nq, budget_s=1.5, steps=args.steps, warmup=args.warmup)
+        line = {"impl": "reference", "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "n": n_local, "dim": dim, "similarity": SIM_NAMES[w["sim"]], "pq": f"{m}x256" if m else "none", "k": k,
                            "rerank_k": rk, "graph": f"Vamana R={R} beamWidth=100 (fixture built on the GPU, shared with our arm)"},
-                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                                 "sample": f"{sample} queries per step, OpenMP one query per thread (CPU restatement of jVector 4.0.0-rc.9, not the JVM)"},
-                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "cpu_baseline": {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample", "cpu_model", "isa", "one_thread_ms_per_query",
+                                                         "checker_value")},
+                "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -520,23 +660,14 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
-    # CPU baseline on rank 0, N=1 only: the oracle port on a bounded sample of the same workload
+    # CPU baseline on rank 0, N=1 only: the tuned CPU arm (oracle/jv_cpu_simd.c) on a bounded sample of the same workload
     if rank == 0 and world == 1:
-        from oracle import oracle as O
-        ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256 if m else 0, pq_codebooks=host["cb"],
-                            pq_global_centroid=host.get("gcent"), pq_codes=host["codes"])
-        cores = O.num_threads()
-        t0 = time.time()
-        ora.search(host["queries"][:256], k, rk)
-        per_q = (time.time() - t0) / 256
-        sample = int(min(nq, max(512, 12.0 / per_q)))
-        t0 = time.time()
-        cd, _, _, cst = ora.search(host["queries"][:sample], k, rk)
-        el = time.time() - t0
-        line["cpu_baseline"] = {"value": sample / el, "unit": "queries/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} of the {nq} queries, one query per OpenMP thread, same index (CPU restatement, not the JVM)",
-                                "recall_at_10": recall_at_k(cd, truth[:sample]),
-                                "visited_per_query": float(cst[:, 0].mean())}
+        base = cpu_arm(host, w, k, rk, nq, budget_s=12.0, steps=1, warmup=0, truth=truth)
+        line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample", "cpu_model", "isa", "one_thread_ms_per_query",
+                                                        "checker_value", "recall_at_10", "visited_per_query")}
+        if base.get("visited_per_query"):  # the same kernel time charged only the reference loop's visits (the GPU's wide step visits more)
+            ref_bytes = adc_bytes * base["visited_per_query"] / max(float(st[:, 0].mean()), 1.0)
+            line["roofline"]["frac_on_reference_visits"] = ref_bytes / (k2_ms * 1e-3) / 1e9 / peak
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -172,6 +172,20 @@ JV_API int32_t jv_version(void);                 /* (major << 16) | minor */
 JV_API const char *jv_last_error(void);          /* thread-local, never NULL */
 JV_API int32_t jv_device_count(int32_t *out_count);
 
+/* ---- page-locked host buffers ---------------------------------------------------------------------------------------
+ * jv_search_batch / jv_exact_topk / jv_pq_encode take HOST pointers (what JVectorReader.search has in hand, JVectorReader.java:147:
+ * the query float[] and the collector's result arrays).  Copies from pageable memory are staged by the driver and cannot overlap the
+ * kernels; from page-locked memory they are asynchronous DMA and the chunked H2D pipeline of jv_search_batch overlaps them with the
+ * traversal.  A Panama caller gets page-locked memory in one of two ways (INTEGRATION.md "Host buffers"):
+ *   jv_host_alloc      cudaHostAlloc'ed buffer (portable across devices); wrap it with MemorySegment.reinterpret(bytes)
+ *   jv_host_register   page-lock memory the JVM already owns (an Arena-allocated off-heap segment); the range must stay
+ *                      allocated until jv_host_unregister.  Never register Java heap arrays (the GC moves them).
+ * Both are optional: every entry point also accepts pageable pointers. */
+JV_API int32_t jv_host_alloc(int64_t bytes, void **out_ptr);
+JV_API int32_t jv_host_free(void *ptr);
+JV_API int32_t jv_host_register(void *ptr, int64_t bytes);
+JV_API int32_t jv_host_unregister(void *ptr);
+
 /* ---- index lifetime: FieldEntry ctor / close, JVectorReader.java:284-337, 367-378 ---- */
 JV_API int32_t jv_index_create(const jv_index_desc *desc, jv_index **out_index);
 JV_API int32_t jv_index_destroy(jv_index *index);
@@ -225,6 +239,10 @@ JV_API int32_t jv_pq_adc_scores(jv_index *index, const float *queries, int32_t n
  * [g][nq][k] with doc=-1 padding; docs must already be global ids.  Ties -> lower doc. */
 JV_API int32_t jv_merge_topk(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *docs, const float *scores,
                       int32_t *out_doc, float *out_score, int32_t *out_count);
+/* jv_merge_topk_stream: the same merge enqueued on the caller's CUDA stream (cudaStream_t passed as void*, NULL = the legacy
+ * default stream) without a host synchronisation, so that the exchange + merge of one batch overlaps the search of the next. */
+JV_API int32_t jv_merge_topk_stream(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *d_docs, const float *d_scores,
+                             int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, void *cuda_stream);
 JV_API int32_t jv_merge_topk_dev(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *d_docs, const float *d_scores,
                           int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, float *out_kernel_ms);
 

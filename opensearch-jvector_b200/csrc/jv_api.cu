@@ -139,6 +139,32 @@ int32_t jv_device_count(int32_t *out_count) {
     return JV_OK;
 }
 
+// page-locked host buffers for the callers of the host-pointer entry points (the FFM shim, JVectorReader.java:147)
+int32_t jv_host_alloc(int64_t bytes, void **out_ptr) {
+    JV_REQUIRE(out_ptr != nullptr && bytes > 0, "bad arguments");
+    *out_ptr = nullptr;
+    JV_CUDA_TRY(cudaHostAlloc(out_ptr, (size_t)bytes, cudaHostAllocPortable));
+    return JV_OK;
+}
+
+int32_t jv_host_free(void *ptr) {
+    if (ptr == nullptr) return JV_OK;
+    JV_CUDA_TRY(cudaFreeHost(ptr));
+    return JV_OK;
+}
+
+int32_t jv_host_register(void *ptr, int64_t bytes) {
+    JV_REQUIRE(ptr != nullptr && bytes > 0, "bad arguments");
+    JV_CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return JV_OK;
+}
+
+int32_t jv_host_unregister(void *ptr) {
+    JV_REQUIRE(ptr != nullptr, "bad arguments");
+    JV_CUDA_TRY(cudaHostUnregister(ptr));
+    return JV_OK;
+}
+
 int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
     JV_REQUIRE(desc != nullptr && out != nullptr, "desc/out is NULL");
     *out = nullptr;
@@ -751,6 +777,16 @@ int32_t jv_pq_adc_scores(jv_index *ix, const float *queries, int32_t nq, const i
 // -------------------------------------------------------------------------------------------------
 // merge
 // -------------------------------------------------------------------------------------------------
+int32_t jv_merge_topk_stream(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *d_docs, const float *d_scores,
+                             int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, void *cuda_stream) {
+    JV_REQUIRE(g >= 1 && nq >= 0 && k >= 1, "bad arguments");
+    if (nq == 0) return JV_OK;
+    JV_REQUIRE(d_docs && d_scores && d_out_doc && d_out_score, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    return launch_merge_topk(static_cast<cudaStream_t>(cuda_stream), g, nq, k, d_docs, d_scores, d_out_doc, d_out_score, d_out_count);
+}
+
 int32_t jv_merge_topk_dev(int32_t device, int32_t g, int32_t nq, int32_t k, const int32_t *d_docs, const float *d_scores,
                           int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count, float *out_kernel_ms) {
     JV_REQUIRE(g >= 1 && nq >= 0 && k >= 1, "bad arguments");

@@ -58,6 +58,10 @@ SYMBOLS = {
     "jv_version": (_I32, []),
     "jv_last_error": (C.c_char_p, []),
     "jv_device_count": (_I32, [_P]),
+    "jv_host_alloc": (_I32, [_I64, _P]),
+    "jv_host_free": (_I32, [_P]),
+    "jv_host_register": (_I32, [_P, _I64]),
+    "jv_host_unregister": (_I32, [_P]),
     "jv_index_create": (_I32, [_P, _P]),
     "jv_index_destroy": (_I32, [_P]),
     "jv_index_device_bytes": (_I32, [_P, _P]),
@@ -73,6 +77,7 @@ SYMBOLS = {
     "jv_pq_adc_scores": (_I32, [_P, _P, _I32, _P, _I32, _P]),
     "jv_merge_topk": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "jv_merge_topk_dev": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "jv_merge_topk_stream": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "jv_pq_train": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
     "jv_pq_train_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
     "jv_graph_build": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
@@ -118,6 +123,22 @@ def load() -> C.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def host_alloc(shape, dtype):
+    """numpy array over a page-locked buffer from jv_host_alloc (freed with host_free(arr))."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    check(load().jv_host_alloc(max(n * dt.itemsize, 1), C.byref(p)))
+    buf = (C.c_byte * max(n * dt.itemsize, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    return arr, p.value
+
+
+def host_free(ptr: int) -> None:
+    check(load().jv_host_free(C.c_void_p(ptr)))
 
 
 def check(status: int) -> None:

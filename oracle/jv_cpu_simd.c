@@ -254,6 +254,7 @@ typedef struct {
 typedef struct jvs_index {
     jv_index_desc d;
     int sub; /* uniform sub-vector size (dim / M) */
+    float *cbT;       /* codebooks transposed per subspace: [M][sub][256], so the table build vectorises over the centroids */
     float *node_norm; /* cosine: ||decode(code)||^2 per node */
     float *vec_norm;  /* cosine: ||x||^2 per node */
 } jvs_index;
@@ -266,6 +267,12 @@ JVS_EXPORT jvs_index *jvs_create(const jv_index_desc *desc) {
     ix->sub = desc->pq_m > 0 ? desc->dim / desc->pq_m : 0;
     const int64_t n = desc->n;
     const int dim = desc->dim, M = desc->pq_m;
+    if (M > 0) {
+        ix->cbT = (float *)aligned_alloc(64, sizeof(float) * (size_t)M * ix->sub * 256);
+        for (int m = 0; m < M; m++)
+            for (int c = 0; c < 256; c++)
+                for (int j = 0; j < ix->sub; j++) ix->cbT[((size_t)m * ix->sub + j) * 256 + c] = desc->pq_codebooks[((size_t)m * 256 + c) * ix->sub + j];
+    }
     if (desc->similarity == JV_SIM_COSINE) {
         ix->vec_norm = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
 #pragma omp parallel for schedule(static)
@@ -290,6 +297,7 @@ JVS_EXPORT jvs_index *jvs_create(const jv_index_desc *desc) {
 
 JVS_EXPORT void jvs_destroy(jvs_index *ix) {
     if (!ix) return;
+    free(ix->cbT);
     free(ix->node_norm);
     free(ix->vec_norm);
     free(ix);
@@ -305,24 +313,21 @@ static void build_lut(const jvs_index *ix, scratch_t *S, const float *q) {
         qq = S->qc;
     }
     const int l2 = d->similarity == JV_SIM_EUCLIDEAN;
-    for (int m = 0; m < M; m++) {
-        const float *cb = d->pq_codebooks + (size_t)m * 256 * sub;
+    for (int m = 0; m < M; m++) { /* inner loops run over the 256 centroids: unit stride, vectorised by the compiler */
+        const float *cb = ix->cbT + (size_t)m * sub * 256;
         const float *qs = qq + m * sub;
-        float *out = S->lut + m * 256;
-        if (l2) {
-            for (int c = 0; c < 256; c++) {
-                float s = 0.f;
-                for (int j = 0; j < sub; j++) {
-                    const float t = qs[j] - cb[c * sub + j];
-                    s += t * t;
+        float *restrict out = S->lut + m * 256;
+        for (int c = 0; c < 256; c++) out[c] = 0.f;
+        for (int j = 0; j < sub; j++) {
+            const float qj = qs[j];
+            const float *restrict col = cb + (size_t)j * 256;
+            if (l2) {
+                for (int c = 0; c < 256; c++) {
+                    const float t = qj - col[c];
+                    out[c] += t * t;
                 }
-                out[c] = s;
-            }
-        } else {
-            for (int c = 0; c < 256; c++) {
-                float s = 0.f;
-                for (int j = 0; j < sub; j++) s += qs[j] * cb[c * sub + j];
-                out[c] = s;
+            } else {
+                for (int c = 0; c < 256; c++) out[c] += qj * col[c];
             }
         }
     }

@@ -18,14 +18,17 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_build" / "libjvoracle.so"
+_SIMD_PATH = _HERE / "_build" / "libjvcpusimd.so"  # tuned CPU arm of the benchmark (jv_cpu_simd.c), never the checker
 
 SIM_EUCLIDEAN, SIM_DOT, SIM_COSINE, SIM_MIP = 0, 1, 2, 3
 
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc only)."""
-    src = _HERE / "jv_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    stale = False
+    for lib_path, src in ((_LIB_PATH, _HERE / "jv_oracle.c"), (_SIMD_PATH, _HERE / "jv_cpu_simd.c")):
+        stale |= not lib_path.exists() or lib_path.stat().st_mtime < src.stat().st_mtime
+    if force or stale:
         subprocess.run(["make", "-C", str(_HERE), "-s"], check=True)
     return _LIB_PATH
 
@@ -347,6 +350,76 @@ def merge_topk(docs, scores, k: int):
     oc = np.empty(nq, dtype=np.int32)
     lib().jvo_merge_topk(C.c_int32(g), C.c_int32(nq), C.c_int32(k), _p(d), _p(s), _p(od), _p(os_), _p(oc))
     return od, os_, oc
+
+
+_simd = None
+
+
+def simd_lib() -> C.CDLL:
+    global _simd
+    if _simd is None:
+        build()
+        _simd = C.CDLL(str(_SIMD_PATH))
+        _simd.jvs_create.restype = C.c_void_p
+        _simd.jvs_create.argtypes = [C.POINTER(IndexDesc)]
+        _simd.jvs_destroy.argtypes = [C.c_void_p]
+        _simd.jvs_isa.restype = C.c_int32
+        _simd.jvs_num_procs.restype = C.c_int32
+    return _simd
+
+
+class SimdIndex:
+    """The tuned CPU arm (jv_cpu_simd.c): same algorithm as OracleIndex.search for unfiltered queries with the default collector
+    parameters, AVX-512 / AVX2 gathers and FMAs, free summation order.  Bench baseline; gated against the checker by recall."""
+
+    def __init__(self, oracle_index: "OracleIndex"):
+        self._keep = oracle_index  # owns the arrays the description points to
+        self._h = simd_lib().jvs_create(C.byref(oracle_index.desc))
+        if not self._h:
+            raise ValueError("the tuned CPU arm needs K = 256 and uniform sub-vectors")
+        self.isa = "avx512" if simd_lib().jvs_isa() == 512 else "avx2"
+
+    def close(self):
+        if self._h:
+            simd_lib().jvs_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, queries, k: int, rerank_k: int, threads: int = 0):
+        q = _f32(np.atleast_2d(queries))
+        nq = q.shape[0]
+        docs = np.empty((nq, k), dtype=np.int32)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        stats = (QueryStats * nq)()
+        rc = simd_lib().jvs_search_batch(C.c_void_p(self._h), _p(q), C.c_int32(nq), C.c_int32(k), C.c_int32(rerank_k), _p(docs), _p(scores),
+                                         _p(counts), stats, C.c_int32(threads))
+        if rc != 0:
+            raise ValueError("bad arguments")
+        return docs, scores, counts, np.frombuffer(stats, dtype=np.int32).reshape(nq, 4).copy()
+
+
+def host_cores() -> int:
+    """Cores this process may run on (torchrun exports OMP_NUM_THREADS=1: never trust omp_get_max_threads for a baseline)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def num_threads() -> int:
