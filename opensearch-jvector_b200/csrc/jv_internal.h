@@ -66,10 +66,11 @@ namespace jv {
 struct Q8Knobs {
     int occ = 0;        // JVGPU_Q8_OCC: cap the CTAs per SM
     int chunk = 0;      // JVGPU_Q8_CHUNK: table staging buffer of n queries
-    int warps = 0;      // JVGPU_Q8_WARPS: warps per CTA (4 or 8)
+    int warps = 0;      // JVGPU_Q8_WARPS: warps per CTA (4 or 8; manager / scorer kernel: 4, 5 or 8 including the manager)
     bool prof = false;  // JVGPU_PROFILE: per-phase cycle counters (synchronous kernel)
     bool fused = false; // JVGPU_Q8_FUSED: K3 as the epilogue of the synchronous kernel
-    bool pipe = false;  // JVGPU_Q8_PIPE: experimental token-passing pipelined kernel (jv_q8_pipe.cu) instead of the round-synchronous one
+    bool sync = false;  // JVGPU_Q8_SYNC: the round-synchronous kernel of jv_q8.cu instead of the manager / scorer kernel (jv_q8_beam.cu)
+    int depth = 0;      // JVGPU_Q8_DEPTH: steps in flight of the manager / scorer kernel (1 or 2; default 2)
     bool h2d_single = false; // JVGPU_H2D_SINGLE: no chunked H2D pipeline in jv_search_batch
 };
 const Q8Knobs &q8_knobs();   // the environment is read once per process ...

@@ -39,7 +39,8 @@ void q8_knobs_refresh() {
     if (const char *e = getenv("JVGPU_Q8_WARPS")) v.warps = atoi(e);
     v.prof = getenv("JVGPU_PROFILE") != nullptr;
     v.fused = getenv("JVGPU_Q8_FUSED") != nullptr;
-    v.pipe = getenv("JVGPU_Q8_PIPE") != nullptr;
+    v.sync = getenv("JVGPU_Q8_SYNC") != nullptr;
+    if (const char *e = getenv("JVGPU_Q8_DEPTH")) v.depth = atoi(e);
     v.h2d_single = getenv("JVGPU_H2D_SINGLE") != nullptr;
     g_knobs = v;
 }
@@ -933,7 +934,10 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
     // default width: 4 (measured best without a filter); filtered queries need ~1/selectivity more expansions anyway, so a
     // wider step costs few wasted visits and saves steps (measured at 10 % selectivity: 2/4/6/8 -> 265k/453k/514k/460k queries/s;
     // at 50 %: 4 -> 1.13 M, 8 -> 1.08 M)
-    const int dflt = a.d_accept != nullptr ? 6 : 4;
+    // the manager / scorer kernel (M = 161..192, no filter, list <= 64) works two steps deep: 3 candidates per step measured best
+    // there (cfg2: 3 -> 1.46 ms / 1 078 visited, 4 -> 1.47 ms / 1 218 visited; cfg4 shape: 1.26 / 1.31 ms)
+    const bool beam_shape = !q8_knobs().sync && a.d_accept == nullptr && q8_beam_supported(ix, a.rerank_k, ix->R, 3);
+    const int dflt = a.d_accept != nullptr ? 6 : beam_shape ? 3 : 4;
     int E = a.expand_width <= 0 ? dflt : (a.expand_width > kQMaxE ? kQMaxE : a.expand_width);
     for (int q0 = 0; q0 < a.nq; q0 += chunk) {
         const int nqc = a.nq - q0 < chunk ? a.nq - q0 : chunk;
@@ -990,11 +994,11 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         p.surv_cap = E * ((ix->R + 31) / 32) * 32;
         int32_t st;
         const bool prof = q8_knobs().prof; // per-phase cycle counters (costs registers): diagnostics only
-        const int warps = q8_knobs().warps ? q8_knobs().warps : 4;
-        // experimental (JVGPU_Q8_PIPE=1): the token-passing pipelined kernel of jv_q8_pipe.cu.  Measured at cfg2: 1.75 ms against
-        // 1.55 ms for the round-synchronous kernel below, so it is not the default.
-        if (q8_knobs().pipe && !filt && !fuse && q8_pipe_supported(ix, a.rerank_k, ix->R)) {
-            JV_TRY(launch_q8_pipe(ix, ctx, p, warps));
+        const int warps = q8_knobs().warps == 8 ? 8 : 4;
+        // production: manager / scorer kernel (jv_q8_beam.cu); the round-synchronous kernel below keeps filtered queries, lists
+        // longer than 64 entries and steps wider than 4 adjacency chunks (JVGPU_Q8_SYNC=1 forces it: diagnostics)
+        if (!q8_knobs().sync && !filt && !fuse && q8_beam_supported(ix, a.rerank_k, ix->R, E)) {
+            JV_TRY(launch_q8_beam(ix, ctx, p));
             if (launches) *launches += 2;
             continue;
         }

@@ -1,7 +1,9 @@
 // jv_q8.cuh — pieces shared by the two traversal kernels of the 8-bit table path: jv_q8.cu (K1 + the round-synchronous
-// kernel, still the path of filtered queries) and jv_q8_pipe.cu (the pipelined production kernel).
+// kernel: filtered queries, lists longer than 64) and jv_q8_beam.cu (manager / scorer warps, the production kernel).
 #pragma once
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "jv_search_common.cuh"
 
@@ -133,8 +135,8 @@ __device__ __forceinline__ bool q_filter_insert(uint32_t *filter, int set_bits, 
     }
 }
 
-// jv_q8_pipe.cu
-bool q8_pipe_supported(const jv_index *ix, int L, int R);
-int32_t launch_q8_pipe(jv_index *ix, SearchCtx *ctx, Q8Params &p, int warps);
+// jv_q8_beam.cu
+bool q8_beam_supported(const jv_index *ix, int L, int R, int E);
+int32_t launch_q8_beam(jv_index *ix, SearchCtx *ctx, Q8Params &p);
 
 }  // namespace jv

@@ -214,7 +214,7 @@ class GpuIndex:
         N.check(N.load().jv_index_debug_counter(self.handle, 200, C.addressof(b)))
 
     PHASES = ("setup", "table_build", "select", "neighbour_rows", "scoring", "merge", "emit", "steps",
-              "sub_code_words", "sub_lookups", "sub_offers", "sub_spare")
+              "sub_code_words", "sub_lookups", "sub_offers", "sub_11", "sub_12", "sub_13", "sub_14", "sub_15")
 
     def phase_cycles(self, reset: bool = False) -> dict:
         """Per-phase SM cycles of the fast traversal kernel (thread 0 of each CTA, summed) + step count."""

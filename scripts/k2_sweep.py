@@ -1,6 +1,6 @@
 """GPU box: one fixture, many traversal-kernel configurations (kernel flavour, warps per CTA, expansions in flight, CTAs per SM).
 
-    python scripts/k2_sweep.py [workload] [spec ...]        spec = name:ENV=V,ENV=V:E      e.g.  pipe4:JVGPU_Q8_WARPS=4:4
+    python scripts/k2_sweep.py [workload] [spec ...]        spec = name:ENV=V,ENV=V:E      e.g.  beam8:JVGPU_Q8_WARPS=8:4
 
 Prints one JSON line per configuration: K2 kernel ms (CUDA events around the traversal launch), recall@k against the exact
 top-k, visited / expanded per query and the fraction of the measured HBM roofline on the GPU's own visit count."""
@@ -20,9 +20,9 @@ jv = jvpkg.load()
 args = sys.argv[1:]
 wl = args[0] if args and ":" not in args[0] else "cfg2-1Mx768-dot-pq192"
 specs = [a for a in args if ":" in a] or [
-    "sync-e4::4", "sync-e2::2", "sync-e1::1", "pipe-e1:JVGPU_Q8_PIPE=1:1", "pipe-e2:JVGPU_Q8_PIPE=1:2", "pipe-e3:JVGPU_Q8_PIPE=1:3",
-    "pipe-e4:JVGPU_Q8_PIPE=1:4"]
-KNOBS = ("JVGPU_Q8_PIPE", "JVGPU_Q8_WARPS", "JVGPU_Q8_OCC", "JVGPU_PROFILE", "JVGPU_Q8_FUSED")
+    "sync-e4:JVGPU_Q8_SYNC=1:4", "beam-d1-e1:JVGPU_Q8_DEPTH=1:1", "beam-d1-e4:JVGPU_Q8_DEPTH=1:4", "beam-d2-e2:JVGPU_Q8_DEPTH=2:2",
+    "beam-d2-e3:JVGPU_Q8_DEPTH=2:3", "beam-d2-e4:JVGPU_Q8_DEPTH=2:4"]
+KNOBS = ("JVGPU_Q8_SYNC", "JVGPU_Q8_DEPTH", "JVGPU_Q8_WARPS", "JVGPU_Q8_OCC", "JVGPU_PROFILE", "JVGPU_Q8_FUSED")
 
 w = dict(bench.WORKLOADS[wl])
 host, dq = bench.build_fixture(torch, jv, w, 0, 1234, w["n"], lambda m: print("[sweep]", m, file=sys.stderr, flush=True))
@@ -71,7 +71,7 @@ for spec in specs:
         ph = gi.phase_cycles(reset=True)
         vals = list(ph.values())
         div = max(vals[7], 1)
-        prof = {"per": "expansion" if "PIPE" in envs else "step", "count_per_query": round(vals[7] / nq, 1),
+        prof = {"per": "step", "count_per_query": round(vals[7] / nq, 1),
                 "cycles": [round(v / div) for v in vals[:7]] + [round(v / div) for v in vals[8:]]}
     print(json.dumps({"name": name, "prof": prof, "env": envs, "E": int(E), "k2_ms": round(k2, 4), "lut_ms": round(float(np.median([t.get("lut_ms", 0) for t in ts])), 4),
                       "rerank_ms": round(float(np.median([t["rerank_ms"] for t in ts])), 4),
