@@ -52,6 +52,7 @@ WORKLOADS = {
     "cfg5-shard-12.5Mx128-dot-pq64-k100": dict(n=12_500_000, dim=128, sim=1, pq_m=64, R=32, k=100, over=5, nq=10_000, latent=32, clusters=51200),
 }
 SIM_NAMES = {0: "l2", 1: "dot", 2: "cosine", 3: "mip"}
+KERNEL_NAMES = {0: "search_kernel (strict)", 1: "fast_search_kernel", 2: "q8_search_kernel", 3: "q8_beam_kernel"}
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -261,7 +262,7 @@ def cpu_arm(host, w, k, rk, nq, budget_s, steps, warmup, truth=None):
     return out
 
 
-def shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="cfg3-10Mx96-l2-pq48"):
+def shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="cfg3-10Mx96-l2-pq48", n_per_rank=None, host_vectors=False):
     """BASELINE.json configs[2]: the index partitioned across the ranks (disjoint doc ranges, one Vamana graph + codes per rank), the
     query batch broadcast, every rank searches its shard, per-rank top-k lists all-gathered over NCCL/NVLink and merged on the device
     (K7).  The exchange + merge of batch i runs on a side stream while the search of batch i+1 runs (double-buffered results)."""
@@ -269,7 +270,7 @@ def shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="
     lib = N.load()
     w = dict(WORKLOADS[workload])
     k, rk, nq, dim, m, R = w["k"], w["k"] * w["over"], w["nq"], w["dim"], w["pq_m"], w["R"]
-    n_local = w["n"] // world
+    n_local = n_per_rank or w["n"] // world
     dev_t = torch.device("cuda", local_rank)
     host, dq = build_fixture(torch, jv, w, local_rank, 4321 + rank * 17, n_local, log)
     if world > 1:
@@ -315,6 +316,11 @@ def shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="
         exchange(0, gtd, gts)
     barrier()
     truth = md[0].cpu().numpy().copy()
+    if host_vectors:  # config 5: the same shard with its fp32 rerank vectors in pinned host memory (codes + graph stay in HBM)
+        gi.close()
+        gi = jv.GpuIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256, pq_codebooks=host["cb"],
+                         pq_global_centroid=host.get("gcent"), pq_codes=host["codes"], device=local_rank,
+                         flags=N.FLAG_LUT_U8 | N.FLAG_NO_VECTORS_ON_DEVICE)
 
     def run(steps, overlap):
         timings = []
@@ -359,7 +365,8 @@ def shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="
     s = st.cpu().numpy()
     adc_bytes, rr_bytes = algorithmic_bytes(s, m, R, dim)
     peak, _ = measured_peak()
-    res = {"workload": workload, "layout": "shards", "n_total": w["n"], "n_per_gpu": n_local, "query_batch": nq, "k": k, "rerank_k": rk,
+    res = {"workload": workload, "layout": "shards", "n_total": n_local * world, "n_per_gpu": n_local,
+           "rerank_vectors": "pinned host memory" if host_vectors else "HBM", "query_batch": nq, "k": k, "rerank_k": rk,
            "value": nq * args.steps / t_over, "unit": "queries/s", "ms_per_step": t_over / args.steps * 1e3,
            "value_serial": nq * args.steps / t_serial, "ms_per_step_serial": t_serial / args.steps * 1e3,
            "gather_merge_ms": xchg_ms if world > 1 else 0.0, "recall_at_10": -neg_rec, "scaling": "strong",
@@ -394,6 +401,9 @@ def main():
     ap.add_argument("--host-vectors", action="store_true",
                     help="keep the fp32 rerank vectors in pinned host memory (JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE, config 5); the exact "
                          "ground truth is computed first on a device-resident copy of the same index")
+    ap.add_argument("--no-shards", action="store_true",
+                    help="skip the `shards` block (configs[2]: 10M x 96 split over the ranks, NCCL all-gather + K7 merge; at 8 ranks also "
+                         "configs[4]: 8 x 12.5M x 128 with the rerank vectors in pinned host memory)")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
@@ -535,6 +545,7 @@ def main():
     lut_bytes = nq * ((m + 31) // 32 * 32) * 256 if args.adc_table == "u8" else 0  # K1 writes one byte per table entry
     rerank_ms = sum(t["rerank_ms"] for t in timings) / args.steps
     launches = sum(t["launches"] for t in timings) + (args.steps if shards else 0)
+    used_E, used_kernel = int(timings[-1].get("expand_width_used", 0)), int(timings[-1].get("traversal_kernel", -1))
 
     # recall against exact ground truth (per shard merged when sharded)
     if shards:
@@ -547,19 +558,21 @@ def main():
     st = stats.cpu().numpy()
     adc_bytes, rr_bytes = algorithmic_bytes(st, m, R, dim)
 
-    # ---- e2e through the host-pointer entry point (what the Java codec calls): pinned host queries, host results
-    hq = torch.from_numpy(host["queries"]).pin_memory()
-    h_doc = torch.empty(nq, k, dtype=torch.int32).pin_memory()
-    h_score = torch.empty(nq, k, dtype=torch.float32).pin_memory()
-    h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
-    h_stats = torch.empty(nq, 4, dtype=torch.int32).pin_memory()
+    # ---- e2e through the host-pointer entry point (what the Java codec calls).  The buffers come from the ABI itself
+    # (jv_host_alloc: page-locked, what INTEGRATION.md tells the FFM caller to wrap with MemorySegment.reinterpret); the same call
+    # from pageable numpy buffers is timed next to it (`e2e_pageable`: what a caller that ignores that advice gets)
+    hq, hq_p = N.host_alloc((nq, dim), np.float32)
+    hq[:] = host["queries"]
+    h_doc, h_doc_p = N.host_alloc((nq, k), np.int32)
+    h_score, h_score_p = N.host_alloc((nq, k), np.float32)
+    h_cnt, h_cnt_p = N.host_alloc((nq,), np.int32)
+    h_stats, h_stats_p = N.host_alloc((nq, 4), np.int32)
     p = gi._params(k, rk, 0.0, 0.0, None, 0, args.expand_width)
 
     def step_e2e():
-        N.check(lib.jv_search_batch(gi.handle, hq.data_ptr(), nq, C.addressof(p), h_doc.data_ptr(), h_score.data_ptr(), h_cnt.data_ptr(),
-                                    h_stats.data_ptr(), None))
+        N.check(lib.jv_search_batch(gi.handle, hq_p, nq, C.addressof(p), h_doc_p, h_score_p, h_cnt_p, h_stats_p, None))
         if shards:
-            md, _, _ = merge_shards(h_doc.to(dev_t, non_blocking=True), h_score.to(dev_t, non_blocking=True))
+            md, _, _ = merge_shards(torch.from_numpy(h_doc).to(dev_t), torch.from_numpy(h_score).to(dev_t))
             md.cpu()
 
     for _ in range(2):
@@ -571,6 +584,21 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - e0
 
+    pq_ = np.ascontiguousarray(host["queries"])  # pageable
+    pg = (np.empty((nq, k), np.int32), np.empty((nq, k), np.float32), np.empty(nq, np.int32), np.empty((nq, 4), np.int32))
+    for _ in range(2):
+        N.check(lib.jv_search_batch(gi.handle, pq_.ctypes.data, nq, C.addressof(p), pg[0].ctypes.data, pg[1].ctypes.data, pg[2].ctypes.data,
+                                    pg[3].ctypes.data, None))
+    barrier()
+    e0 = time.perf_counter()
+    psteps = max(3, args.steps // 4)
+    for _ in range(psteps):
+        N.check(lib.jv_search_batch(gi.handle, pq_.ctypes.data, nq, C.addressof(p), pg[0].ctypes.data, pg[1].ctypes.data, pg[2].ctypes.data,
+                                    pg[3].ctypes.data, None))
+    barrier()
+    e2e_pageable = nq * psteps / (time.perf_counter() - e0)
+    pageable_same = bool((pg[0] == h_doc).all())
+
     # ---- the same call from TWO host threads at once (Lucene searches the leaves of a shard from a thread pool, and the
     # reference reader is shared between threads: KNNJVectorTests.java:982-1028): the copies of one caller overlap the kernels
     # of the other.  Reported next to the single-caller number, never instead of it.
@@ -578,7 +606,7 @@ def main():
     if world == 1:
         bufs = []
         for _ in range(2):
-            bufs.append((hq.clone().pin_memory(), torch.empty(nq, k, dtype=torch.int32).pin_memory(), torch.empty(nq, k, dtype=torch.float32).pin_memory(),
+            bufs.append((torch.from_numpy(host["queries"]).clone().pin_memory(), torch.empty(nq, k, dtype=torch.int32).pin_memory(), torch.empty(nq, k, dtype=torch.float32).pin_memory(),
                          torch.empty(nq, dtype=torch.int32).pin_memory(), torch.empty(nq, 4, dtype=torch.int32).pin_memory()))
         per_thread = max(1, args.steps // 2)
         errs = []
@@ -605,7 +633,7 @@ def main():
         conc_wall = time.perf_counter() - c0
         if errs:
             raise errs[0]
-        same = bool((bufs[0][1] == h_doc).all() and (bufs[1][1] == h_doc).all())
+        same = bool((bufs[0][1].numpy() == h_doc).all() and (bufs[1][1].numpy() == h_doc).all())
         e2e_conc = {"value": 2 * per_thread * nq / conc_wall, "unit": "queries/s", "callers": 2, "batches": 2 * per_thread,
                     "results_identical_to_single_caller": same}
 
@@ -625,10 +653,10 @@ def main():
     line = {
         "metric": "QPS at recall@10>=0.95 (1Mx768 PQ)", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "u8 table sums (traversal) + f32 (table build, exact rerank)" if args.adc_table == "u8" else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "n": w["n"], "dim": dim, "similarity": SIM_NAMES[w["sim"]], "pq": f"{m}x256" if m else "none", "k": k, "rerank_k": rk,
                    "graph": f"Vamana R={R} beamWidth=100", "query_batch": nq, "layout": args.layout if world > 1 else "single",
-                   "adc_table": args.adc_table, "expand_width": args.expand_width or 4,
+                   "adc_table": args.adc_table, "expand_width": used_E, "traversal_kernel": KERNEL_NAMES.get(used_kernel, "?"),
                    "rerank_vectors": "pinned host memory" if args.host_vectors else "HBM",
                    "l2": (f"index working set {gi.device_bytes() / 2**30:.2f} GiB >> 126 MB L2, no flush needed" if gi.device_bytes() > 4 * 126e6 else
                           f"index working set {gi.device_bytes() / 2**20:.1f} MiB fits the 126 MB L2 and is NOT flushed between steps: a hot "
@@ -638,12 +666,13 @@ def main():
         "visited_set_overflows": gi.visited_overflows(),
         # dominant kernel: the traversal (K2).  With the 8-bit table the table build (K1) is a separate launch whose time is
         # measured by its own event pair and reported next to it; the fp16/fp32 kernels fuse K1 into the traversal.
-        "roofline": {"bound": "hbm", "kernel": "q8_search_kernel (K2 beam search + ADC, 8-bit table staged with TMA)" if args.adc_table == "u8"
-                     else "fast_search_kernel (K4 beam search with exact scores, un-quantised segment)" if m == 0
-                     else "fast_search_kernel (K1 LUT + K2 beam search + ADC)",
+        "roofline": {"bound": "hbm", "kernel": {3: "q8_beam_kernel (K2 beam search + ADC: 8-bit table staged with TMA, manager warp + scorer warps, 2 steps in flight)",
+                                                2: "q8_search_kernel (K2 beam search + ADC, 8-bit table staged with TMA, round-synchronous)"}.get(used_kernel)
+                     or ("fast_search_kernel (K4 beam search with exact scores, un-quantised segment)" if m == 0
+                         else "fast_search_kernel (K1 LUT + K2 beam search + ADC)"),
                      "achieved": adc_bytes / (k2_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": adc_bytes / (k2_ms * 1e-3) / 1e9 / peak,
-                     "traffic": ncu_traffic(args.workload, args.adc_table, args.expand_width or 4), "peak_source": peak_src,
+                     "traffic": ncu_traffic(args.workload, args.adc_table, used_E), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": adc_bytes, "kernel_ms": k2_ms,
                      "k1_k2": {"kernel_ms": search_ms, "achieved": adc_bytes / (search_ms * 1e-3) / 1e9,
                                "frac": adc_bytes / (search_ms * 1e-3) / 1e9 / peak},
@@ -656,10 +685,30 @@ def main():
         "pq_encode": {"kernel_ms": host["enc_ms"], "vectors_per_s": n_local / (host["enc_ms"] * 1e-3)} if m else None,
         "e2e": {"value": units / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                 "d2h_bytes_per_step": nq * k * 8 + nq * 4 + nq * 16},
+        "e2e_pageable": {"value": e2e_pageable, "unit": "queries/s", "note": "same jv_search_batch call from pageable host buffers (single rank figure)",
+                         "results_identical": pageable_same},
         "e2e_two_callers": e2e_conc,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
+    # ---- the sharded machine (BASELINE.json configs[2] / [4]) in the same line: the headline above is the replicas layout
+    run_shards = (not args.no_shards and os.environ.get("JV_BENCH_SHARDS", "1") != "0" and args.layout == "replicas"
+                  and args.workload == "cfg2-1Mx768-dot-pq192" and not args.host_vectors)
+    if run_shards:
+        gi.close()
+        gi = None
+        torch.cuda.empty_cache()
+        blocks = [shards_block(torch, dist, jv, args, rank, world, local_rank, log)]
+        if world == 8:
+            import psutil
+            ok = torch.tensor([1 if psutil.virtual_memory().available > 8 * 12.5e6 * 128 * 4 * 2.5 else 0], device=dev_t)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()):
+                blocks.append(shards_block(torch, dist, jv, args, rank, world, local_rank, log, workload="cfg5-shard-12.5Mx128-dot-pq64-k100",
+                                           n_per_rank=12_500_000, host_vectors=True))
+            else:
+                blocks.append({"workload": "cfg5-shard-12.5Mx128-dot-pq64-k100", "skipped": "not enough host memory for 8 x 6.4 GB of pinned vectors"})
+        line["shards"] = blocks
     # CPU baseline on rank 0, N=1 only: the tuned CPU arm (oracle/jv_cpu_simd.c) on a bounded sample of the same workload
     if rank == 0 and world == 1:
         base = cpu_arm(host, w, k, rk, nq, budget_s=12.0, steps=1, warmup=0, truth=truth)
@@ -674,7 +723,8 @@ def main():
         os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line), flush=True)
-    gi.close()
+    if gi is not None:
+        gi.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -143,7 +143,16 @@ typedef struct jv_batch_timing {
     int32_t launches; /* kernels launched for this batch                               */
     float lut_ms;     /* share of search_ms spent in the batched 8-bit table build (first chunk; 0 when the
                          table build is fused into the traversal kernel)                  */
+    int32_t expand_width_used; /* candidates expanded per step by the traversal kernel that ran (0: strict kernel)   */
+    int32_t traversal_kernel;  /* JV_KERNEL_*: which traversal kernel served the batch                              */
 } jv_batch_timing;
+
+enum {
+    JV_KERNEL_STRICT = 0,   /* search_kernel: candidate heap + result heap, reference order (jv_search.cu)             */
+    JV_KERNEL_FAST = 1,     /* fast_search_kernel: fp32 / fp16 table or exact scores, wide steps (jv_search_fast.cu)   */
+    JV_KERNEL_Q8_SYNC = 2,  /* q8_search_kernel: 8-bit table, round-synchronous CTA per query (jv_q8.cu)               */
+    JV_KERNEL_Q8_BEAM = 3   /* q8_beam_kernel: 8-bit table, manager warp + scorer warps, two steps in flight (jv_q8_beam.cu) */
+};
 
 typedef struct jv_search_params {
     int32_t struct_size;   /* = sizeof(jv_search_params)                                        */

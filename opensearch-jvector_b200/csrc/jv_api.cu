@@ -439,6 +439,8 @@ static void fill_timing(SearchCtx *c, jv_batch_timing *t, int launches, bool hos
     }
     t->launches = launches;
     if (c->lut_timed) cudaEventElapsedTime(&t->lut_ms, c->ev[1], c->ev[5]);
+    t->expand_width_used = c->last_width;
+    t->traversal_kernel = c->last_kernel;
 }
 
 int32_t jv_search_batch_dev(jv_index *ix, const float *d_queries, int32_t nq, const jv_search_params *p, int32_t *d_out_doc,

@@ -18,6 +18,7 @@ struct SearchCtx {
     DevBuf lut8, qparams;             // 8-bit ADC tables of the current chunk + per-query (delta, base, ||q||^2)
     DevBuf slice_doc, slice_score;    // brute force: per-slice partial top-k
     bool lut_timed = false;           // ev[5] was recorded after the first chunk's table build
+    int last_width = 0, last_kernel = 0; // what the last traversal launch used (jv_batch_timing)
     void *pinned = nullptr;           // host staging
     size_t pinned_bytes = 0;
     int32_t init(int device);

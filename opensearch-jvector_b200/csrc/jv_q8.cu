@@ -1000,6 +1000,8 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
         if (!q8_knobs().sync && !filt && !fuse && q8_beam_supported(ix, a.rerank_k, ix->R, E)) {
             JV_TRY(launch_q8_beam(ix, ctx, p));
             if (launches) *launches += 2;
+            ctx->last_width = E;
+            ctx->last_kernel = JV_KERNEL_Q8_BEAM;
             continue;
         }
         // the diagnostic instantiations (8 warps, phase counters) exist for the headline shape (M = 192) only
@@ -1028,6 +1030,8 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
 #undef JV_Q8_CASE
         JV_TRY(st);
         if (launches) *launches += 2;
+        ctx->last_width = E;
+        ctx->last_kernel = JV_KERNEL_Q8_SYNC;
     }
     return JV_OK;
 }

@@ -288,6 +288,8 @@ static int32_t launch_typed(jv_index *ix, SearchCtx *ctx, SearchParams &p, size_
 
 int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *launches, bool *reranked) {
     if (reranked) *reranked = false;
+    ctx->last_width = 0;
+    ctx->last_kernel = JV_KERNEL_STRICT;
     if (a.nq <= 0) return JV_OK;
     JV_REQUIRE(ix->R <= kMaxR, "max_degree %d exceeds the supported %d", ix->R, kMaxR);
     SearchParams p;
@@ -326,6 +328,8 @@ int32_t launch_search(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, int *
     if (plain && (!ix->has_pq || (p.M & 3) == 0)) {
         const int32_t fs = launch_search_fast(ix, ctx, p, a.expand_width == 0 ? 4 : a.expand_width, f16);
         if (fs == JV_OK && launches) *launches += 1;
+        ctx->last_width = p.expand_width;
+        ctx->last_kernel = JV_KERNEL_FAST;
         return fs;
     }
     size_t fixed = 0;

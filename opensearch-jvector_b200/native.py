@@ -43,7 +43,8 @@ class QueryStats(C.Structure):
 
 class BatchTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("search_ms", C.c_float), ("rerank_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("total_ms", C.c_float), ("launches", C.c_int32), ("lut_ms", C.c_float)]
+                ("total_ms", C.c_float), ("launches", C.c_int32), ("lut_ms", C.c_float), ("expand_width_used", C.c_int32),
+                ("traversal_kernel", C.c_int32)]
 
 
 class SearchParams(C.Structure):

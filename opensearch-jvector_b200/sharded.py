@@ -56,6 +56,10 @@ class ShardedSearcher:
         q = queries
         if dist is not None and dist.is_initialized() and self.spec.world > 1:
             dist.broadcast(q, src=0)  # the batch is replicated: every shard answers every query
+        if getattr(q, "is_cuda", False):
+            # the library searches on its own non-blocking stream: the broadcast (NCCL work ordered against torch's current
+            # stream) and any producer kernel of `queries` must have finished before it reads them
+            torch.cuda.current_stream(q.device).synchronize()
         docs, scores = self.local_search(q, k)
         docs = torch.where(docs >= 0, docs + self.spec.begin, docs)  # global docIds
         if self.spec.world == 1 or dist is None:
