@@ -359,7 +359,11 @@ int32_t jv_index_device_bytes(const jv_index *ix, int64_t *out_bytes) {
 }
 
 int32_t jv_index_debug_counter(jv_index *ix, int32_t which, int64_t *out_value) {
-    JV_REQUIRE(ix && out_value && ((which >= 0 && which < 4) || (which >= 8 && which < 24) || which == 100 || which == 200), "bad arguments");
+    JV_REQUIRE(ix && out_value && ((which >= 0 && which < 6) || (which >= 8 && which < 24) || which == 100 || which == 200), "bad arguments");
+    if (which == 4 || which == 5) { // brute-force batches answered by the tensor-core path / handed back to the fp32 kernel (overflow)
+        *out_value = which == 4 ? ix->tc_batches : ix->tc_fallbacks;
+        return JV_OK;
+    }
     if (which == 200) { // re-read the diagnostic environment knobs (they are cached: never a getenv on the search path)
         q8_knobs_refresh();
         *out_value = 0;

@@ -17,6 +17,8 @@ struct SearchCtx {
     DevBuf visited;                   // global visited tables (fallback when they do not fit in smem)
     DevBuf lut8, qparams;             // 8-bit ADC tables of the current chunk + per-query (delta, base, ||q||^2)
     DevBuf slice_doc, slice_score;    // brute force: per-slice partial top-k
+    DevBuf tc_q, tc_f, tc_chunk, tc_cand, tc_cnt; // brute force on the tensor cores (jv_exact_tc.cu): bf16 queries, per-query floats,
+                                      // pass-A chunk maxima, pass-B candidates + counts
     bool lut_timed = false;           // ev[5] was recorded after the first chunk's table build
     int last_width = 0, last_kernel = 0; // what the last traversal launch used (jv_batch_timing)
     void *pinned = nullptr;           // host staging
@@ -49,6 +51,11 @@ struct jv_index {
     jv::DevBuf nvq_bytes, nvq_params, nvq_gmean, nvq_off;
     bool has_nvq = false;
     int nvq_m = 0;
+    // tensor-core brute force (jv_exact_tc.cu): bf16 copy of the vectors (COSINE: normalised), EUCLIDEAN bias, max ||x||^2; lazy
+    jv::DevBuf tc_base, tc_bias, tc_maxnorm;
+    bool tc_ready = false;
+    int tc_dp = 0;
+    int64_t tc_batches = 0, tc_fallbacks = 0; // diagnostics (jv_index_debug_counter 4, 5)
     bool q8_ok = false;
     int q8_nj = 0; // 32-subspace blocks per code row (M rounded up to 32)
     int fused_stride = 0;
@@ -73,6 +80,7 @@ struct Q8Knobs {
     bool sync = false;  // JVGPU_Q8_SYNC: the round-synchronous kernel of jv_q8.cu instead of the manager / scorer kernel (jv_q8_beam.cu)
     int depth = 0;      // JVGPU_Q8_DEPTH: steps in flight of the manager / scorer kernel (1 or 2; default 2)
     bool h2d_single = false; // JVGPU_H2D_SINGLE: no chunked H2D pipeline in jv_search_batch
+    int exact_tc = -1;  // JVGPU_EXACT_TC: brute force on the tensor cores (jv_exact_tc.cu): 1 always (tests), 0 never, unset = by size
 };
 const Q8Knobs &q8_knobs();   // the environment is read once per process ...
 void q8_knobs_refresh();     // ... and again on jv_index_debug_counter(which = 200) (tests and sweeps change the knobs)
@@ -120,6 +128,11 @@ int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int 
 int32_t launch_exact_topk(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, const uint64_t *d_accept,
                           int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
                           int *launches);
+
+// K5 on the tensor cores (jv_exact_tc.cu): *done = false -> a candidate list overflowed, use the fp32 kernel
+bool exact_tc_eligible(const jv_index *ix, int nq, int k, const uint64_t *d_accept);
+int32_t launch_exact_topk_tc(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int32_t *d_out_doc, float *d_out_score,
+                             int32_t *d_out_count, int *launches, bool *done);
 
 // K7
 int32_t launch_merge_topk(cudaStream_t stream, int g, int nq, int k, const int32_t *d_docs, const float *d_scores,

@@ -408,6 +408,11 @@ int32_t launch_exact_topk(jv_index *ix, SearchCtx *ctx, const float *d_queries, 
                           int *launches) {
     if (nq <= 0) return JV_OK;
     JV_REQUIRE(k >= 1 && k <= 1024, "exact_topk: 1 <= k <= 1024");
+    if (exact_tc_eligible(ix, nq, k, d_accept)) { // tensor-core candidate generation + canonical fp32 re-scoring (jv_exact_tc.cu)
+        bool done = false;
+        JV_TRY(launch_exact_topk_tc(ix, ctx, d_queries, nq, k, d_out_doc, d_out_score, d_out_count, launches, &done));
+        if (done) return JV_OK;
+    }
     const int dim = ix->dim;
     const int nch = (dim + 127) / 128;
     const bool fast = (dim & 3) == 0 && nch <= 16 && ((reinterpret_cast<uintptr_t>(d_queries) & 15) == 0);

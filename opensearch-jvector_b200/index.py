@@ -213,6 +213,15 @@ class GpuIndex:
         b = C.c_int64(0)
         N.check(N.load().jv_index_debug_counter(self.handle, 200, C.addressof(b)))
 
+    def exact_tc_counters(self):
+        """(brute-force batches answered by the tensor-core path, batches handed back to the fp32 kernel after an overflow)."""
+        b = C.c_int64(0)
+        out = []
+        for which in (4, 5):
+            N.check(N.load().jv_index_debug_counter(self.handle, which, C.addressof(b)))
+            out.append(int(b.value))
+        return tuple(out)
+
     PHASES = ("setup", "table_build", "select", "neighbour_rows", "scoring", "merge", "emit", "steps",
               "sub_code_words", "sub_lookups", "sub_offers", "sub_11", "sub_12", "sub_13", "sub_14", "sub_15")
 
