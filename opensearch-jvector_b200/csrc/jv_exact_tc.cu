@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kTcSelThreads)
 tc_select_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_norm, const int32_t *__restrict__ ord_to_doc, int dim,
                  int sim, float mul, const float *__restrict__ queries, int k, const unsigned long long *__restrict__ cand,
                  const int *__restrict__ cand_count, const float *__restrict__ eps, int32_t *__restrict__ out_doc,
-                 float *__restrict__ out_score, int32_t *__restrict__ out_count, int *__restrict__ overflow) {
+                 float *__restrict__ out_score, int32_t *__restrict__ out_count, int *__restrict__ overflow, int *__restrict__ ovf_q) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     float *sq = reinterpret_cast<float *>(sel_smem);
     uint64_t *keys = reinterpret_cast<uint64_t *>(sel_smem + ((((size_t)dim * 4) + 15) & ~(size_t)15)); // [kTcCap2]
@@ -338,7 +338,10 @@ tc_select_kernel(const float *__restrict__ vectors, const float *__restrict__ ve
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = cand_count[q];
     if (total > kTcCap) {
-        if (tid == 0) atomicExch(overflow, 1);
+        if (tid == 0) {
+            atomicAdd(overflow, 1);
+            ovf_q[q] = 1;
+        }
         return;
     }
     const unsigned long long *cq = cand + (int64_t)q * kTcCap;
@@ -376,7 +379,10 @@ tc_select_kernel(const float *__restrict__ vectors, const float *__restrict__ ve
     __syncthreads();
     const int n2 = s_n2;
     if (n2 > kTcCap2) {
-        if (tid == 0) atomicExch(overflow, 1);
+        if (tid == 0) {
+            atomicAdd(overflow, 1);
+            ovf_q[q] = 1;
+        }
         return;
     }
     const bool vec4 = (dim & 3) == 0 && (reinterpret_cast<uintptr_t>(vectors) & 15) == 0;
@@ -504,7 +510,8 @@ static int32_t tc_launch_gemm(jv_index *ix, cudaStream_t stream, const CUtensorM
     return JV_OK;
 }
 
-// returns JV_OK with *done = false when a candidate list overflowed (the caller falls back to the fp32 kernel)
+// returns JV_OK with *done = false when many candidate lists overflowed (the caller answers the whole batch with the fp32 kernel);
+// a few overflowing queries are re-answered by the fp32 kernel here
 int32_t launch_exact_topk_tc(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int32_t *d_out_doc, float *d_out_score,
                              int32_t *d_out_count, int *launches, bool *done) {
     *done = false;
@@ -527,16 +534,16 @@ int32_t launch_exact_topk_tc(jv_index *ix, SearchCtx *ctx, const float *d_querie
         const int nqp = (nqb + kTcBM - 1) / kTcBM * kTcBM;
         const float *dq = d_queries + (int64_t)q0 * ix->dim;
         JV_TRY(ctx->tc_q.ensure((size_t)nqp * Dp * 2));
-        JV_TRY(ctx->tc_f.ensure((size_t)nqb * 12 + 16)); // qnorm2 | thr | eps | overflow flag
+        JV_TRY(ctx->tc_f.ensure((size_t)nqb * 16 + 16)); // qnorm2 | thr | eps | per-query overflow flags | overflow count
         JV_TRY(ctx->tc_chunk.ensure((size_t)nqb * nchunks * 4));
         JV_TRY(ctx->tc_cand.ensure((size_t)nqb * kTcCap * 8));
         JV_TRY(ctx->tc_cnt.ensure((size_t)nqb * 4));
         float *qn2 = ctx->tc_f.as<float>(), *thr = qn2 + nqb, *eps = thr + nqb;
-        int *ovf = reinterpret_cast<int *>(eps + nqb);
+        int *ovf_q = reinterpret_cast<int *>(eps + nqb), *ovf = ovf_q + nqb;
         tc_convert_queries_kernel<<<(nqp + 7) / 8, 256, 0, st>>>(dq, nqb, nqp, ix->dim, Dp, ctx->tc_q.as<__nv_bfloat16>(), qn2);
         JV_CUDA_TRY(cudaGetLastError());
         JV_CUDA_TRY(cudaMemsetAsync(ctx->tc_cnt.p, 0, (size_t)nqb * 4, st));
-        JV_CUDA_TRY(cudaMemsetAsync(ovf, 0, 4, st));
+        JV_CUDA_TRY(cudaMemsetAsync(ovf_q, 0, (size_t)nqb * 4 + 4, st));
         CUtensorMap tmA, tmS, tmB;
         JV_TRY(tc_make_map(&tmA, ctx->tc_q.p, nqp, Dp, (int64_t)Dp * 2, kTcBM));
         JV_TRY(tc_make_map(&tmS, ix->tc_base.p, n_sample, Dp, (int64_t)Dp * 2 * stride, kTcBN));
@@ -566,15 +573,38 @@ int32_t launch_exact_topk_tc(jv_index *ix, SearchCtx *ctx, const float *d_querie
         JV_CUDA_TRY(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_select_kernel<<<nqb, kTcSelThreads, smem, st>>>(ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, mul, dq, k,
                                                            p.cand, p.cand_count, eps, d_out_doc + (int64_t)q0 * k, d_out_score + (int64_t)q0 * k,
-                                                           d_out_count + q0, ovf);
+                                                           d_out_count + q0, ovf, ovf_q);
         JV_CUDA_TRY(cudaGetLastError());
         int h_ovf = 0;
         JV_CUDA_TRY(cudaMemcpyAsync(&h_ovf, ovf, 4, cudaMemcpyDeviceToHost, st));
         JV_CUDA_TRY(cudaStreamSynchronize(st));
         if (launches) *launches += 5;
-        if (h_ovf) { // *done stays false: the whole batch goes to the fp32 kernel
-            ix->tc_fallbacks++;
-            return JV_OK;
+        if (h_ovf) {
+            // queries whose candidate list overflowed (thousands of vectors within 2 eps of the k-th best: adversarial or degenerate
+            // data) are answered by the fp32 kernel, one by one when they are few, the whole batch otherwise
+            ix->tc_fallbacks += h_ovf;
+            if (h_ovf > nqb / 8 + 16) return JV_OK; // *done stays false
+            std::vector<int> flags((size_t)nqb);
+            JV_CUDA_TRY(cudaMemcpyAsync(flags.data(), ovf_q, (size_t)nqb * 4, cudaMemcpyDeviceToHost, st));
+            JV_CUDA_TRY(cudaStreamSynchronize(st));
+            std::vector<int> redo;
+            for (int i = 0; i < nqb; i++)
+                if (flags[i]) redo.push_back(i);
+            const size_t r = redo.size();
+            JV_TRY(ctx->tc_redo.ensure(r * ((size_t)ix->dim * 4 + (size_t)k * 8 + 4)));
+            float *rq = ctx->tc_redo.as<float>();
+            int32_t *rd = reinterpret_cast<int32_t *>(rq + r * ix->dim);
+            float *rs = reinterpret_cast<float *>(rd + r * k);
+            int32_t *rc = reinterpret_cast<int32_t *>(rs + r * k);
+            for (size_t j = 0; j < r; j++)
+                JV_CUDA_TRY(cudaMemcpyAsync(rq + j * ix->dim, dq + (int64_t)redo[j] * ix->dim, (size_t)ix->dim * 4, cudaMemcpyDeviceToDevice, st));
+            JV_TRY(launch_exact_topk_fp32(ix, ctx, rq, (int)r, k, nullptr, 0, rd, rs, rc, launches));
+            for (size_t j = 0; j < r; j++) {
+                const int64_t q = (int64_t)q0 + redo[j];
+                JV_CUDA_TRY(cudaMemcpyAsync(d_out_doc + q * k, rd + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st));
+                JV_CUDA_TRY(cudaMemcpyAsync(d_out_score + q * k, rs + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st));
+                JV_CUDA_TRY(cudaMemcpyAsync(d_out_count + q, rc + j, 4, cudaMemcpyDeviceToDevice, st));
+            }
         }
     }
     ix->tc_batches++;

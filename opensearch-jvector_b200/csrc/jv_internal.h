@@ -17,7 +17,7 @@ struct SearchCtx {
     DevBuf visited;                   // global visited tables (fallback when they do not fit in smem)
     DevBuf lut8, qparams;             // 8-bit ADC tables of the current chunk + per-query (delta, base, ||q||^2)
     DevBuf slice_doc, slice_score;    // brute force: per-slice partial top-k
-    DevBuf tc_q, tc_f, tc_chunk, tc_cand, tc_cnt; // brute force on the tensor cores (jv_exact_tc.cu): bf16 queries, per-query floats,
+    DevBuf tc_q, tc_f, tc_chunk, tc_cand, tc_cnt, tc_redo; // brute force on the tensor cores (jv_exact_tc.cu): bf16 queries, per-query floats,
                                       // pass-A chunk maxima, pass-B candidates + counts
     bool lut_timed = false;           // ev[5] was recorded after the first chunk's table build
     int last_width = 0, last_kernel = 0; // what the last traversal launch used (jv_batch_timing)
@@ -129,6 +129,9 @@ int32_t launch_exact_topk(jv_index *ix, SearchCtx *ctx, const float *d_queries, 
                           int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
                           int *launches);
 
+int32_t launch_exact_topk_fp32(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, const uint64_t *d_accept,
+                               int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
+                               int *launches);
 // K5 on the tensor cores (jv_exact_tc.cu): *done = false -> a candidate list overflowed, use the fp32 kernel
 bool exact_tc_eligible(const jv_index *ix, int nq, int k, const uint64_t *d_accept);
 int32_t launch_exact_topk_tc(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int32_t *d_out_doc, float *d_out_score,

@@ -413,6 +413,14 @@ int32_t launch_exact_topk(jv_index *ix, SearchCtx *ctx, const float *d_queries, 
         JV_TRY(launch_exact_topk_tc(ix, ctx, d_queries, nq, k, d_out_doc, d_out_score, d_out_count, launches, &done));
         if (done) return JV_OK;
     }
+    return launch_exact_topk_fp32(ix, ctx, d_queries, nq, k, d_accept, accept_stride_words, d_out_doc, d_out_score, d_out_count, launches);
+}
+
+// the plain fp32 kernel: every (query, vector) pair through the canonical reduction
+int32_t launch_exact_topk_fp32(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, const uint64_t *d_accept,
+                               int64_t accept_stride_words, int32_t *d_out_doc, float *d_out_score, int32_t *d_out_count,
+                               int *launches) {
+    if (nq <= 0) return JV_OK;
     const int dim = ix->dim;
     const int nch = (dim + 127) / 128;
     const bool fast = (dim & 3) == 0 && nch <= 16 && ((reinterpret_cast<uintptr_t>(d_queries) & 15) == 0);
