@@ -57,8 +57,10 @@ typedef enum jv_status {
 } jv_status;
 
 /* ---- similarity ordinals --------------------------------------------
- * Same ordinals as the meta file's simOrd, JVectorReader.java:389-394
- * (VectorSimilarityMapper.JVECTOR_SUPPORTED_SIMILARITY_FUNCTIONS):
+ * = the ordinals of Lucene's VectorSimilarityFunction (FieldInfo.getVectorSimilarityFunction().ordinal()).  The meta file's
+ * simOrd (JVectorReader.java:389-409: distFuncToOrd = indexOf in [EUCLIDEAN, DOT_PRODUCT, COSINE, DOT_PRODUCT]) is 0, 1 or 2:
+ * a MAXIMUM_INNER_PRODUCT field is stored as 1, so the loader needs FieldInfo to tell MIP from DOT
+ * (jv_segment_set_lucene_similarity).
  *   0 EUCLIDEAN  score = 1/(1+||a-b||^2)
  *   1 DOT        score = (1+a.b)/2
  *   2 COSINE     score = (1+cos)/2
@@ -329,7 +331,8 @@ typedef struct jv_field_meta {        /* one VectorIndexFieldMetadata record */
     int32_t struct_size;              /* = sizeof(jv_field_meta), set by the caller */
     int32_t field_number;
     int32_t vector_encoding;          /* Lucene VectorEncoding ordinal: 0 BYTE, 1 FLOAT32 */
-    int32_t similarity;               /* JV_SIM_* (the record's simOrd, JVectorReader.java:389-394) */
+    int32_t similarity;               /* JV_SIM_*: the record's simOrd (0..2; MIP fields read 1 = DOT) until
+                                       * jv_segment_set_lucene_similarity() overrides it from FieldInfo */
     int32_t dim;
     int32_t quantization_type;        /* 0 none, 1 PQ, 2 NVQ-inline (JVectorIndexQuantization.QUANTIZATION_TYPE_*) */
     int64_t index_offset, index_length; /* OnDiskGraphIndex bytes inside the field data file */
@@ -347,6 +350,10 @@ JV_API int32_t jv_segment_open(const char *meta_path, uint32_t flags, jv_segment
 JV_API int32_t jv_segment_close(jv_segment *segment);
 JV_API int32_t jv_segment_field_count(const jv_segment *segment, int32_t *out_count);
 JV_API int32_t jv_segment_field_meta(const jv_segment *segment, int32_t i, jv_field_meta *out_meta);
+/* FieldInfo.getVectorSimilarityFunction() of field i (JV_SIM_* = the Lucene enum ordinal).  Needed for MAXIMUM_INNER_PRODUCT
+ * fields, whose meta record says DOT_PRODUCT: the x2 wrap of the un-quantised traversal and of the brute-force scorer
+ * (JVectorReader.java:220-239, JVectorVectorScorer.java:43-50) depends on it.  Fails when it contradicts the record. */
+JV_API int32_t jv_segment_set_lucene_similarity(jv_segment *segment, int32_t i, int32_t lucene_similarity);
 /* ordinal -> Lucene docId, -1 for deleted ordinals; capacity >= graph_nodes */
 JV_API int32_t jv_segment_field_doc_map(const jv_segment *segment, int32_t i, int32_t *out_ord_to_doc, int32_t capacity);
 JV_API int32_t jv_segment_load_field(const jv_segment *segment, int32_t i, const char *field_data_path, uint32_t flags,

@@ -34,7 +34,7 @@ PQ_LLOYD_ITERATIONS = 6
 
 
 class VectorSimilarityFunction(enum.Enum):
-    """Lucene's enum; `.jvector_ord` is the meta-file simOrd (JVectorReader.java:389-394)."""
+    """Lucene's enum (same ordinals as JV_SIM_*); `.meta_ord` is the meta-file simOrd (JVectorReader.java:389-409)."""
 
     EUCLIDEAN = N.SIM_EUCLIDEAN
     DOT_PRODUCT = N.SIM_DOT
@@ -43,7 +43,14 @@ class VectorSimilarityFunction(enum.Enum):
 
     @property
     def jvector_ord(self) -> int:
+        """JV_SIM_* of the library = Lucene's enum ordinal."""
         return self.value
+
+    @property
+    def meta_ord(self) -> int:
+        """simOrd of the meta record: VectorSimilarityMapper.distFuncToOrd (JVectorReader.java:407-413) = indexOf in
+        [EUCLIDEAN, DOT_PRODUCT, COSINE, DOT_PRODUCT], so MAXIMUM_INNER_PRODUCT is written as 1."""
+        return N.SIM_DOT if self is VectorSimilarityFunction.MAXIMUM_INNER_PRODUCT else self.value
 
 
 def default_num_subspaces(original_dimension: int) -> int:
@@ -375,12 +382,13 @@ class JVectorReader:
                 device=device, flags=flags)
 
     @classmethod
-    def open(cls, directory, field_infos: Dict[int, str], segment_name: str = "_0", segment_suffix: str = "JVector_0",
+    def open(cls, directory, field_infos: Dict[int, object], segment_name: str = "_0", segment_suffix: str = "JVector_0",
              device: int = 0, flags: int = 0, load_flags: int = 0) -> "JVectorReader":
         """JVectorReader(SegmentReadState), JVectorReader.java:52-81: read the meta file, then one FieldEntry per record
         (:255-337) — here a single native call per field (jv_segment_index_create) that parses the field data file and
         copies graph, vectors, PQ codebooks + codes and doc map to the device.  `field_infos` maps Lucene field numbers to
-        names (FieldInfos lives outside this codec)."""
+        names, or to (name, VectorSimilarityFunction) pairs (FieldInfos lives outside this codec).  The pair form is REQUIRED for
+        MAXIMUM_INNER_PRODUCT fields: their meta record says DOT_PRODUCT (distFuncToOrd) and only FieldInfo knows better."""
         from pathlib import Path as _Path
 
         from .segment_files import META_EXTENSION, SegmentFiles, field_data_file_name, segment_file_name
@@ -392,6 +400,9 @@ class JVectorReader:
         try:
             for i, m in enumerate(self._seg_files.metas):
                 name = field_infos[m.field_number]
+                if isinstance(name, tuple):
+                    name, lucene_sim = name
+                    self._seg_files.set_lucene_similarity(i, lucene_sim.jvector_ord)
                 path = directory / field_data_file_name(segment_name, segment_suffix, name)
                 self._entries[name] = self._seg_files.index_create(i, path, device, flags, load_flags)
                 self._files[name] = (i, path)

@@ -471,7 +471,12 @@ int32_t jv_segment_open(const char *meta_path, uint32_t flags, jv_segment **out)
         if (map_version != DOC_MAP_VERSION) JV_CORRUPT("Unsupported version: %d", map_version);
         if (m.field_number != number) JV_CORRUPT("%s: field number %d repeated as %d", meta_path, number, m.field_number);
         if (m.vector_encoding < 0 || m.vector_encoding > 1) JV_CORRUPT("Invalid vector encoding id: %d", m.vector_encoding);
-        if (m.similarity < JV_SIM_EUCLIDEAN || m.similarity > JV_SIM_MIP) JV_CORRUPT("invalid distance function: %d", m.similarity);
+        // simOrd indexes JVECTOR_SUPPORTED_SIMILARITY_FUNCTIONS = [EUCLIDEAN, DOT_PRODUCT, COSINE, DOT_PRODUCT] (JVectorReader.java:389-394):
+        // distFuncToOrd writes indexOf(...) so MAXIMUM_INNER_PRODUCT fields are stored as 1 and ordinal 3 never appears on disk; a
+        // 3 would still resolve to DOT_PRODUCT (ordToDistFunc).  Whether the field is MAXIMUM_INNER_PRODUCT is FieldInfo's knowledge:
+        // jv_segment_set_lucene_similarity().
+        if (m.similarity < 0 || m.similarity > 3) JV_CORRUPT("invalid distance function: %d", m.similarity);
+        if (m.similarity == 3) m.similarity = JV_SIM_DOT;
         if (m.quantization_type < 0 || m.quantization_type > 2) JV_CORRUPT("unknown quantization type %d", m.quantization_type);
         m.graph_nodes = c.vint();
         m.max_doc = c.vint();
@@ -509,6 +514,19 @@ int32_t jv_segment_field_meta(const jv_segment *segment, int32_t i, jv_field_met
     JV_REQUIRE(i >= 0 && i < (int32_t)segment->fields.size(), "field index %d out of range", i);
     JV_REQUIRE(out_meta->struct_size == (int32_t)sizeof(jv_field_meta), "jv_field_meta.struct_size mismatch");
     *out_meta = segment->fields[(size_t)i].meta;
+    return JV_OK;
+}
+
+int32_t jv_segment_set_lucene_similarity(jv_segment *segment, int32_t i, int32_t lucene_similarity) {
+    JV_REQUIRE(segment != nullptr, "segment is NULL");
+    JV_REQUIRE(i >= 0 && i < (int32_t)segment->fields.size(), "field index %d out of range", i);
+    JV_REQUIRE(lucene_similarity >= JV_SIM_EUCLIDEAN && lucene_similarity <= JV_SIM_MIP, "invalid distance function: %d", lucene_similarity);
+    jv_field_meta &m = segment->fields[(size_t)i].meta;
+    const int32_t stored = m.similarity == JV_SIM_MIP ? JV_SIM_DOT : m.similarity; // what the meta record said
+    const int32_t expect = lucene_similarity == JV_SIM_MIP ? JV_SIM_DOT : lucene_similarity;
+    JV_REQUIRE(stored == expect, "field %d: FieldInfo similarity %d does not match the meta record's distance function %d", m.field_number,
+               lucene_similarity, stored);
+    m.similarity = lucene_similarity;
     return JV_OK;
 }
 

@@ -92,6 +92,7 @@ SYMBOLS = {
     "jv_segment_field_count": (_I32, [_P, _P]),
     "jv_segment_field_meta": (_I32, [_P, _I32, _P]),
     "jv_segment_field_doc_map": (_I32, [_P, _I32, _P, _I32]),
+    "jv_segment_set_lucene_similarity": (_I32, [_P, _I32, _I32]),
     "jv_segment_load_field": (_I32, [_P, _I32, C.c_char_p, C.c_uint32, _P]),
     "jv_field_data_desc": (_I32, [_P, _P]),
     "jv_field_data_free": (_I32, [_P]),

@@ -208,7 +208,7 @@ def write_segment(segment, directory, segment_name: str = "_0", suffix: str = "J
         paths[name] = path
         qtype = QUANTIZATION_TYPE_PQ if pl else QUANTIZATION_TYPE_NONE
         meta.write(struct.pack("<i", number))                              # writeField, :299-300
-        rec = struct.pack("<iii", number, 1, fd.similarity.jvector_ord)    # toOutput, :528-540 (VectorEncoding.FLOAT32 = 1)
+        rec = struct.pack("<iii", number, 1, fd.similarity.meta_ord)       # toOutput, :528-540 (VectorEncoding.FLOAT32 = 1; MIP -> 1)
         rec += _vint(fd.vectors.shape[1]) + _vlong(io) + _vlong(il) + _vlong(po) + _vlong(pl)
         if version >= VERSION_WITH_QUANTIZATION_TYPE:
             rec += bytes([qtype])
@@ -245,6 +245,11 @@ class SegmentFiles:
             if m.field_number == field_number:
                 return i
         raise KeyError(field_number)
+
+    def set_lucene_similarity(self, i: int, lucene_similarity: int) -> None:
+        """FieldInfo.getVectorSimilarityFunction() of field i (needed for MAXIMUM_INNER_PRODUCT, stored as DOT_PRODUCT)."""
+        N.check(N.load().jv_segment_set_lucene_similarity(self._h, i, int(lucene_similarity)))
+        self.metas[i].similarity = int(lucene_similarity)
 
     def doc_map(self, i: int) -> np.ndarray:
         out = np.empty(self.metas[i].graph_nodes, dtype=np.int32)

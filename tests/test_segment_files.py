@@ -108,7 +108,12 @@ def test_two_fields_and_empty_doc_map_edge(jv, tmp_path):
     b = _segment(jv, seed=3, n=1500, dim=10, R=16, m=4, sim=V.MAXIMUM_INNER_PRODUCT, centroid=False, deleted=(0, 1499))
     paths = jv.JVectorWriter.write(jv.Segment(1550, {"a": a, "b": b}), tmp_path, field_numbers={"a": 0, "b": 9})
     with SF.SegmentFiles(paths["meta"]) as s:
-        assert [m.field_number for m in s.metas] == [0, 9] and [m.similarity for m in s.metas] == [0, 3]
+        # distFuncToOrd (JVectorReader.java:407-413) stores MAXIMUM_INNER_PRODUCT as 1 = DOT_PRODUCT: ordinal 3 is never on disk
+        assert [m.field_number for m in s.metas] == [0, 9] and [m.similarity for m in s.metas] == [0, 1]
+        with pytest.raises(ValueError):                         # FieldInfo says COSINE, the record says DOT_PRODUCT
+            s.set_lucene_similarity(1, V.COSINE.jvector_ord)
+        s.set_lucene_similarity(1, V.MAXIMUM_INNER_PRODUCT.jvector_ord)   # what FieldInfo knows
+        assert s.metas[1].similarity == 3
         _assert_same(s.load_field(0, paths["a"]), a)
         _assert_same(s.load_field(1, paths["b"]), b)
         with pytest.raises(jv.native.JVectorNativeError):       # field b's records do not match field a's file
