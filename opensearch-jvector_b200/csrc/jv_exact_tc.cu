@@ -92,6 +92,16 @@ constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k
                    "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                         \
                  : "r"(taddr))
 
+// pass B: (query q, column) reached the threshold
+__device__ __noinline__ void tc_append(unsigned long long *cand, int *cand_count, const int32_t *ord_to_doc, int64_t n_cols, int64_t col_stride, int q,
+                                       float s, int64_t cj) {
+    if (cj >= n_cols) return;
+    const int64_t ord = cj * col_stride;
+    if (ord_to_doc != nullptr && __ldg(ord_to_doc + ord) < 0) return; // deleted
+    const int slot = atomicAdd(cand_count + q, 1);
+    if (slot < kTcCap) cand[(int64_t)q * kTcCap + slot] = ((unsigned long long)jv_f2ord(s) << 32) | (unsigned long long)(uint32_t)ord;
+}
+
 // MODE 0: per-(query, 32 columns) maxima of the approximate scores (pass A).  MODE 1: append (approx score, ordinal) of every
 // column whose approximate score reaches thr[query] (pass B).  BIAS: add bias[ordinal] to the dot product (EUCLIDEAN).
 template <int MODE, bool BIAS>
@@ -184,7 +194,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
             const uint32_t tph = (uint32_t)(t >> 1) & 1u;
-            mbar_wait(&tfull[buf], tph);
+            if (lane == 0) mbar_wait(&tfull[buf], tph); // one lane polls, the warp follows
+            __syncwarp();
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < kTcBN / 32; c++) {
@@ -214,32 +225,12 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (qok && col < p.n_cols) p.chunkmax[(int64_t)q * p.nchunks + (col >> 5)] = m;
                 } else {
-                    bool any = false;
-                    float sv[32];
+                    // one compare + (rarely taken) branch per element: about one (query, vector) pair in a thousand is a candidate
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         float s = __uint_as_float(v[j]);
                         if (BIAS) s += __shfl_sync(JV_FULL_MASK, myb, j);
-                        sv[j] = s;
-                        any |= s >= thr;
-                    }
-                    if (any && qok) {
-#pragma unroll 1
-                        for (int j = 0; j < 32; j++) {
-                            // (the register array is indexed dynamically only on this rare path)
-                            float s = -INFINITY;
-#pragma unroll
-                            for (int jj = 0; jj < 32; jj++) s = jj == j ? sv[jj] : s;
-                            const int64_t cj = col + j;
-                            if (s >= thr && cj < p.n_cols) {
-                                const int64_t ord = cj * p.col_stride;
-                                if (p.ord_to_doc == nullptr || __ldg(p.ord_to_doc + ord) >= 0) {
-                                    const int slot = atomicAdd(p.cand_count + q, 1);
-                                    if (slot < kTcCap)
-                                        p.cand[(int64_t)q * kTcCap + slot] = ((unsigned long long)jv_f2ord(s) << 32) | (unsigned long long)(uint32_t)ord;
-                                }
-                            }
-                        }
+                        if (s >= thr && qok) tc_append(p.cand, p.cand_count, p.ord_to_doc, p.n_cols, p.col_stride, q, s, col + j);
                     }
                 }
             }
@@ -488,15 +479,20 @@ static int32_t tc_prepare_index(jv_index *ix, cudaStream_t stream) {
 template <int MODE>
 static int32_t tc_launch_gemm(jv_index *ix, cudaStream_t stream, const CUtensorMap &tmA, const CUtensorMap &tmB, TcParams &p, int nqp) {
     const int qtiles = nqp / kTcBM;
-    // slices: about two waves of CTAs, each a whole number of 256-column tiles
+    // slices: a whole number of 256-column tiles each; between 2 and 12 waves of CTAs, the count that fills its last wave best
     const int64_t tiles = (p.n_cols + kTcBN - 1) / kTcBN;
-    int64_t S = (2 * (int64_t)ix->sm_count + qtiles - 1) / qtiles;
-    if (S > tiles) S = tiles;
-    if (S < 1) S = 1;
-    if (S > 65535) S = 65535;
-    const int64_t tiles_per = (tiles + S - 1) / S;
+    const int sms = ix->sm_count;
+    int64_t best_S = 1;
+    double best_fill = -1.0;
+    for (int64_t S = 1; S <= tiles && S <= 65535 && S * qtiles <= (int64_t)12 * sms; S++) {
+        const int64_t tp = (tiles + S - 1) / S, Se = (tiles + tp - 1) / tp, ctas = Se * qtiles;
+        if (ctas < 2 * sms && S < tiles) continue;
+        const double fill = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        if (fill > best_fill + 1e-9) best_fill = fill, best_S = Se;
+    }
+    const int64_t tiles_per = (tiles + best_S - 1) / best_S;
     p.cols_per_cta = tiles_per * kTcBN;
-    S = (tiles + tiles_per - 1) / tiles_per;
+    const int64_t S = (tiles + tiles_per - 1) / tiles_per;
     const size_t smem = (size_t)kTcStages * kTcStageBytes + 256 + 1024;
     const dim3 grid((unsigned)qtiles, (unsigned)S);
     if (p.bias) {

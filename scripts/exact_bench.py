@@ -44,7 +44,7 @@ for name, env, slot in (("tensor_core", "1", 0), ("fp32", "0", 1)):
 res["tc_counters"] = gi.exact_tc_counters()
 res["ids_identical"] = bool((od[0] == od[1]).all().item())
 res["score_bits_identical"] = bool((os_[0].view(torch.int32) == os_[1].view(torch.int32)).all().item())
-res["contraction_tflops_tc"] = 2.0 * nq * n * dim * (1 + 1.0 / 150) / (res["tensor_core_ms"] * 1e-3) / 1e12
+res["contraction_tflops_tc"] = 2.0 * nq * n * dim * (1 + 1.0 / (160 // k)) / (res["tensor_core_ms"] * 1e-3) / 1e12  # pass B + the 1/stride sample of pass A
 res["workload"] = wl
 print(json.dumps(res), flush=True)
 gi.close()
