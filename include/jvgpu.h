@@ -304,6 +304,23 @@ JV_API int32_t jv_graph_remove_deleted_dev(int32_t device, const float *d_vector
                                     int32_t max_degree, float alpha, const int32_t *d_adjacency, const uint8_t *d_deleted,
                                     int32_t entry_node, int32_t *d_out_adjacency, int32_t *out_entry_node);
 
+/* ---- PQ decode + graph build with PQ build scores ------------------------------------------------------------------
+ * jv_pq_decode: ProductQuantization.decode — out[row] = concatenated centroids of the row's codes (+ global centroid).
+ * jv_graph_build_pq: GraphIndexBuilder driven by BuildScoreProvider.pqBuildScoreProvider (JVectorIndexQuantization.java:408,
+ * JVectorWriter.java:238-244 at flush, :1143-1151 when a merge rebuilds from scratch): every build-time score is a score between PQ
+ * reconstructions; the fp32 vectors are not read.  Same schedule, pruning and outputs as jv_graph_build. */
+JV_API int32_t jv_pq_decode(int32_t device, const uint8_t *codes, int64_t n, int32_t dim, int32_t m, int32_t k, const float *codebooks,
+                     const float *global_centroid, float *out_vectors);
+JV_API int32_t jv_pq_decode_dev(int32_t device, const uint8_t *d_codes, int64_t n, int32_t dim, int32_t m, int32_t k,
+                         const float *d_codebooks, const float *d_global_centroid, float *d_out_vectors);
+JV_API int32_t jv_graph_build_pq(int32_t device, const uint8_t *codes, int64_t n, int32_t dim, int32_t similarity, int32_t pq_m,
+                          int32_t pq_k, const float *codebooks, const float *global_centroid, int32_t max_degree,
+                          int32_t beam_width, float neighbor_overflow, float alpha, int32_t *out_adjacency, int32_t *out_entry_node);
+JV_API int32_t jv_graph_build_pq_dev(int32_t device, const uint8_t *d_codes, int64_t n, int32_t dim, int32_t similarity, int32_t pq_m,
+                              int32_t pq_k, const float *d_codebooks, const float *d_global_centroid, int32_t max_degree,
+                              int32_t beam_width, float neighbor_overflow, float alpha, int32_t *d_out_adjacency,
+                              int32_t *out_entry_node);
+
 /* ---- "next" row SURVEY 8f-1: segment-file loader ------------------------------------------------
  * Reads the files JVectorWriter persists straight into the decoded arrays of a jv_index_desc, so that
  * the Java side hands over two paths instead of extracting arrays through jVector's API:

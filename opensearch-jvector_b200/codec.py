@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import native as N
-from .index import GpuIndex, graph_build, graph_extend, graph_remove_deleted, make_accept_bits, pq_encode, pq_train
+from .index import GpuIndex, graph_build, graph_build_pq, graph_extend, graph_remove_deleted, make_accept_bits, pq_encode, pq_train
 
 # ---- constants (KNNConstants.java:83-114, JVectorFormat.java:22-35) -------------------------------
 DEFAULT_MAX_CONN = 32
@@ -276,13 +276,17 @@ class JVectorWriter:
             doc_map = GraphNodeIdToDocMap(f["docs"], max_doc)
             n = vecs.shape[0]
             fd = FieldData(sim, vecs, np.zeros((n, self.max_conn), np.int32), 0, doc_map)
-            if n > 0:
-                fd.adjacency, fd.entry_node = graph_build(vecs, sim.jvector_ord, self.max_conn, self.beam_width,
-                                                          self.neighbor_overflow, self.alpha, self.device)
-            if n >= self.min_batch:                                   # JVectorWriter.java:267-279
+            if n >= self.min_batch:                                   # JVectorWriter.java:267-279: quantise first ...
                 m = self.num_pq_subspaces(vecs.shape[1])
                 fd.pq_m, fd.pq_k, fd.pq_codebooks, fd.pq_global_centroid, fd.pq_codes = \
                     JVectorIndexQuantization.compute_pq_vectors(vecs, sim, m, self.device)
+                # ... then getGraph(quantizationResult.buildScoreProvider(), ..) (:238-244): PQ build scores
+                fd.adjacency, fd.entry_node = graph_build_pq(fd.pq_codes, vecs.shape[1], fd.pq_k, fd.pq_codebooks, fd.pq_global_centroid,
+                                                             sim.jvector_ord, self.max_conn, self.beam_width, self.neighbor_overflow,
+                                                             self.alpha, self.device)
+            elif n > 0:                                               # randomAccessScoreProvider (:274-278): exact build scores
+                fd.adjacency, fd.entry_node = graph_build(vecs, sim.jvector_ord, self.max_conn, self.beam_width,
+                                                          self.neighbor_overflow, self.alpha, self.device)
             seg.fields[name] = fd
         return seg
 
@@ -326,6 +330,7 @@ class JVectorWriter:
             out = FieldData(lead.similarity, vecs, np.zeros((n, self.max_conn), np.int32), 0, GraphNodeIdToDocMap(docs, merged.max_doc))
             n0 = lead.vectors.shape[0]
             sim_ord = lead.similarity.jvector_ord
+            rebuild = False                                           # no usable leading graph: build from scratch (below)
             if n > 0:
                 if n0 > 0 and lead_keep.any() and lead.adjacency.shape[1] == self.max_conn:
                     # heap ordinal space of the reference (:1240-1262): every leading node, deleted ones included, then the others
@@ -344,8 +349,7 @@ class JVectorWriter:
                         entry = int(to_final[entry])
                     out.adjacency, out.entry_node = np.ascontiguousarray(adj, np.int32), entry
                 else:
-                    out.adjacency, out.entry_node = graph_build(vecs, sim_ord, self.max_conn, self.beam_width,
-                                                                self.neighbor_overflow, self.alpha, self.device)
+                    rebuild = True
             if n > 0 and lead.pq_codes is not None:
                 # mergePQ, :1072-1124: the leading reader's codebooks are kept as they are ("We are not refining PQ codes on
                 # merge presently") and every merged vector is re-encoded with them: PQVectors.encodeAndBuild = K6
@@ -355,6 +359,14 @@ class JVectorWriter:
                 m = self.num_pq_subspaces(vecs.shape[1])
                 out.pq_m, out.pq_k, out.pq_codebooks, out.pq_global_centroid, out.pq_codes = \
                     JVectorIndexQuantization.compute_pq_vectors(vecs, lead.similarity, m, self.device)
+            if rebuild:
+                if out.pq_codes is not None:                          # "PQ codebooks found, building graph from scratch with PQ vectors", :1143-1151
+                    out.adjacency, out.entry_node = graph_build_pq(out.pq_codes, vecs.shape[1], out.pq_k, out.pq_codebooks, out.pq_global_centroid,
+                                                                   sim_ord, self.max_conn, self.beam_width, self.neighbor_overflow,
+                                                                   self.alpha, self.device)
+                else:                                                 # randomAccessScoreProvider, :1139-1141
+                    out.adjacency, out.entry_node = graph_build(vecs, sim_ord, self.max_conn, self.beam_width,
+                                                                self.neighbor_overflow, self.alpha, self.device)
             merged.fields[name] = out
         return merged
 

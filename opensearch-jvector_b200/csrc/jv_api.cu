@@ -719,6 +719,48 @@ int32_t jv_pq_encode(int32_t device, const float *vectors, int64_t n, int32_t di
     return JV_OK;
 }
 
+int32_t jv_pq_decode_dev(int32_t device, const uint8_t *d_codes, int64_t n, int32_t dim, int32_t m, int32_t k, const float *d_codebooks,
+                         const float *d_gcent, float *d_out_vectors) {
+    JV_REQUIRE(n >= 0 && dim >= 1 && m >= 1 && m <= dim && k >= 1 && k <= 256, "bad PQ shape");
+    if (n == 0) return JV_OK;
+    JV_REQUIRE(d_codes && d_codebooks && d_out_vectors, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    PqShape s;
+    s.init(dim, m, k);
+    JV_TRY(launch_pq_decode(nullptr, s, d_codes, n, d_codebooks, d_gcent, d_out_vectors));
+    JV_CUDA_TRY(cudaDeviceSynchronize());
+    return JV_OK;
+}
+
+int32_t jv_pq_decode(int32_t device, const uint8_t *codes, int64_t n, int32_t dim, int32_t m, int32_t k, const float *codebooks,
+                     const float *gcent, float *out_vectors) {
+    JV_REQUIRE(n >= 0 && dim >= 1 && m >= 1 && m <= dim && k >= 1 && k <= 256, "bad PQ shape");
+    if (n == 0) return JV_OK;
+    JV_REQUIRE(codes && codebooks && out_vectors, "NULL buffer");
+    JV_TRY(check_device(device));
+    DeviceGuard guard(device);
+    PqShape s;
+    s.init(dim, m, k);
+    DevBuf dcb, dg, dc, dout;
+    JV_TRY(dcb.alloc((size_t)s.cb_floats * 4));
+    JV_CUDA_TRY(cudaMemcpy(dcb.p, codebooks, (size_t)s.cb_floats * 4, cudaMemcpyHostToDevice));
+    if (gcent) {
+        JV_TRY(dg.alloc((size_t)dim * 4));
+        JV_CUDA_TRY(cudaMemcpy(dg.p, gcent, (size_t)dim * 4, cudaMemcpyHostToDevice));
+    }
+    const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, ((int64_t)1 << 30) / ((int64_t)dim * 4)));
+    JV_TRY(dc.alloc((size_t)chunk * m));
+    JV_TRY(dout.alloc((size_t)chunk * dim * 4));
+    for (int64_t o = 0; o < n; o += chunk) {
+        const int64_t cn = std::min(chunk, n - o);
+        JV_CUDA_TRY(cudaMemcpy(dc.p, codes + o * m, (size_t)cn * m, cudaMemcpyHostToDevice));
+        JV_TRY(launch_pq_decode(nullptr, s, dc.as<uint8_t>(), cn, dcb.as<float>(), dg.as<float>(), dout.as<float>()));
+        JV_CUDA_TRY(cudaMemcpy(out_vectors + o * dim, dout.p, (size_t)cn * dim * 4, cudaMemcpyDeviceToHost));
+    }
+    return JV_OK;
+}
+
 int32_t jv_pq_lut(jv_index *ix, const float *queries, int32_t nq, float *out_lut) {
     JV_REQUIRE(ix && queries && out_lut && nq >= 0, "bad arguments");
     JV_REQUIRE(ix->has_pq, "index has no PQ");

@@ -918,6 +918,60 @@ int32_t jv_graph_build(int32_t device, const float *vectors, int64_t n, int32_t 
     return JV_OK;
 }
 
+// Graph build with PQ build scores (BuildScoreProvider.pqBuildScoreProvider, JVectorWriter.java:238-244, 1143-1151): every score the
+// builder takes — search for a node's neighbours, diversity pruning, the approximate centroid — is a score between PQ
+// RECONSTRUCTIONS (the provider decodes node i and scores it against the codes of the others, never touching the fp32 vectors),
+// i.e. the exact builder run on decode(codes).  The reconstructions are made on the device and dropped afterwards.
+int32_t jv_graph_build_pq_dev(int32_t device, const uint8_t *d_codes, int64_t n, int32_t dim, int32_t similarity, int32_t pq_m, int32_t pq_k,
+                              const float *d_codebooks, const float *d_gcent, int32_t max_degree, int32_t beam_width,
+                              float neighbor_overflow, float alpha, int32_t *d_out_adjacency, int32_t *out_entry_node) {
+    JV_REQUIRE(d_codes && d_codebooks && d_out_adjacency && out_entry_node && n >= 1 && dim >= 1 && max_degree >= 1, "bad arguments");
+    JV_REQUIRE(pq_m >= 1 && pq_m <= dim && pq_k >= 1 && pq_k <= 256, "bad PQ shape");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) {
+        set_error("no usable CUDA device %d; libjvgpu has no CPU fallback", device);
+        return JV_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    PqShape s;
+    s.init(dim, pq_m, pq_k);
+    DevBuf dx;
+    JV_TRY(dx.alloc((size_t)n * dim * 4));
+    JV_TRY(launch_pq_decode(nullptr, s, d_codes, n, d_codebooks, d_gcent, dx.as<float>()));
+    JV_CUDA_TRY(cudaDeviceSynchronize());
+    return graph_build_dev_impl(device, dx.as<float>(), n, dim, similarity, max_degree, beam_width, neighbor_overflow, alpha,
+                                d_out_adjacency, out_entry_node);
+}
+
+int32_t jv_graph_build_pq(int32_t device, const uint8_t *codes, int64_t n, int32_t dim, int32_t similarity, int32_t pq_m, int32_t pq_k,
+                          const float *codebooks, const float *gcent, int32_t max_degree, int32_t beam_width, float neighbor_overflow,
+                          float alpha, int32_t *out_adjacency, int32_t *out_entry_node) {
+    JV_REQUIRE(codes && codebooks && out_adjacency && out_entry_node && n >= 1 && dim >= 1 && max_degree >= 1, "bad arguments");
+    JV_REQUIRE(pq_m >= 1 && pq_m <= dim && pq_k >= 1 && pq_k <= 256, "bad PQ shape");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) {
+        set_error("no usable CUDA device %d; libjvgpu has no CPU fallback", device);
+        return JV_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    PqShape s;
+    s.init(dim, pq_m, pq_k);
+    DevBuf dc, dcb, dg, dadj;
+    JV_TRY(dc.alloc((size_t)n * pq_m));
+    JV_TRY(dcb.alloc((size_t)s.cb_floats * 4));
+    JV_TRY(dadj.alloc((size_t)n * max_degree * 4));
+    JV_CUDA_TRY(cudaMemcpy(dc.p, codes, (size_t)n * pq_m, cudaMemcpyHostToDevice));
+    JV_CUDA_TRY(cudaMemcpy(dcb.p, codebooks, (size_t)s.cb_floats * 4, cudaMemcpyHostToDevice));
+    if (gcent) {
+        JV_TRY(dg.alloc((size_t)dim * 4));
+        JV_CUDA_TRY(cudaMemcpy(dg.p, gcent, (size_t)dim * 4, cudaMemcpyHostToDevice));
+    }
+    JV_TRY(jv_graph_build_pq_dev(device, dc.as<uint8_t>(), n, dim, similarity, pq_m, pq_k, dcb.as<float>(), dg.as<float>(), max_degree,
+                                 beam_width, neighbor_overflow, alpha, dadj.as<int32_t>(), out_entry_node));
+    JV_CUDA_TRY(cudaMemcpy(out_adjacency, dadj.p, (size_t)n * max_degree * 4, cudaMemcpyDeviceToHost));
+    return JV_OK;
+}
+
 int32_t jv_graph_extend_dev(int32_t device, const float *d_vectors, int64_t n, int64_t n0, const int32_t *d_seed_adjacency,
                             int32_t seed_entry, int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width,
                             float neighbor_overflow, float alpha, int32_t *d_out_adjacency) {

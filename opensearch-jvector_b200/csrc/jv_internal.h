@@ -145,6 +145,9 @@ int32_t launch_merge_topk(cudaStream_t stream, int g, int nq, int k, const int32
 int32_t launch_pq_encode(cudaStream_t stream, const PqShape &shape, const float *d_vectors, int64_t n,
                          const float *d_codebooks, const float *d_gcent, uint8_t *d_out, int out_stride);
 
+int32_t launch_pq_decode(cudaStream_t stream, const PqShape &shape, const uint8_t *d_codes, int64_t n, const float *d_codebooks,
+                         const float *d_gcent, float *d_out);
+
 // K1 (test hook) + ADC on explicit pairs
 int32_t launch_pq_lut(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, float *d_lut);
 int32_t launch_adc_pairs(jv_index *ix, cudaStream_t stream, const float *d_queries, int nq, const int32_t *d_nodes,

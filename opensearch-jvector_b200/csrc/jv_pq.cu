@@ -122,6 +122,40 @@ encode_kernel_generic(const float *__restrict__ x, int64_t n, int dim, int M, in
     }
 }
 
+// PQ decode (ProductQuantization.decode): out[row][off_m + j] = C_m[code[row][m]][j] (+ global centroid, one fp32 add per element like
+// the CPU restatement).  One thread per output float; codebooks laid out [m][c][size_m] with jVector's sub-vector split.
+__global__ void pq_decode_kernel(const uint8_t *__restrict__ codes, int64_t n, int dim, int M, int K, int base, int rem,
+                                 const float *__restrict__ codebooks, const float *__restrict__ gcent, float *__restrict__ out) {
+    const int64_t total = n * dim;
+    const int wide = rem * (base + 1); // the first `rem` subspaces are one element wider
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / dim;
+        const int d = (int)(i - row * dim);
+        int m, j, size, off;
+        if (d < wide) {
+            m = d / (base + 1), j = d - m * (base + 1), size = base + 1, off = m * (base + 1);
+        } else {
+            const int r = d - wide;
+            m = rem + r / base, j = r - (r / base) * base, size = base, off = wide + (m - rem) * base;
+        }
+        const int c = codes[row * M + m];
+        float v = __ldg(codebooks + (int64_t)K * off + (int64_t)c * size + j);
+        if (gcent) v = __fadd_rn(v, __ldg(gcent + d));
+        out[i] = v;
+    }
+}
+
+int32_t launch_pq_decode(cudaStream_t stream, const PqShape &s, const uint8_t *d_codes, int64_t n, const float *d_codebooks,
+                         const float *d_gcent, float *d_out) {
+    if (n <= 0) return JV_OK;
+    const int64_t total = n * s.dim;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pq_decode_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_codes, n, s.dim, s.M, s.K, s.dim / s.M, s.dim % s.M, d_codebooks, d_gcent, d_out);
+    JV_CUDA_TRY(cudaGetLastError());
+    return JV_OK;
+}
+
 int32_t launch_pq_encode(cudaStream_t stream, const PqShape &s, const float *d_vectors, int64_t n, const float *d_codebooks,
                          const float *d_gcent, uint8_t *d_out, int out_stride) {
     if (n <= 0) return JV_OK;

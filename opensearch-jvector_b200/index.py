@@ -76,6 +76,32 @@ def graph_build(vectors, similarity: int, max_degree: int = 32, beam_width: int 
     return adj, int(entry.value)
 
 
+def pq_decode(codes, dim: int, k: int, codebooks, global_centroid=None, device: int = 0):
+    """ProductQuantization.decode on the GPU: reconstructions [n, dim] float32 of the code rows."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    n, m = c.shape
+    cb = _f32(codebooks)
+    g = _f32(global_centroid)
+    out = np.empty((n, dim), dtype=np.float32)
+    N.check(N.load().jv_pq_decode(device, _ptr(c), n, dim, m, k, _ptr(cb), _ptr(g), _ptr(out)))
+    return out
+
+
+def graph_build_pq(codes, dim: int, k: int, codebooks, global_centroid, similarity: int, max_degree: int = 32, beam_width: int = 100,
+                   neighbor_overflow: float = 1.2, alpha: float = 1.2, device: int = 0):
+    """GraphIndexBuilder with BuildScoreProvider.pqBuildScoreProvider on the GPU (JVectorWriter.java:238-244, 1143-1151): build
+    scores between PQ reconstructions.  Returns (adjacency[n, R] int32, entry_node)."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    n, m = c.shape
+    cb = _f32(codebooks)
+    g = _f32(global_centroid)
+    adj = np.empty((n, max_degree), dtype=np.int32)
+    entry = C.c_int32(0)
+    N.check(N.load().jv_graph_build_pq(device, _ptr(c), n, dim, similarity, m, k, _ptr(cb), _ptr(g), max_degree, beam_width,
+                                       neighbor_overflow, alpha, _ptr(adj), C.addressof(entry)))
+    return adj, int(entry.value)
+
+
 def graph_extend(vectors, seed_adjacency, seed_entry: int, similarity: int, beam_width: int = 100, neighbor_overflow: float = 1.2,
                  alpha: float = 1.2, device: int = 0):
     """Leading-segment merge, insert-only (JVectorWriter.java:1166-1341): ordinals [0, len(seed_adjacency)) keep their graph

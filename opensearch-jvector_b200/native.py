@@ -81,6 +81,10 @@ SYMBOLS = {
     "jv_merge_topk_stream": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "jv_pq_train": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
     "jv_pq_train_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _U64, _P, _P]),
+    "jv_pq_decode": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "jv_pq_decode_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "jv_graph_build_pq": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _F, _F, _P, _P]),
+    "jv_graph_build_pq_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _F, _F, _P, _P]),
     "jv_graph_build": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
     "jv_graph_build_dev": (_I32, [_I32, _P, _I64, _I32, _I32, _I32, _I32, _F, _F, _P, _P]),
     "jv_graph_extend": (_I32, [_I32, _P, _I64, _I64, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _P]),

@@ -140,6 +140,35 @@ def pq_encode(vectors, m: int, k: int, codebooks, gcent=None, threads: int = 0) 
     return out
 
 
+def pq_decode(codes, dim: int, k: int, codebooks, gcent=None) -> np.ndarray:
+    """ProductQuantization.decode (jVector 4.0.0-rc.9): the reconstruction of a code row is the concatenation of its centroids
+    (+ the global centroid, one fp32 add per element).  Sub-vector split of SURVEY A.3: size = dim // M, the first dim % M
+    subspaces one wider; codebooks laid out [m][c][size_m]."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    n, m = c.shape
+    cb = _f32(codebooks).ravel()
+    out = np.empty((n, dim), dtype=np.float32)
+    base, rem, off = dim // m, dim % m, 0
+    for j in range(m):
+        size = base + (1 if j < rem else 0)
+        book = cb[k * off:k * off + k * size].reshape(k, size)
+        out[:, off:off + size] = book[c[:, j]]
+        off += size
+    if gcent is not None:
+        out = (out + _f32(gcent).reshape(1, dim)).astype(np.float32)
+    return out
+
+
+def graph_build_pq(codes, dim: int, k: int, codebooks, gcent, sim: int, max_degree: int = 32, beam_width: int = 100,
+                   overflow: float = 1.2, alpha: float = 1.2, max_batch: int = 8192, frac: float = 0.02):
+    """Fixture builder with PQ build scores (BuildScoreProvider.pqBuildScoreProvider, JVectorWriter.java:238-244, 1143-1151): the
+    provider decodes node i and scores it against the codes of the other nodes, for the neighbour search, for the diversity
+    pruning and for the approximate centroid alike — every build-time score is a score between reconstructions, so the builder
+    runs on decode(codes).  (The summation order of the jar's ADC is not known here — un-vendored — hence the canonical order of
+    the exact builder; parity unpinned like the rest of the builder)"""
+    return graph_build(pq_decode(codes, dim, k, codebooks, gcent), sim, max_degree, beam_width, overflow, alpha, max_batch, frac)
+
+
 def pq_lut(sim: int, dim: int, m: int, k: int, codebooks, gcent, queries) -> np.ndarray:
     q = _f32(queries)
     cb = _f32(codebooks)

@@ -1,0 +1,56 @@
+"""Graph build with PQ build scores (JVectorWriter.java:238-244 at flush, :1143-1151 when a merge rebuilds):
+PQ decode and the PQ-scored builder on the GPU against the oracle, and the reference's quantised-flush recall floor through the
+writer mirror (KNNJVectorTests.java:1358-1403)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import clustered, recall
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sim,dim,m", [(O.SIM_EUCLIDEAN, 16, 8), (O.SIM_DOT, 64, 16), (O.SIM_COSINE, 26, 8)])
+def test_pq_decode_and_pq_scored_build_match_the_oracle(jv, sim, dim, m):
+    base, _ = clustered(3000, dim, 4, seed=dim, normalize=sim == O.SIM_DOT)
+    center = sim == O.SIM_EUCLIDEAN
+    cb, g = O.pq_train(base, m, 256, center=center, iters=4, seed=3)
+    codes = O.pq_encode(base, m, 256, cb, g)
+    want = O.pq_decode(codes, dim, 256, cb, g)
+    got = jv.pq_decode(codes, dim, 256, cb, g)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    wadj, wentry = O.graph_build_pq(codes, dim, 256, cb, g, sim, 16, 100)
+    gadj, gentry = jv.graph_build_pq(codes, dim, 256, cb, g, sim, 16, 100)
+    assert gentry == wentry
+    np.testing.assert_array_equal(gadj, wadj)
+    eadj, _ = O.graph_build(base, sim, 16, 100)          # the exact-score graph is a different graph
+    assert not np.array_equal(wadj, eadj)
+
+
+def test_quantised_flush_builds_with_pq_scores_and_keeps_the_recall_floor(jv):
+    """testJVectorKnnIndex_simpleCase_withQuantization (KNNJVectorTests.java:1358-1403): 1024 uniform 16-d vectors = exactly the
+    minimum batch for quantisation, EUCLIDEAN, one flush, k = 50, recall 1.0 +- 0.05."""
+    V = jv.VectorSimilarityFunction
+    rng = np.random.default_rng(42)
+    n, dim, k = 1024, 16, 50
+    vectors = rng.random((n, dim), dtype=np.float32)
+    target = np.zeros(dim, np.float32)
+    w = jv.JVectorWriter()
+    w.add_field("vec", V.EUCLIDEAN)
+    for i in range(n):
+        w.add_value("vec", i, vectors[i])
+    seg = w.flush(n)
+    fd = seg.fields["vec"]
+    assert fd.pq_codes is not None
+    # the flushed graph is the PQ-scored one (JVectorWriter.java:238-244), not the exact-score one
+    padj, pentry = jv.graph_build_pq(fd.pq_codes, dim, fd.pq_k, fd.pq_codebooks, fd.pq_global_centroid, V.EUCLIDEAN.jvector_ord, w.max_conn, w.beam_width)
+    np.testing.assert_array_equal(fd.adjacency, padj)
+    assert fd.entry_node == pentry
+    truth = np.argsort(((vectors - target) ** 2).sum(1), kind="stable")[:k]
+    reader = jv.JVectorReader(seg)
+    col = jv.JVectorKnnCollector(jv.TopKnnCollector(k), 0.0, 0.0, 5)
+    reader.search("vec", target, col)
+    found = np.array([sd.doc for sd in col.top_docs()], np.int64)
+    reader.close()
+    assert len(found) == k
+    assert recall(found[None, :], truth[None, :]) >= 0.95
