@@ -143,8 +143,9 @@ typedef struct jv_batch_timing {
     float d2h_ms;
     float total_ms;
     int32_t launches; /* kernels launched for this batch                               */
-    float lut_ms;     /* share of search_ms spent in the batched 8-bit table build (first chunk; 0 when the
-                         table build is fused into the traversal kernel)                  */
+    float lut_ms;     /* share of search_ms spent in the batched 8-bit table build (0 when the table build is fused
+                         into the traversal kernel).  jv_search_batch pipelines large host batches in chunks:
+                         search_ms / rerank_ms / lut_ms are then the FIRST chunk's, total_ms the whole batch's */
     int32_t expand_width_used; /* candidates expanded per step by the traversal kernel that ran (0: strict kernel)   */
     int32_t traversal_kernel;  /* JV_KERNEL_*: which traversal kernel served the batch                              */
 } jv_batch_timing;

@@ -165,6 +165,30 @@ int32_t jv_host_unregister(void *ptr) {
     return JV_OK;
 }
 
+// jv_index_create validation: the decoded arrays come from the caller, and a neighbour id, doc id or code
+// out of range would be an out-of-bounds device read later — which poisons the CUDA context of the whole JVM.  flags: 1 adjacency,
+// 2 ord_to_doc, 4 PQ code.
+__global__ void validate_index_kernel(const int32_t *__restrict__ adjacency, int64_t n, int R, const int32_t *__restrict__ ord_to_doc,
+                                      int max_doc, const uint8_t *__restrict__ codes, int code_stride, int M, int K, int *flags) {
+    int bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < n * R; i += stride) {
+        const int32_t nb = adjacency[i];
+        if (nb < -1 || nb >= n) bad |= 1;
+    }
+    if (ord_to_doc)
+        for (int64_t i = t0; i < n; i += stride) {
+            const int32_t d = ord_to_doc[i];
+            if (d < -1 || d >= max_doc) bad |= 2;
+        }
+    if (codes && K < 256)
+        for (int64_t i = t0; i < n * M; i += stride) {
+            const int64_t row = i / M;
+            if (codes[row * code_stride + (i - row * M)] >= K) bad |= 4;
+        }
+    if (bad) atomicOr(flags, bad);
+}
+
 int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
     JV_REQUIRE(desc != nullptr && out != nullptr, "desc/out is NULL");
     *out = nullptr;
@@ -189,6 +213,8 @@ int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
         }
     }
     JV_REQUIRE(d->n == 0 || (d->entry_node >= 0 && d->entry_node < d->n), "entry_node out of range");
+    JV_REQUIRE(d->max_doc >= 0 && (d->ord_to_doc != nullptr || d->n == 0 || (int64_t)d->max_doc >= d->n),
+               "max_doc %d is smaller than the %lld ordinals of an identity doc map", d->max_doc, (long long)d->n);
     const bool has_pq = d->pq_m > 0;
     if (has_pq) {
         JV_REQUIRE(d->pq_codes && d->pq_codebooks, "pq_codes/pq_codebooks are NULL");
@@ -330,6 +356,22 @@ int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
             ix->q8_ok = true;
         }
     }
+    if (n > 0) { // range checks on the device copies (dbg slot 3 is the scratch flag word; it is cleared again below)
+        int *vflags = ix->dbg.as<int>() + 3;
+        validate_index_kernel<<<ix->sm_count * 4, 256>>>(ix->adjacency.as<int32_t>(), d->n, d->max_degree, ix->ord_to_doc.as<int32_t>(), d->max_doc,
+                                                         has_pq ? ix->codes.as<uint8_t>() : nullptr, ix->code_stride, d->pq_m, d->pq_k, vflags);
+        int h = 0;
+        if (cudaMemcpy(&h, vflags, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("index validation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(JV_ERR_CUDA);
+        }
+        cudaMemset(vflags, 0, 4);
+        if (h) {
+            set_error("jv_index_desc holds out-of-range data:%s%s%s", (h & 1) ? " adjacency (neighbour ids must be -1 or in [0, n))" : "",
+                      (h & 2) ? " ord_to_doc (doc ids must be -1 or in [0, max_doc))" : "", (h & 4) ? " pq_codes (codes must be < pq_k)" : "");
+            return fail(JV_ERR_INVALID_ARGUMENT);
+        }
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) {
         set_error("index creation kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(JV_ERR_CUDA);
@@ -410,6 +452,7 @@ static int32_t search_core(jv_index *ix, SearchCtx *c, const float *d_queries, i
     a.entry_override = -1;
     a.n_limit = ix->n;
     a.expand_width = p->expand_width;
+    c->time_lut = timed; // the table-build event (ev[5]) belongs to the chunk whose ev[1..3] are recorded
     if (timed) {
         c->lut_timed = false;
         JV_CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));

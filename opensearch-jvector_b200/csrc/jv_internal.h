@@ -20,6 +20,7 @@ struct SearchCtx {
     DevBuf tc_q, tc_f, tc_chunk, tc_cand, tc_cnt, tc_redo; // brute force on the tensor cores (jv_exact_tc.cu): bf16 queries, per-query floats,
                                       // pass-A chunk maxima, pass-B candidates + counts
     bool lut_timed = false;           // ev[5] was recorded after the first chunk's table build
+    bool time_lut = true;             // this launch is the timed chunk of a pipelined host batch
     int last_width = 0, last_kernel = 0; // what the last traversal launch used (jv_batch_timing)
     void *pinned = nullptr;           // host staging
     size_t pinned_bytes = 0;

@@ -943,7 +943,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
     for (int q0 = 0; q0 < a.nq; q0 += chunk) {
         const int nqc = a.nq - q0 < chunk ? a.nq - q0 : chunk;
         JV_TRY(launch_lut_q8(ix, ctx->stream, a.d_queries + (int64_t)q0 * ix->dim, nqc, ctx->lut8.as<uint8_t>(), ctx->qparams.as<float4>()));
-        if (q0 == 0) {
+        if (q0 == 0 && ctx->time_lut) {
             JV_CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
             ctx->lut_timed = true;
         }

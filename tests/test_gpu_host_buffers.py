@@ -49,3 +49,27 @@ def test_search_batch_from_allocated_registered_and_pageable_buffers(jv):
     bad = C.c_void_p()
     assert lib.jv_host_alloc(0, C.byref(bad)) != N.JV_OK              # zero bytes: invalid argument
     assert lib.jv_host_unregister(None) != N.JV_OK
+
+
+def test_index_create_rejects_out_of_range_arrays(jv):
+    """jv_index_create range-checks the caller's decoded arrays on the device (a bad id would be an out-of-bounds read later)."""
+    base, q = clustered(500, 16, 4, seed=2)
+    fx = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=8, pq_m=4, pq_k=64)
+    ok = fx.gpu_index(jv)
+    ok.close()
+    bad_adj = fx.adjacency.copy()
+    bad_adj[17, 3] = 500                                             # == n
+    with pytest.raises(ValueError, match="adjacency"):
+        jv.GpuIndex(fx.sim, fx.base, bad_adj, fx.entry, pq_m=fx.pq_m, pq_k=fx.pq_k, pq_codebooks=fx.codebooks, pq_global_centroid=fx.gcent,
+                    pq_codes=fx.codes)
+    bad_map = np.arange(500, dtype=np.int32)
+    bad_map[3] = 900
+    with pytest.raises(ValueError, match="ord_to_doc"):
+        jv.GpuIndex(fx.sim, fx.base, fx.adjacency, fx.entry, ord_to_doc=bad_map, max_doc=600)
+    bad_codes = fx.codes.copy()
+    bad_codes[5, 1] = 200                                            # >= K = 64
+    with pytest.raises(ValueError, match="pq_codes"):
+        jv.GpuIndex(fx.sim, fx.base, fx.adjacency, fx.entry, pq_m=fx.pq_m, pq_k=fx.pq_k, pq_codebooks=fx.codebooks, pq_global_centroid=fx.gcent,
+                    pq_codes=bad_codes)
+    with pytest.raises(ValueError, match="max_doc"):
+        jv.GpuIndex(fx.sim, fx.base, fx.adjacency, fx.entry, max_doc=10)
