@@ -54,3 +54,32 @@ def test_quantised_flush_builds_with_pq_scores_and_keeps_the_recall_floor(jv):
     reader.close()
     assert len(found) == k
     assert recall(found[None, :], truth[None, :]) >= 0.95
+
+
+def test_two_quantised_flushes_force_merged_keep_the_recall_floor(jv):
+    """testJVectorKnnIndex_happyCase_withQuantization_multipleSegments (KNNJVectorTests.java:1471-1530) through the writer mirror:
+    two flushes of exactly the minimum batch (each quantised, PQ-scored graph), force-merged (leading-segment merge + mergePQ with
+    the leading codebooks), k = 50, recall 1.0 +- 0.05."""
+    V = jv.VectorSimilarityFunction
+    dim, per, k = 16, 1024, 50
+    vectors = O.java_random_vectors(2 * per, dim, 1)
+    target = np.zeros(dim, np.float32)
+    segs = []
+    for s in range(2):
+        w = jv.JVectorWriter()
+        w.add_field("test_field", V.EUCLIDEAN)
+        for i in range(per):
+            w.add_value("test_field", i, vectors[s * per + i])
+        segs.append(w.flush(per))
+        assert segs[-1].fields["test_field"].pq_codes is not None
+    merged = jv.JVectorWriter().merge(segs)
+    fd = merged.fields["test_field"]
+    assert fd.vectors.shape[0] == 2 * per and fd.pq_codes is not None
+    np.testing.assert_array_equal(fd.pq_codebooks, segs[0].fields["test_field"].pq_codebooks)   # "not refining PQ codes on merge"
+    truth = np.argsort(((vectors - target) ** 2).sum(1), kind="stable")[:k]
+    reader = jv.JVectorReader(merged)
+    col = jv.JVectorKnnCollector(jv.TopKnnCollector(k), 0.0, 0.0, 5)
+    reader.search("test_field", target, col)
+    found = np.array([sd.doc for sd in col.top_docs()], np.int64)
+    reader.close()
+    assert len(found) == k and recall(found[None, :], truth[None, :]) >= 0.95

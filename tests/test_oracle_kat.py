@@ -328,3 +328,63 @@ def test_nvq_rerank_recall_floor_at_the_reference_seed():
     for i in range(5):
         for d, s in zip(docs[i], scores[i]):
             assert s == np.float32(O.exact_score(O.SIM_EUCLIDEAN, q[i], deq[d]))
+
+
+# ---- quantised flush builds its graph with PQ build scores (JVectorWriter.java:238-244): same recall floor as above through
+#      the PQ-scored builder (testJVectorKnnIndex_simpleCase_withQuantization, KNNJVectorTests.java:1358-1403) ----------------
+def test_pq_scored_build_recall_floor_reference_seed():
+    dim, n, k = 16, 1024, 50
+    base = O.java_random_vectors(n, dim, 1)
+    target = np.zeros((1, dim), np.float32)
+    m = O.default_num_subspaces(dim)
+    cb, g = O.pq_train(base, m, 256, center=True, iters=6, seed=7)
+    codes = O.pq_encode(base, m, 256, cb, g)
+    dec = O.pq_decode(codes, dim, 256, cb, g)
+    assert np.abs(dec - base).max() < np.abs(base).max()            # reconstructions, not the vectors
+    adj, entry = O.graph_build_pq(codes, dim, 256, cb, g, O.SIM_EUCLIDEAN, 32, 100)
+    ix = O.OracleIndex(O.SIM_EUCLIDEAN, base, adj, entry, pq_m=m, pq_k=256, pq_codebooks=cb, pq_global_centroid=g, pq_codes=codes)
+    docs, _, counts, _ = ix.search(target, k, k * 5)
+    gt, _, _ = ix.exact_topk(target, k)
+    assert counts[0] == k and recall(docs, gt) >= 0.95
+
+
+# ---- testJVectorKnnIndex_simpleCase_withQuantization_rerank (KNNJVectorTests.java:1409-1464): vectors (0, .., 0, i), i = 1..1024,
+#      k = 1; "recall" = the top document's score reaches the score of (0, .., 0, k); over-query 1 must not beat over-query 5 ----
+def test_quantization_rerank_reference_fixture():
+    dim, n, k = 16, 1024, 1
+    base = np.zeros((n, dim), np.float32)
+    base[:, -1] = np.arange(1, n + 1, dtype=np.float32)
+    target = np.zeros((1, dim), np.float32)
+    m = O.default_num_subspaces(dim)
+    cb, g = O.pq_train(base, m, 256, center=True, iters=6, seed=7)
+    codes = O.pq_encode(base, m, 256, cb, g)
+    adj, entry = O.graph_build_pq(codes, dim, 256, cb, g, O.SIM_EUCLIDEAN, 32, 100)
+    ix = O.OracleIndex(O.SIM_EUCLIDEAN, base, adj, entry, pq_m=m, pq_k=256, pq_codebooks=cb, pq_global_centroid=g, pq_codes=codes)
+    expected_min = 1.0 / (1.0 + float(k) ** 2)                      # EUCLIDEAN.compare(target, (0, .., 0, k))
+
+    def score_recall(over):
+        _, scores, counts, _ = ix.search(target, k, k * over)
+        assert counts[0] == k
+        return float(np.mean(scores[0, :k] >= expected_min - 1e-6))
+
+    low, high = score_recall(1), score_recall(5)
+    assert low <= high and high == 1.0
+
+
+# ---- testJVectorKnnIndex_happyCase_withQuantization_multipleSegments (KNNJVectorTests.java:1471-1530): two flushes of exactly the
+#      minimum batch, force-merged: leading-segment merge (exact scores, :1290) + mergePQ with the leading codebooks (:1072-1124) --
+def test_quantised_two_segment_merge_recall_floor():
+    dim, per, k = 16, 1024, 50
+    vectors = O.java_random_vectors(2 * per, dim, 1)
+    target = np.zeros((1, dim), np.float32)
+    m = O.default_num_subspaces(dim)
+    lead = vectors[:per]
+    cb, g = O.pq_train(lead, m, 256, center=True, iters=6, seed=7)
+    lead_codes = O.pq_encode(lead, m, 256, cb, g)
+    lead_adj, lead_entry = O.graph_build_pq(lead_codes, dim, 256, cb, g, O.SIM_EUCLIDEAN, 32, 100)     # flush of segment 0
+    adj = O.graph_extend(vectors, lead_adj, lead_entry, O.SIM_EUCLIDEAN, 100)                          # merge: insert segment 1
+    codes = O.pq_encode(vectors, m, 256, cb, g)                                                        # mergePQ: leading codebooks
+    ix = O.OracleIndex(O.SIM_EUCLIDEAN, vectors, adj, lead_entry, pq_m=m, pq_k=256, pq_codebooks=cb, pq_global_centroid=g, pq_codes=codes)
+    docs, _, counts, _ = ix.search(target, k, k * 5)
+    gt, _, _ = ix.exact_topk(target, k)
+    assert counts[0] == k and recall(docs, gt) >= 0.95
