@@ -42,6 +42,9 @@ WORKLOADS = {
     # the other BASELINE.json configs at a size that builds in seconds (parity / recall checks at scale, not bench lines)
     "cfg3-1Mx96-l2-pq48": dict(n=1_000_000, dim=96, sim=0, pq_m=48, R=32, k=10, over=5, nq=10_000, latent=32, clusters=4096),
     "cfg4-250kx1536-cos-pq192": dict(n=250_000, dim=1536, sim=2, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=1024),
+    # BASELINE.json configs[3] at full size: 1M x 1536 cosine, PQ 192 (sub-dim 8), 10 %-selectivity accept bitset over docIds (one
+    # bitset for the batch, like a filtered knn query), 5x over-query + exact rerank
+    "cfg4-1Mx1536-cos-pq192-filter10": dict(n=1_000_000, dim=1536, sim=2, pq_m=192, R=32, k=10, over=5, nq=10_000, latent=64, clusters=4096, filter=0.1),
     "cfg5-1Mx128-dot-pq64-k100": dict(n=1_000_000, dim=128, sim=1, pq_m=64, R=32, k=100, over=5, nq=10_000, latent=32, clusters=4096),
     # config 1 (the reference's own CPU-runnable case: 10k x 128 iid U[0,1) like TestUtils.java:108-120, cosine, NO PQ -> exact
     # traversal K4, M=16 beamWidth=100, k=10, 1k-query batch)
@@ -231,9 +234,29 @@ def cpu_arm(host, w, k, rk, nq, budget_s, steps, warmup, truth=None):
     m = w["pq_m"]
     ora = O.OracleIndex(w["sim"], host["base"], host["adj"], host["entry"], pq_m=m, pq_k=256 if m else 0, pq_codebooks=host["cb"],
                         pq_global_centroid=host.get("gcent"), pq_codes=host["codes"])
-    fast = O.SimdIndex(ora)
     cores = O.host_cores()
     q = host["queries"]
+    if host.get("accept_bits") is not None:  # filtered workload: the tuned build has no filtered loop, the checker does
+        bits = host["accept_bits"]
+        t0 = time.time()
+        ora.search(q[:128], k, rk, accept_bits=bits, threads=cores)
+        per_q = (time.time() - t0) / 128
+        sample = int(min(nq, max(128, budget_s / per_q)))
+        for _ in range(warmup):
+            ora.search(q[:sample], k, rk, accept_bits=bits, threads=cores)
+        t0 = time.time()
+        for _ in range(steps):
+            cd, _, _, cst = ora.search(q[:sample], k, rk, accept_bits=bits, threads=cores)
+        el = time.time() - t0
+        out = {"value": sample * steps / el, "unit": "queries/s", "cores": cores, "kind": "port", "ms_per_step": el / steps * 1e3,
+               "sample": f"{sample} of the {nq} queries per step, one query per OpenMP thread, same index and accept bitset; CPU restatement of "
+                         "jVector 4.0.0-rc.9, checker build (the tuned build has no filtered loop) — not the JVM",
+               "cpu_model": O.cpu_model(), "isa": "scalar ADC, -mavx2 auto-vectorised reductions", "one_thread_ms_per_query": None,
+               "checker_value": sample * steps / el, "visited_per_query": float(cst[:, 0].mean())}
+        if truth is not None:
+            out["recall_at_10"] = recall_at_k(cd, truth[:sample])
+        return out
+    fast = O.SimdIndex(ora)
     t0 = time.time()
     fast.search(q[:256], k, rk, threads=cores)
     per_q = (time.time() - t0) / 256
@@ -456,6 +479,12 @@ def main():
         dist.broadcast(d_queries, src=0)
         host["queries"] = d_queries.cpu().numpy()
 
+    # accept bitset of a filtered workload: Bernoulli over docIds, the same for every query of the batch (FixedBitSet words)
+    h_bits = d_bits = None
+    if w.get("filter"):
+        h_bits = jv.make_accept_bits(np.random.default_rng(3236 + rank).random(n_local) < w["filter"])
+        host["accept_bits"] = h_bits
+
     # ------------------------------------------------------------------------------------------ CPU arm
     if args.impl == "reference":
         base = cpu_arm(host, w, k, rk, nq, budget_s=1.5, steps=args.steps, warmup=args.warmup)
@@ -487,8 +516,11 @@ def main():
     gt_doc = torch.empty(nq, k, dtype=torch.int32, device=dev_t)
     gt_score = torch.empty(nq, k, dtype=torch.float32, device=dev_t)
     gt_cnt = torch.empty(nq, dtype=torch.int32, device=dev_t)
+    if h_bits is not None:
+        d_bits = torch.from_numpy(h_bits.view(np.int64)).to(dev_t)
+    bits_ptr = d_bits.data_ptr() if d_bits is not None else None
     t0 = time.time()
-    gi.exact_topk_dev(d_queries.data_ptr(), nq, k, gt_doc.data_ptr(), gt_score.data_ptr(), gt_cnt.data_ptr())  # ground truth (K5)
+    gi.exact_topk_dev(d_queries.data_ptr(), nq, k, gt_doc.data_ptr(), gt_score.data_ptr(), gt_cnt.data_ptr(), d_accept_bits=bits_ptr)  # ground truth (K5)
     log(f"exact ground truth for {nq} queries in {time.time() - t0:.2f}s")
     if args.host_vectors:  # same index, rerank vectors read over PCIe from pinned host memory
         torch.cuda.synchronize(local_rank)
@@ -514,7 +546,7 @@ def main():
 
     def step_dev():
         t = gi.search_dev(d_queries.data_ptr(), nq, k, rk, out_doc.data_ptr(), out_score.data_ptr(), out_count.data_ptr(), stats.data_ptr(),
-                          expand_width=args.expand_width)
+                          d_accept_bits=bits_ptr, expand_width=args.expand_width)
         if shards:
             _, _, kms = merge_shards(out_doc, out_score)
             t["merge_ms"] = kms
@@ -567,7 +599,7 @@ def main():
     h_score, h_score_p = N.host_alloc((nq, k), np.float32)
     h_cnt, h_cnt_p = N.host_alloc((nq,), np.int32)
     h_stats, h_stats_p = N.host_alloc((nq, 4), np.int32)
-    p = gi._params(k, rk, 0.0, 0.0, None, 0, args.expand_width)
+    p = gi._params(k, rk, 0.0, 0.0, h_bits.ctypes.data if h_bits is not None else None, 0, args.expand_width)  # host pointers here
 
     def step_e2e():
         N.check(lib.jv_search_batch(gi.handle, hq_p, nq, C.addressof(p), h_doc_p, h_score_p, h_cnt_p, h_stats_p, None))
@@ -658,6 +690,7 @@ def main():
                    "graph": f"Vamana R={R} beamWidth=100", "query_batch": nq, "layout": args.layout if world > 1 else "single",
                    "adc_table": args.adc_table, "expand_width": used_E, "traversal_kernel": KERNEL_NAMES.get(used_kernel, "?"),
                    "rerank_vectors": "pinned host memory" if args.host_vectors else "HBM",
+                   "filter_selectivity": w.get("filter"),
                    "l2": (f"index working set {gi.device_bytes() / 2**30:.2f} GiB >> 126 MB L2, no flush needed" if gi.device_bytes() > 4 * 126e6 else
                           f"index working set {gi.device_bytes() / 2**20:.1f} MiB fits the 126 MB L2 and is NOT flushed between steps: a hot "
                           "segment of this size is cache-resident in steady state (parity-scale workload, not a bench line)")},
@@ -666,7 +699,7 @@ def main():
         "visited_set_overflows": gi.visited_overflows(),
         # dominant kernel: the traversal (K2).  With the 8-bit table the table build (K1) is a separate launch whose time is
         # measured by its own event pair and reported next to it; the fp16/fp32 kernels fuse K1 into the traversal.
-        "roofline": {"bound": "hbm", "kernel": {3: "q8_beam_kernel (K2 beam search + ADC: 8-bit table staged with TMA, manager warp + scorer warps, 2 steps in flight)",
+        "roofline": {"bound": "hbm", "kernel": ("q8_search_kernel<FILT> (K2 beam search + ADC over accepted and rejected nodes, 8-bit table staged with TMA)" if h_bits is not None else None) or {3: "q8_beam_kernel (K2 beam search + ADC: 8-bit table staged with TMA, manager warp + scorer warps, 2 steps in flight)",
                                                 2: "q8_search_kernel (K2 beam search + ADC, 8-bit table staged with TMA, round-synchronous)"}.get(used_kernel)
                      or ("fast_search_kernel (K4 beam search with exact scores, un-quantised segment)" if m == 0
                          else "fast_search_kernel (K1 LUT + K2 beam search + ADC)"),
@@ -692,6 +725,8 @@ def main():
         "clocks": clocks.summary(),
     }
     # ---- the sharded machine (BASELINE.json configs[2] / [4]) in the same line: the headline above is the replicas layout
+    if h_bits is not None:
+        line["e2e"]["h2d_bytes_per_step"] += int(h_bits.nbytes)
     run_shards = (not args.no_shards and os.environ.get("JV_BENCH_SHARDS", "1") != "0" and args.layout == "replicas"
                   and args.workload == "cfg2-1Mx768-dot-pq192" and not args.host_vectors)
     if run_shards:

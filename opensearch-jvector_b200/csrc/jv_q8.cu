@@ -777,11 +777,14 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                     const int up = __shfl_up_sync(JV_FULL_MASK, v, o);
                     if (lane >= o) v += up;
                 }
+                uint32_t selmask = 0u; // the selected entries of this chunk (warp-uniform: nsel compares per chunk, not per entry)
+                for (int e = 0; e < nsel; e++) {
+                    const int d = w_pos[warp][e] - c0;
+                    if (d >= 0 && d < 32) selmask |= 1u << d;
+                }
                 if (t < n) {
                     uint64_t k = list[t];
-                    bool selected = false;
-                    for (int e = 0; e < nsel; e++) selected |= (w_pos[warp][e] == t);
-                    if (selected) k &= ~1ull;
+                    if ((selmask >> lane) & 1u) k &= ~1ull;
                     const int pos = t + offset + v;
                     if (pos < Lc) out[pos] = k;
                 }
