@@ -293,8 +293,8 @@ class JVectorWriter:
     def merge(self, segments: Sequence[Segment], live_docs: Optional[Sequence[Optional[np.ndarray]]] = None) -> Segment:
         """mergeOneField over whole segments (JVectorWriter.java:1040-1160): the merged segment holds the live documents of
         `segments` in order (docIds re-based like Lucene's MergeState doc maps: segment i starts after the live docs of the
-        segments before it).  The first segment is the LEADING one: its graph is kept, the other segments' live vectors are
-        inserted into it (tryLeadingSegmentMerge, :1166-1341 -> jv_graph_extend), its deleted nodes are consolidated away
+        segments before it).  Per field the segment with the most live vectors is the LEADING one (:784-848): its graph is kept, the
+        other segments' live vectors are inserted into it (tryLeadingSegmentMerge, :1166-1341 -> jv_graph_extend), its deleted nodes are consolidated away
         (markNodeDeleted + cleanup -> jv_graph_remove_deleted) and the ordinals are compacted as the on-disk writer does.  PQ: the
         leading segment's codebooks are reused and all merged vectors re-encoded (mergePQ, :1072-1124), or trained when it has none.
         `live_docs[i]`: bool mask over segment i's docIds (None = all live)."""
@@ -310,18 +310,36 @@ class JVectorWriter:
             bases.append(base)
             base += int(mask.sum())
         merged.max_doc = base
-        for name, lead in segments[0].fields.items():
-            vec_parts, doc_parts = [], []
-            lead_keep = None
+        names = []
+        for seg in segments:                         # the union of the segments' vector fields, first appearance first
+            for name in seg.fields:
+                if name not in names:
+                    names.append(name)
+        for name in names:
+            # the LEADING reader is the one with the most live vectors, ties -> the later one, and it is swapped (not rotated) to
+            # position 0 (JVectorWriter.java:784-848); docIds are still re-based in the original segment order (MergeState doc maps)
+            keeps = {}
             for si, seg in enumerate(segments):
                 fd = seg.fields.get(name)
                 if fd is None:
                     continue
                 ords = fd.doc_map.graph_node_ids_to_doc_ids
-                new_docs = np.where(ords >= 0, remap[si][np.maximum(ords, 0)], -1)
-                keep = new_docs >= 0
-                if si == 0:
-                    lead_keep = keep
+                new_docs = np.where(ords >= 0, remap[si][np.maximum(ords, 0)], -1) if len(ords) else np.zeros(0, np.int64)
+                keeps[si] = (fd, new_docs, new_docs >= 0)
+            if not keeps:
+                continue
+            lead_idx, lead_live = -1, -1
+            for si, (_, _, keep) in keeps.items():
+                if int(keep.sum()) >= lead_live:
+                    lead_idx, lead_live = si, int(keep.sum())
+            order = sorted(keeps)
+            pos = order.index(lead_idx)
+            order[0], order[pos] = order[pos], order[0]
+            lead = keeps[order[0]][0]
+            vec_parts, doc_parts = [], []
+            lead_keep = keeps[order[0]][2]
+            for si in order:
+                fd, new_docs, keep = keeps[si]
                 vec_parts.append(fd.vectors[keep])
                 doc_parts.append(new_docs[keep])
             vecs = np.concatenate(vec_parts).astype(np.float32)

@@ -83,3 +83,40 @@ def test_two_quantised_flushes_force_merged_keep_the_recall_floor(jv):
     found = np.array([sd.doc for sd in col.top_docs()], np.int64)
     reader.close()
     assert len(found) == k and recall(found[None, :], truth[None, :]) >= 0.95
+
+
+def test_merge_picks_the_segment_with_the_most_live_vectors_as_leading_and_keeps_every_field(jv):
+    """JVectorWriter.java:784-848: the leading reader is the one with the most live vectors (ties -> the later one), swapped to
+    position 0; docIds are re-based in the original segment order.  Fields missing from the first segment are not dropped."""
+    V = jv.VectorSimilarityFunction
+    rng = np.random.default_rng(12)
+    small, big = rng.random((60, 8), dtype=np.float32), rng.random((500, 8), dtype=np.float32)
+    extra = rng.random((40, 8), dtype=np.float32)
+
+    def flush(fields, n):
+        w = jv.JVectorWriter()
+        for name, vecs in fields.items():
+            w.add_field(name, V.EUCLIDEAN)
+            for i, v in enumerate(vecs):
+                w.add_value(name, i, v)
+        return w.flush(n)
+
+    s0, s1 = flush({"a": small}, 60), flush({"a": big, "b": extra}, 500)
+    merged = jv.JVectorWriter().merge([s0, s1])
+    assert set(merged.fields) == {"a", "b"} and merged.max_doc == 560
+    a = merged.fields["a"]
+    # leading = segment 1 (500 live vectors): its vectors come first in the merged ordinal space, with docIds 60..559
+    np.testing.assert_array_equal(a.vectors[:500], big)
+    np.testing.assert_array_equal(a.doc_map.graph_node_ids_to_doc_ids[:500], np.arange(60, 560))
+    np.testing.assert_array_equal(a.doc_map.graph_node_ids_to_doc_ids[500:], np.arange(0, 60))
+    # and the leading graph was kept: the first 500 rows still contain the leading segment's edges among themselves
+    lead_adj = s1.fields["a"].adjacency
+    kept = np.mean([len(set(lead_adj[i][lead_adj[i] >= 0]) & set(a.adjacency[i][a.adjacency[i] >= 0])) / max(1, (lead_adj[i] >= 0).sum()) for i in range(0, 500, 7)])
+    assert kept > 0.7
+    b = merged.fields["b"]
+    np.testing.assert_array_equal(b.doc_map.graph_node_ids_to_doc_ids, np.arange(60, 100))
+    reader = jv.JVectorReader(merged)
+    col = jv.JVectorKnnCollector(jv.TopKnnCollector(5), 0.0, 0.0, 5)
+    reader.search("a", small[7], col)
+    assert col.top_docs()[0].doc == 7
+    reader.close()
