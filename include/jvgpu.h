@@ -114,7 +114,9 @@ typedef struct jv_index_desc {
     /* ---- struct_size >= 128: NVQ-inline segments ("nvq+pq", JVectorWriter.java:436-466).  The graph nodes carry
      * 8-bit non-uniform-quantised vectors instead of fp32; the reranker (view.rerankerFor, JVectorReader.java:352-358)
      * scores the dequantised vector: JVectorIndexQuantization.java:316-361.  `vectors` may then be NULL (brute force is
-     * unsupported on such segments, as in the reference: JVectorQuantizedNvqVectorValues.java:33-36). */
+     * unsupported on such segments, as in the reference: JVectorQuantizedNvqVectorValues.java:33-36).  With pq_m = 0 the segment
+     * is NVQ-only (JVectorReader.java:357-358): the traversal itself is scored by the NVQ reranker, un-wrapped; the inline
+     * vectors are dequantised once on the device (n * dim * 4 bytes) and traversed exactly. */
     int32_t nvq_m;             /* number of NVQ sub-vectors (0 = no NVQ); sizes per the PQ split rule */
     int32_t nvq_reserved;
     const uint8_t *nvq_bytes;  /* [n * dim] quantised components                                */

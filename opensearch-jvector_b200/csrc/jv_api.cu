@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "jv_internal.h"
+#include "jv_rerank_body.cuh"
 
 namespace jv {
 
@@ -165,6 +166,39 @@ int32_t jv_host_unregister(void *ptr) {
     return JV_OK;
 }
 
+// NVQ-only segments (no auxiliary PQ blob): the traversal is scored by the NVQ reranker itself (JVectorReader.java:357-358:
+// DefaultSearchScoreProvider(view.rerankerFor(q, sim)), not MIP-wrapped), i.e. by exact scores against the DEQUANTISED vectors.  They are
+// dequantised once, at index creation, with the operations of nvq_decode_warp (jv_rerank_body.cuh; JVectorIndexQuantization.java:316-361):
+// one warp per vector.
+__global__ void nvq_dequantize_all_kernel(const uint8_t *__restrict__ bytes, const float *__restrict__ params, const float *__restrict__ gmean,
+                                          const int32_t *__restrict__ off, int m, int64_t n, int dim, float *__restrict__ out) {
+    extern __shared__ float nvq_consts[]; // [warps][m][4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t node = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (node >= n) return;
+    float *c = nvq_consts + (size_t)warp * m * 4;
+    if (lane < m) {
+        const float *prm = params + (node * m + lane) * 4;
+        const float growth = __ldg(prm), midpoint = __ldg(prm + 1), lo = __ldg(prm + 2), hi = __ldg(prm + 3);
+        const float delta = __fsub_rn(hi, lo);
+        const float sgr = __fdiv_rn(growth, delta);
+        const float mid = __fmul_rn(midpoint, delta);
+        const float bias = nvq_logistic(lo, sgr, mid);
+        c[lane * 4 + 0] = __fdiv_rn(__fsub_rn(nvq_logistic(hi, sgr, mid), bias), 255.0f);
+        c[lane * 4 + 1] = bias;
+        c[lane * 4 + 2] = __fdiv_rn(1.0f, sgr);
+        c[lane * 4 + 3] = mid;
+    }
+    __syncwarp();
+    const uint8_t *b = bytes + node * dim;
+    for (int i = lane; i < dim; i += 32) {
+        int sub = 0;
+        while (sub + 1 < m && i >= __ldg(off + sub + 1)) sub++;
+        const float y = nvq_logit(__fmaf_rn((float)__ldg(b + i), c[sub * 4], c[sub * 4 + 1]), c[sub * 4 + 2], c[sub * 4 + 3]);
+        out[node * dim + i] = __fadd_rn(y, __ldg(gmean + i));
+    }
+}
+
 // jv_index_create validation: the decoded arrays come from the caller, and a neighbour id, doc id or code
 // out of range would be an out-of-bounds device read later — which poisons the CUDA context of the whole JVM.  flags: 1 adjacency,
 // 2 ord_to_doc, 4 PQ code.
@@ -203,12 +237,12 @@ int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
     JV_REQUIRE(d->dim >= 1 && d->n >= 0 && d->n < 0x7fffffffLL, "bad dim/n");
     JV_REQUIRE(d->max_degree >= 1 && d->max_degree <= 128, "max_degree must be in [1,128]");
     JV_REQUIRE(d->n == 0 || d->adjacency, "adjacency is NULL");
-    JV_REQUIRE(d->n == 0 || d->vectors || (has_nvq && d->pq_m > 0), "vectors are NULL (only an nvq+pq segment may omit them)");
+    JV_REQUIRE(d->n == 0 || d->vectors || has_nvq, "vectors are NULL (only an NVQ-inline segment may omit them)");
     if (has_nvq) {
         JV_REQUIRE(d->nvq_bytes && d->nvq_params && d->nvq_global_mean, "nvq_bytes/nvq_params/nvq_global_mean are NULL");
         JV_REQUIRE(d->nvq_m <= 32 && d->nvq_m <= d->dim, "nvq_m must be in [1, 32]");
-        if (d->pq_m <= 0) {
-            set_error("NVQ-inline segments without the auxiliary PQ blob (exact traversal scored by the NVQ reranker) are not supported");
+        if (d->pq_m <= 0 && (d->flags & JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE)) {
+            set_error("an NVQ-only segment is traversed over its dequantised vectors, which live on the device");
             return JV_ERR_UNSUPPORTED;
         }
     }
@@ -283,6 +317,25 @@ int32_t jv_index_create(const jv_index_desc *desc, jv_index **out) {
         if ((st = upload(ix->nvq_off, off.data(), off.size() * 4, &total)) != JV_OK) return fail(st);
         ix->has_nvq = true;
         ix->nvq_m = d->nvq_m;
+        ix->fp32_given = d->vectors != nullptr;
+        if (!has_pq && n > 0) {
+            // NVQ-only: the dequantised vectors ARE the vectors of this index (they replace fp32 inline vectors if those were given too:
+            // "NVQ wins", like the rerank of nvq+pq segments)
+            ix->vectors.release();
+            if ((st = ix->vectors.alloc(n * d->dim * 4)) != JV_OK) return fail(st);
+            total += (int64_t)n * d->dim * 4;
+            const int wpb = 8;
+            nvq_dequantize_all_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, (size_t)wpb * d->nvq_m * 16>>>(
+                ix->nvq_bytes.as<uint8_t>(), ix->nvq_params.as<float>(), ix->nvq_gmean.as<float>(), ix->nvq_off.as<int32_t>(), d->nvq_m, d->n, d->dim,
+                ix->vectors.as<float>());
+            if (cudaGetLastError() != cudaSuccess) {
+                set_error("NVQ dequantisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return fail(JV_ERR_CUDA);
+            }
+            ix->vectors_dev = ix->vectors.as<float>();
+            ix->vectors_on_host = false;
+            ix->nvq_only = true;
+        }
     }
     if (d->ord_to_doc)
         if ((st = upload(ix->ord_to_doc, d->ord_to_doc, n * 4, &total)) != JV_OK) return fail(st);
@@ -644,7 +697,7 @@ int32_t jv_exact_topk_dev(jv_index *ix, const float *d_queries, int32_t nq, int3
     if (nq == 0) return JV_OK;
     JV_REQUIRE(d_queries && d_out_doc && d_out_score && d_out_count, "NULL buffer");
     JV_REQUIRE(ix->n > 0, "index is empty");
-    if (!ix->vectors_dev) {
+    if (!ix->vectors_dev || ix->nvq_only) {
         set_error("brute force is not supported on NVQ-inline segments (JVectorQuantizedNvqVectorValues.java:33-36)");
         return JV_ERR_UNSUPPORTED;
     }
@@ -668,7 +721,7 @@ int32_t jv_exact_topk(jv_index *ix, const float *queries, int32_t nq, int32_t k,
         for (int i = 0; i < nq; i++) out_count[i] = 0;
         return JV_OK;
     }
-    if (!ix->vectors_dev) {
+    if (!ix->vectors_dev || ix->nvq_only) {
         set_error("brute force is not supported on NVQ-inline segments (JVectorQuantizedNvqVectorValues.java:33-36)");
         return JV_ERR_UNSUPPORTED;
     }

@@ -51,6 +51,8 @@ struct jv_index {
     // NVQ-inline vectors (nvq+pq segments): the reranker scores the dequantised vector
     jv::DevBuf nvq_bytes, nvq_params, nvq_gmean, nvq_off;
     bool has_nvq = false;
+    bool nvq_only = false;   // no auxiliary PQ: traversal scored by the NVQ reranker = exact scores over the dequantised vectors
+    bool fp32_given = true;  // fp32 inline vectors came with the index (brute force needs them on NVQ segments)
     int nvq_m = 0;
     // tensor-core brute force (jv_exact_tc.cu): bf16 copy of the vectors (COSINE: normalised), EUCLIDEAN bias, max ||x||^2; lazy
     jv::DevBuf tc_base, tc_bias, tc_maxnorm;

@@ -317,7 +317,8 @@ static inline void fill_params(const jv_index *ix, SearchParams &p) {
     p.K = ix->pq.K;
     p.code_stride = ix->code_stride;
     p.sub_uniform = ix->pq.uniform ? 1 : 0;
-    p.mip_mul = (ix->sim == JV_SIM_MIP && !ix->has_pq) ? 2.0f : 1.0f; // wrapExactScoreFunction, JVectorReader.java:220-239
+    // wrapExactScoreFunction, JVectorReader.java:220-239 — only the plain un-quantised branch (:359-363); the NVQ-only branch (:357-358) is not wrapped
+    p.mip_mul = (ix->sim == JV_SIM_MIP && !ix->has_pq && !ix->nvq_only) ? 2.0f : 1.0f;
 }
 
 // the fast kernel's launcher (jv_search_fast.cu)

@@ -75,7 +75,9 @@ def test_two_quantised_flushes_force_merged_keep_the_recall_floor(jv):
     merged = jv.JVectorWriter().merge(segs)
     fd = merged.fields["test_field"]
     assert fd.vectors.shape[0] == 2 * per and fd.pq_codes is not None
-    np.testing.assert_array_equal(fd.pq_codebooks, segs[0].fields["test_field"].pq_codebooks)   # "not refining PQ codes on merge"
+    # equal live counts: the LATER segment leads (`>=`, JVectorWriter.java:805-808); its codebooks are kept ("not refining PQ codes on merge")
+    np.testing.assert_array_equal(fd.pq_codebooks, segs[1].fields["test_field"].pq_codebooks)
+    # docIds are re-based in the original segment order whichever segment leads: doc d = vectors[d]
     truth = np.argsort(((vectors - target) ** 2).sum(1), kind="stable")[:k]
     reader = jv.JVectorReader(merged)
     col = jv.JVectorKnnCollector(jv.TopKnnCollector(k), 0.0, 0.0, 5)

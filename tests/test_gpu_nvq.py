@@ -55,9 +55,25 @@ def test_nvq_with_production_traversal_and_reference_recall_floor(jv):
                 assert s == np.float32(O.exact_score(O.SIM_EUCLIDEAN, q[i], deq[d]))
 
 
-def test_nvq_needs_the_auxiliary_pq(jv):
-    base, q = clustered(500, 16, 4, seed=9)
-    fx = make_fixture(O.SIM_EUCLIDEAN, base, q, max_degree=8)
+@pytest.mark.parametrize("sim", [O.SIM_EUCLIDEAN, O.SIM_DOT, O.SIM_COSINE, O.SIM_MIP])
+def test_nvq_only_segment_is_traversed_with_the_nvq_reranker(jv, sim):
+    """No auxiliary PQ blob (JVectorReader.java:357-358): DefaultSearchScoreProvider(view.rerankerFor(q, sim)) — the traversal is
+    scored exactly against the DEQUANTISED inline vectors and the score is NOT MIP-wrapped.  Same as an un-quantised segment whose
+    vectors are the dequantised ones (for MIP: with the plain dot-product score)."""
+    base, q = clustered(1500, 24, 40, seed=17, normalize=sim in (O.SIM_DOT, O.SIM_MIP))
     b, prm, g = O.nvq_encode(base, 2)
-    with pytest.raises(NotImplementedError):
-        jv.GpuIndex(O.SIM_EUCLIDEAN, base, fx.adjacency, fx.entry, nvq_m=2, nvq_bytes=b, nvq_params=prm, nvq_global_mean=g)
+    deq = O.nvq_dequantize(b, prm, g)
+    fx = make_fixture(sim, base, q, max_degree=12)
+    inner = O.SIM_DOT if sim == O.SIM_MIP else sim                        # un-wrapped: MIP scores like DOT here
+    want = O.OracleIndex(inner, deq, fx.adjacency, fx.entry)
+    wd, ws, wc, wst = want.search(q, 10, 50)
+    with jv.GpuIndex(sim, None, fx.adjacency, fx.entry, nvq_m=2, nvq_bytes=b, nvq_params=prm, nvq_global_mean=g) as gi:
+        r = gi.search(q, 10, 50, expand_width=-1)                         # strict reference-order kernel
+        np.testing.assert_array_equal(r.docs, wd)
+        np.testing.assert_array_equal(r.scores.view(np.uint32), ws.view(np.uint32))
+        np.testing.assert_array_equal(r.stats[:, :2], wst[:, :2])
+        rf = gi.search(q, 10, 50)                                         # production (wide-step) kernel
+        gt, _, _ = want.exact_topk(q, 10)
+        assert recall(rf.docs, gt) >= recall(wd, gt) - 0.02
+        with pytest.raises(NotImplementedError):                          # brute force: JVectorQuantizedNvqVectorValues.java:33-36
+            gi.exact_topk(q, 10)
