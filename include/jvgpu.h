@@ -284,9 +284,9 @@ JV_API int32_t jv_graph_build_dev(int32_t device, const float *d_vectors, int64_
 /* Leading-segment merge, insert-only part (JVectorWriter.tryLeadingSegmentMerge, JVectorWriter.java:1166-1341): the first n0
  * ordinals keep the leading segment's graph (seed_adjacency [n0*max_degree], -1 padded at the end of each row; its entry node
  * stays the entry), the cached neighbour scores are recomputed (exact pair scores, what the neighbours-score-cache file holds),
- * and vectors n0..n-1 are inserted like builder.addGraphNode with the batched schedule of jv_graph_build.  A leading segment
- * with deleted documents needs markNodeDeleted + cleanup, which is not modelled: rebuild with jv_graph_build (the reference's
- * own fallback when leading-segment merge is skipped, :1166-1230).  out_adjacency [n*max_degree]. */
+ * and vectors n0..n-1 are inserted like builder.addGraphNode with the batched schedule of jv_graph_build.  Deleted documents
+ * of the leading segment (builder.markNodeDeleted + cleanup, :1318-1327) are consolidated afterwards with
+ * jv_graph_remove_deleted in the same ordinal space.  out_adjacency [n*max_degree]. */
 JV_API int32_t jv_graph_extend(int32_t device, const float *vectors, int64_t n, int64_t n0, const int32_t *seed_adjacency,
                         int32_t seed_entry, int32_t dim, int32_t similarity, int32_t max_degree, int32_t beam_width,
                         float neighbor_overflow, float alpha, int32_t *out_adjacency);

@@ -400,7 +400,9 @@ class JVectorWriter:
 class JVectorReader:
     """JVectorReader.java — per-segment reader; `search` is the drop-in for JVectorReader.java:130-210."""
 
-    def __init__(self, segment: Segment, device: int = 0, flags: int = 0):
+    def __init__(self, segment: Segment, device: int = 0, flags: int = N.FLAG_LUT_U8):
+        """`flags`: JV_INDEX_FLAG_* of every field's device index; the default is the production configuration (8-bit ADC tables;
+        segments the 8-bit path does not cover — un-quantised, K < 256, non-uniform sub-vectors — ignore the flag)."""
         self._segment = segment
         self._entries: Dict[str, GpuIndex] = {}
         self._closed = False
@@ -413,7 +415,7 @@ class JVectorReader:
 
     @classmethod
     def open(cls, directory, field_infos: Dict[int, object], segment_name: str = "_0", segment_suffix: str = "JVector_0",
-             device: int = 0, flags: int = 0, load_flags: int = 0) -> "JVectorReader":
+             device: int = 0, flags: int = N.FLAG_LUT_U8, load_flags: int = 0) -> "JVectorReader":
         """JVectorReader(SegmentReadState), JVectorReader.java:52-81: read the meta file, then one FieldEntry per record
         (:255-337) — here a single native call per field (jv_segment_index_create) that parses the field data file and
         copies graph, vectors, PQ codebooks + codes and doc map to the device.  `field_infos` maps Lucene field numbers to
