@@ -219,6 +219,34 @@ class Segment:
     max_doc: int
     fields: Dict[str, FieldData] = field(default_factory=dict)
 
+    @classmethod
+    def from_files(cls, directory, field_infos: Dict[int, object], max_doc: int, segment_name: str = "_0",
+                   segment_suffix: str = "JVector_0", load_flags: int = 0) -> "Segment":
+        """The decoded arrays of a persisted segment (meta file + one data file per field) — what a merge needs
+        from its input readers (JVectorWriter.mergeOneField reads graph, vectors and PQ of every segment through their readers,
+        JVectorWriter.java:1040-1160).  `field_infos`: field number -> name or (name, VectorSimilarityFunction), as for
+        JVectorReader.open.  The neighbours-score-cache file of the leading segment (:1174) is not read: the merge recomputes the
+        cached neighbour scores on the device (jv_graph_extend).  No GPU is needed here."""
+        from pathlib import Path as _Path
+
+        from .segment_files import META_EXTENSION, SegmentFiles, field_data_file_name, segment_file_name
+        directory = _Path(directory)
+        seg = cls(max_doc=int(max_doc))
+        with SegmentFiles(directory / segment_file_name(segment_name, segment_suffix, META_EXTENSION), load_flags) as sf:
+            for i, m in enumerate(sf.metas):
+                info = field_infos[m.field_number]
+                name, sim = (info if isinstance(info, tuple) else (info, None))
+                if sim is not None:
+                    sf.set_lucene_similarity(i, sim.jvector_ord)
+                d = sf.load_field(i, directory / field_data_file_name(segment_name, segment_suffix, name), load_flags)
+                fd = FieldData(VectorSimilarityFunction(sf.metas[i].similarity), d["vectors"], d["adjacency"], d["entry_node"],
+                               GraphNodeIdToDocMap(sf.doc_map(i), m.max_doc))
+                if d["pq_m"] > 0:
+                    fd.pq_m, fd.pq_k, fd.pq_codebooks = d["pq_m"], d["pq_k"], d["pq_codebooks"]
+                    fd.pq_global_centroid, fd.pq_codes = d["pq_global_centroid"], d["pq_codes"]
+                seg.fields[name] = fd
+        return seg
+
 
 class JVectorIndexQuantization:
     """PQ strategy of JVectorIndexQuantization.java:114-140 on the GPU (train = K8, encode = K6)."""

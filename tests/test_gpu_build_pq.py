@@ -122,3 +122,31 @@ def test_merge_picks_the_segment_with_the_most_live_vectors_as_leading_and_keeps
     reader.search("a", small[7], col)
     assert col.top_docs()[0].doc == 7
     reader.close()
+
+
+def test_a_merge_can_start_from_segment_files(jv, tmp_path):
+    """Flush two segments, persist them in the reference's file layout, read them back with the loader and merge from the FILES:
+    same merged segment as merging the in-memory segments (the neighbours-score cache is recomputed on the device, not read)."""
+    V = jv.VectorSimilarityFunction
+    rng = np.random.default_rng(5)
+    vecs = rng.random((1500, 12), dtype=np.float32)
+    segs, from_files = [], []
+    for s_i, (a, b) in enumerate([(0, 1100), (1100, 1500)]):
+        w = jv.JVectorWriter()
+        w.add_field("vec", V.EUCLIDEAN)
+        for i in range(a, b):
+            w.add_value("vec", i - a, vecs[i])
+        seg = w.flush(b - a)
+        segs.append(seg)
+        d = tmp_path / f"seg{s_i}"
+        d.mkdir()
+        jv.JVectorWriter.write(seg, d, field_numbers={"vec": 4})
+        from_files.append(jv.Segment.from_files(d, {4: "vec"}, max_doc=b - a))
+        np.testing.assert_array_equal(from_files[-1].fields["vec"].adjacency, seg.fields["vec"].adjacency)
+    live = [np.ones(1100, bool), np.ones(400, bool)]
+    live[0][::9] = False                                   # deleted documents in the leading segment
+    want = jv.JVectorWriter().merge(segs, live)
+    got = jv.JVectorWriter().merge(from_files, live)
+    for f in ("vectors", "adjacency", "pq_codes", "pq_codebooks"):
+        np.testing.assert_array_equal(getattr(got.fields["vec"], f), getattr(want.fields["vec"], f))
+    assert got.fields["vec"].entry_node == want.fields["vec"].entry_node and got.max_doc == want.max_doc
