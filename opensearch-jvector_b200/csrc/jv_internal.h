@@ -77,7 +77,7 @@ namespace jv {
 struct Q8Knobs {
     int occ = 0;        // JVGPU_Q8_OCC: cap the CTAs per SM
     int chunk = 0;      // JVGPU_Q8_CHUNK: table staging buffer of n queries
-    int warps = 0;      // JVGPU_Q8_WARPS: warps per CTA (4 or 8; manager / scorer kernel: 4, 5 or 8 including the manager)
+    int warps = 0;      // JVGPU_Q8_WARPS: warps per CTA (4 or 8; manager / scorer kernel: 4, 5 or 8 = 3, 4 or 7 scorer warps)
     bool prof = false;  // JVGPU_PROFILE: per-phase cycle counters (synchronous kernel)
     bool fused = false; // JVGPU_Q8_FUSED: K3 as the epilogue of the synchronous kernel
     bool sync = false;  // JVGPU_Q8_SYNC: the round-synchronous kernel of jv_q8.cu instead of the manager / scorer kernel (jv_q8_beam.cu)

@@ -1,23 +1,26 @@
-// jv_q8_beam.cu — K2, production kernel of the 8-bit table path: manager warp + scorer warps, software-pipelined steps.
+// jv_q8_beam.cu — K2, production kernel of the 8-bit table path: manager warp + expander warp + scorer warps, software-pipelined steps.
 //
 // Reference loop: GraphSearcher.search over the PQ score function (JVectorReader.java:165-173).
 //
 // One CTA owns one query; its 8-bit ADC table is staged in shared memory with one TMA bulk copy (like the round-synchronous
 // kernel of jv_q8.cu, which stays the path of filtered queries and of lists longer than 64).  The warps are specialised:
 //
-//   manager warp       owns the search state.  The sorted list of the best L visited nodes (L <= 64) lives in its REGISTERS,
-//                      two keys per lane (shared memory holds the copy the merge scatters through); selection, visited filter,
-//                      pool of fresh neighbours and the list merge are warp-synchronous — no block barrier, no shared-memory
-//                      atomics on the list or the filter, nothing replicated across warps.  Per step: pick the E best unexpanded
-//                      entries, read their adjacency rows (one coalesced 128-byte load each, all in flight together),
-//                      test-and-insert the visited filter, write the fresh ids to the pool, start their code rows towards L2,
-//                      hand the pool to the scorers.  Merge: binary search per survivor (one per lane), duplicates of list
-//                      members dropped, ranks by counting over broadcast reads of the survivor queue, scatter, reload.
+//   manager warp       owns the list.  The sorted list of the best L visited nodes (L <= 64) lives in its REGISTERS, two keys per
+//                      lane (shared memory holds the copy the merge scatters through); selection and the list merge are
+//                      warp-synchronous — no block barrier, no shared-memory atomics on the list, nothing replicated across
+//                      warps.  Per step: pick the E best unexpanded entries and hand them to the expander.  Merge: binary search
+//                      per survivor (one per lane), duplicates of list members dropped, ranks by counting over broadcast reads
+//                      of the survivor queue, scatter, reload.
+//   expander warp      owns the visited filter (plain loads and stores, no atomics).  Per step: read the adjacency rows of the
+//                      selected entries (one coalesced 128-byte load each, all in flight together), test-and-insert the filter,
+//                      write the fresh ids to the pool, start their code rows towards L2, hand the pool to the scorers.  With the
+//                      manager merging step s while the expander prepares step s+1, neither the adjacency round trip nor the
+//                      filter chain is on the manager's critical path.
 //   scorer warps       score pools: 8 lanes per code row, all 16-byte code loads of a group's rows in flight before the first
 //                      table lookup, bank-conflict-free lookups (layout in jv_q8.cu); sums that beat the admission threshold the
 //                      manager published with the pool are queued (one shared-memory atomic per warp and pass).
 //
-// Hand-over is two named barriers per step (bar.arrive / bar.sync, ids by step parity), so a waiting warp costs no issue
+// Hand-over is three named barriers per step (bar.arrive / bar.sync, ids by step parity), so a waiting warp costs no issue
 // slots.  With depth 2 the manager selects and issues step s+1 BEFORE it merges the scores of step s: its bookkeeping
 // overlaps the scorers' DRAM round trip and lookups.  The selection then lags one step behind the scores — the same relaxation
 // as a wider step — and the result does not depend on timing (survivors are ranked by key, whatever their queue order).
@@ -38,21 +41,22 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 
 constexpr int kBeamPool = 128; // fresh neighbours per step: E * ceil(R / 32) <= 4 adjacency chunks of 32
 constexpr int kBeamList = 64;  // list capacity (two keys per manager lane)
-constexpr int kBarPool = 1;    // +parity: manager arrives, scorers sync (the pool of a step is complete)
+constexpr int kBarPool = 1;    // +parity: expander arrives, scorers sync (the pool of a step is complete)
 constexpr int kBarDone = 3;    // +parity: scorers arrive, manager syncs (the survivors of a step are queued)
+constexpr int kBarSel = 5;     // +parity: manager arrives, expander syncs (the selection of a step is published)
 
-// PROF: cycles of the manager (0 select + adjacency issue, 1 adjacency wait + filter + pool, 2 + 3 wait for the scorers +
-// survivors in registers, 11 binary search + duplicates, 12 rank loop, 13 scatter + reload, 6 rest of the merge, 4 query setup,
-// 5 emit) and of scorer warp 1 (8 wait for a pool, 9 code words in registers, 10 lookups + queue); 7 = steps, 14 = survivors,
-// 15 = merge rounds
+// PROF: cycles of the manager (0 select, 3 wait for the scorers + survivors in registers, 11 binary search + duplicates, 12 rank loop, 13 scatter + reload, 6 rest of the merge, 4 query setup,
+// 5 emit), of the expander (2 wait for a selection, 1 adjacency + filter + pool) and of scorer warp 0 (8 wait for a pool,
+// 9 code words in registers, 10 lookups + queue); 7 = steps, 14 = survivors, 15 = merge rounds
 template <int NJ, int SW, bool PROF>
-__global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Params p, const int depth) {
-    constexpr int kT = (SW + 1) * 32, NG = SW * 4;
+__global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Params p, const int depth) {
+    constexpr int kT = (SW + 2) * 32, NG = SW * 4, kTS = SW * 32; // threads per CTA / row groups / scorer threads
     constexpr int U = SW >= 7 ? 2 : SW == 3 ? 4 : 3; // rows in flight per row group and pass (NG * U >= 48: one pass per typical step)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = p.L, E = p.E, H = 1 << p.hash_log2, R = p.R;
     const uint32_t lt = (1u << lane) - 1u;
+    const int sw = warp - 2; // scorer index (warp 0 manages, warp 1 expands)
 
     unsigned char *sp = smem_raw;
     const uint8_t *lut = sp;
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
 
     __shared__ __align__(8) uint64_t s_bar, s_worst[2];
-    __shared__ int s_query, s_nn[2], s_ns[2], w_sel[2 * kQMaxE];
+    __shared__ int s_query, s_nn[2], s_ns[2], s_nsel[2], s_ru[2], w_sel[2][2 * kQMaxE];
 
     const bool tagged = p.n <= ((int64_t)1 << (p.hash_log2 + 15));
     const bool isum_keys = p.sim != JV_SIM_COSINE;
@@ -142,16 +146,16 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
 
-        if (warp > 0) {
+        if (warp >= 2) {
             // ================================================================================================ scorers
-            const int gid = (warp - 1) * 4 + g;
+            const int gid = sw * 4 + g;
             for (int step = 0;; step++) {
                 const int par = step & 1;
-                nbar_sync(kBarPool + par, kT); // the manager's pool of this step is complete
+                nbar_sync(kBarPool + par, kTS + 32); // the expander's pool of this step is complete
                 const int nn = s_nn[par];
                 if (nn < 0) break; // query finished
                 const uint64_t worst = s_worst[par]; // the list's worst entry when the pool was issued (it only improves)
-                if (warp == 1) JV_PHASE(8)
+                if (sw == 0) JV_PHASE(8)
                 const int32_t *pl = pool + par * kBeamPool;
                 uint64_t *sq = survq + par * kBeamPool;
                 auto pass = [&](int i0, auto nu_tag) {
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
                             for (int j = 0; j < NJ; j++) cw[u][j] = 0u;
                         }
                     }
-                    if (PROF && warp == 1) {
+                    if (PROF && sw == 0) {
                         uint32_t acc = 0;
 #pragma unroll
                         for (int u = 0; u < NU; u++)
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
                     }
                 };
                 for (int i0 = 0; i0 < nn; i0 += NG * U) {
-                    const int left = nn - i0 - (warp - 1) * 4; // rows of this pass at or after this warp's first group (warp-uniform)
+                    const int left = nn - i0 - sw * 4; // rows of this pass at or after this warp's first group (warp-uniform)
                     if (U >= 4 && left > 3 * NG)
                         pass(i0, std::integral_constant<int, U >= 4 ? 4 : 1>());
                     else if (U >= 3 && left > 2 * NG)
@@ -216,12 +220,112 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
                         pass(i0, std::integral_constant<int, 1>());
                 }
                 __threadfence_block();
-                nbar_arrive(kBarDone + par, kT); // the survivors of this step are queued
-                if (warp == 1) JV_PHASE(10)
+                nbar_arrive(kBarDone + par, kTS + 32); // the survivors of this step are queued
+                if (sw == 0) JV_PHASE(10)
             }
-            if (PROF && warp == 1 && lane == 0 && p.dbg) {
+            if (PROF && sw == 0 && lane == 0 && p.dbg) {
                 unsigned long long *ph = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p.dbg) + 64);
                 for (int i = 8; i < 11; i++) atomicAdd(ph + i, (unsigned long long)ck[i]);
+            }
+            continue;
+        }
+
+        const int RC = (R + 31) >> 5; // adjacency chunks of 32 per row (R <= 64 here)
+        if (warp == 1) {
+            // =============================================================================================== expander
+            const int lines = (R * 4 + 127) >> 7;
+            for (int step = 0;; step++) {
+                const int par = step & 1;
+                nbar_sync(kBarSel + par, 64); // the manager's selection of this step is published
+                const int nsel = s_nsel[par];
+                if (nsel < 0) { // query finished: the scorers leave their loop
+                    if (lane == 0) s_nn[par] = -1;
+                    __threadfence_block();
+                    nbar_arrive(kBarPool + par, kTS + 32);
+                    break;
+                }
+                JV_PHASE(2)
+                const int *ws = w_sel[par];
+                const int total = nsel * RC; // <= 4
+                int32_t nb[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    nb[t] = -1;
+                    if (t < total) {
+                        const int e = RC == 1 ? t : (t >> 1), r = (RC == 1 ? 0 : (t & 1) * 32) + lane;
+                        if (r < R) nb[t] = __ldg(p.adjacency + (int64_t)ws[e] * R + r);
+                    }
+                }
+                { // runner-up rows -> L2 (lines per row: 1 or 2)
+                    const int ru = s_ru[par];
+                    const int e = lines == 1 ? lane : (lane >> 1);
+                    if (e < ru)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.adjacency + (int64_t)ws[nsel + e] * R) +
+                                                                      (lines == 1 ? 0 : (lane & 1) * 128)));
+                }
+                int32_t *pl = pool + par * kBeamPool;
+                // visited filter (the expander is its only owner: plain loads and stores).  Hashes of all chunks first
+                // (independent), then one short read-test-write per chunk — a chunk must see the entries of the chunks before
+                // it (the rows of one step share many neighbours).  Two lanes of one chunk that map to the same set can
+                // overwrite each other's tag: the loser may be scored again later and is then dropped by the merge.
+                uint32_t fset[4], ftag[4];
+                bool fresh[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const bool ok = nb[t] >= 0 && nb[t] < p.n;
+                    fresh[t] = ok;
+                    if (tagged) {
+                        const uint32_t x = ((uint32_t)nb[t] * 0x9E3779B1u) & ((1u << (p.hash_log2 + 15)) - 1u);
+                        fset[t] = x >> 15;
+                        ftag[t] = (x & 0x7fffu) | 0x8000u;
+                    } else {
+                        fset[t] = ((uint32_t)nb[t] * 2654435761u) >> (32 - p.hash_log2);
+                        ftag[t] = (uint32_t)nb[t];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (t < total) { // warp-uniform
+                        if (fresh[t]) {
+                            const uint32_t old = filter[fset[t]];
+                            if (tagged) {
+                                if ((old & 0xffffu) == ftag[t] || (old >> 16) == ftag[t])
+                                    fresh[t] = false;
+                                else
+                                    filter[fset[t]] = (old << 16) | ftag[t];
+                            } else {
+                                fresh[t] = old != ftag[t];
+                                filter[fset[t]] = ftag[t];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                int nn = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    if (t < total) {
+                        const uint32_t bal = __ballot_sync(JV_FULL_MASK, fresh[t]);
+                        if (fresh[t]) {
+                            pl[nn + __popc(bal & lt)] = nb[t];
+                            // the scorers read the code row after the barrier: start DRAM -> L2 now (rows are 32-byte aligned
+                            // and <= 256 bytes: the lines of the first and of the last byte cover them)
+                            const char *row = reinterpret_cast<const char *>(p.codes_q8 + (int64_t)nb[t] * (NJ * 32));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                            if (NJ * 32 > 128 || (reinterpret_cast<uintptr_t>(row) & 127) + NJ * 32 > 128)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + NJ * 32 - 1));
+                        }
+                        nn += __popc(bal);
+                    }
+                }
+                if (lane == 0) s_nn[par] = nn; // an empty pool is a step like any other: the scorers arrive at once
+                __threadfence_block();
+                nbar_arrive(kBarPool + par, kTS + 32);
+                JV_PHASE(1)
+            }
+            if (PROF && lane == 0 && p.dbg) {
+                unsigned long long *ph = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p.dbg) + 64);
+                for (int i = 1; i < 3; i++) atomicAdd(ph + i, (unsigned long long)ck[i]);
             }
             continue;
         }
@@ -240,7 +344,7 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
             if (lane == 0) {
                 k0 = qkey_pack(ord_of(s, p.entry), p.entry);
                 lm[0] = k0;
-                if (tagged) { // the entry node is visited
+                if (tagged) { // the entry node is visited (the expander reads the filter after the first selection barrier)
                     const uint32_t x = ((uint32_t)p.entry * 0x9E3779B1u) & ((1u << (p.hash_log2 + 15)) - 1u);
                     filter[x >> 15] = (x & 0x7fffu) | 0x8000u;
                 } else {
@@ -253,13 +357,11 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
         __syncwarp();
         JV_PHASE(4)
 
-        int issued = 0, merged = 0; // steps handed to the scorers / merged back
-        const int RC = (R + 31) >> 5; // adjacency chunks of 32 per row (R <= 64 here)
-        const int lines = (R * 4 + 127) >> 7;
+        int issued = 0, merged = 0; // steps handed to the expander / merged back
         for (;;) {
             bool can_issue = issued - merged < depth;
             if (can_issue) {
-                // ---- select the E best unexpanded entries (runners-up E..2E-1: adjacency rows prefetched into L2)
+                // ---- select the E best unexpanded entries (runners-up E..2E-1: adjacency rows prefetched into L2 by the expander)
                 const bool un0 = lane < n && (k0 & 1ull), un1 = lane + 32 < n && (k1 & 1ull);
                 const uint32_t b0 = __ballot_sync(JV_FULL_MASK, un0), b1 = __ballot_sync(JV_FULL_MASK, un1);
                 const int c0 = __popc(b0), found = c0 + __popc(b1);
@@ -268,107 +370,33 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
                     if (issued == merged) break; // nothing to expand, nothing in flight: done
                     can_issue = false;           // the scores in flight may bring new candidates
                 } else {
+                    const int par = issued & 1;
+                    int *ws = w_sel[par];
                     const int r0 = __popc(b0 & lt), r1 = c0 + __popc(b1 & lt);
-                    if (un0 && r0 < 2 * E) w_sel[r0] = qkey_node(k0);
-                    if (un1 && r1 < 2 * E) w_sel[r1] = qkey_node(k1);
+                    if (un0 && r0 < 2 * E) ws[r0] = qkey_node(k0);
+                    if (un1 && r1 < 2 * E) ws[r1] = qkey_node(k1);
                     if (un0 && r0 < nsel) k0 &= ~1ull;
                     if (un1 && r1 < nsel) k1 &= ~1ull;
-                    __syncwarp();
-                    const int total = nsel * RC; // <= 4
-                    int32_t nb[4];
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        nb[t] = -1;
-                        if (t < total) {
-                            const int e = RC == 1 ? t : (t >> 1), r = (RC == 1 ? 0 : (t & 1) * 32) + lane;
-                            if (r < R) nb[t] = __ldg(p.adjacency + (int64_t)w_sel[e] * R + r);
-                        }
+                    uint64_t worst = 0ull; // admission threshold: the L-th entry once the list is full
+                    if (n >= L) worst = shfl64(L > 32 ? k1 : k0, (L - 1) & 31) >> 1;
+                    if (lane == 0) {
+                        s_nsel[par] = nsel;
+                        s_ru[par] = found - nsel < nsel ? found - nsel : nsel;
+                        s_worst[par] = worst;
                     }
-                    {
-                        const int ru = found - nsel < nsel ? found - nsel : nsel; // runner-up rows -> L2 (lines per row: 1 or 2)
-                        const int e = lines == 1 ? lane : (lane >> 1);
-                        if (e < ru)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.adjacency + (int64_t)w_sel[nsel + e] * R) +
-                                                                          (lines == 1 ? 0 : (lane & 1) * 128)));
-                    }
-                    JV_PHASE(0)
-                    const int par = issued & 1;
-                    int32_t *pl = pool + par * kBeamPool;
-                    // visited filter (the manager is its only owner: plain loads and stores).  Hashes of all chunks first
-                    // (independent), then one short read-test-write per chunk — a chunk must see the entries of the chunks before
-                    // it (the rows of one step share many neighbours).  Two lanes of one chunk that map to the same set can
-                    // overwrite each other's tag: the loser may be scored again later and is then dropped by the merge.
-                    uint32_t fset[4], ftag[4];
-                    bool fresh[4];
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const bool ok = nb[t] >= 0 && nb[t] < p.n;
-                        fresh[t] = ok;
-                        if (tagged) {
-                            const uint32_t x = ((uint32_t)nb[t] * 0x9E3779B1u) & ((1u << (p.hash_log2 + 15)) - 1u);
-                            fset[t] = x >> 15;
-                            ftag[t] = (x & 0x7fffu) | 0x8000u;
-                        } else {
-                            fset[t] = ((uint32_t)nb[t] * 2654435761u) >> (32 - p.hash_log2);
-                            ftag[t] = (uint32_t)nb[t];
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (t < total) { // warp-uniform
-                            if (fresh[t]) {
-                                const uint32_t old = filter[fset[t]];
-                                if (tagged) {
-                                    if ((old & 0xffffu) == ftag[t] || (old >> 16) == ftag[t])
-                                        fresh[t] = false;
-                                    else
-                                        filter[fset[t]] = (old << 16) | ftag[t];
-                                } else {
-                                    fresh[t] = old != ftag[t];
-                                    filter[fset[t]] = ftag[t];
-                                }
-                            }
-                            __syncwarp();
-                        }
-                    }
-                    int nn = 0;
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        if (t < total) {
-                            const uint32_t bal = __ballot_sync(JV_FULL_MASK, fresh[t]);
-                            if (fresh[t]) {
-                                pl[nn + __popc(bal & lt)] = nb[t];
-                                // the scorers read the code row after the barrier: start DRAM -> L2 now (rows are 32-byte aligned
-                                // and <= 256 bytes: the lines of the first and of the last byte cover them)
-                                const char *row = reinterpret_cast<const char *>(p.codes_q8 + (int64_t)nb[t] * (NJ * 32));
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-                                if (NJ * 32 > 128 || (reinterpret_cast<uintptr_t>(row) & 127) + NJ * 32 > 128)
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + NJ * 32 - 1));
-                            }
-                            nn += __popc(bal);
-                        }
-                    }
+                    __threadfence_block();
+                    nbar_arrive(kBarSel + par, 64);
+                    issued++;
                     expanded += nsel;
-                    visited += nn;
-                    JV_PHASE(1)
-                    if (nn > 0) {
-                        uint64_t worst = 0ull; // admission threshold: the L-th entry once the list is full
-                        if (n >= L) worst = shfl64(L > 32 ? k1 : k0, (L - 1) & 31) >> 1;
-                        if (lane == 0) {
-                            s_nn[par] = nn;
-                            s_worst[par] = worst;
-                        }
-                        __threadfence_block();
-                        nbar_arrive(kBarPool + par, kT);
-                        issued++;
-                    }
+                    JV_PHASE(0)
                     continue;
                 }
             }
             // ---- merge the oldest step in flight
             const int par = merged & 1;
-            nbar_sync(kBarDone + par, kT);
+            nbar_sync(kBarDone + par, kTS + 32);
             const int ns = s_ns[par];
+            visited += s_nn[par];
             const uint64_t *sr0 = survq + par * kBeamPool;
             uint64_t a_first = lane < ns ? sr0[lane] : 0ull;
             if (PROF) {
@@ -441,12 +469,12 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
             merged++;
             JV_PHASE(6)
         }
-        // ---- the scorers leave their loop
+        // ---- the expander and (through it) the scorers leave their loops
         {
             const int par = issued & 1;
-            if (lane == 0) s_nn[par] = -1;
+            if (lane == 0) s_nsel[par] = -1;
             __threadfence_block();
-            nbar_arrive(kBarPool + par, kT);
+            nbar_arrive(kBarSel + par, 64);
         }
         // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank step
         {
@@ -474,7 +502,8 @@ __global__ void __launch_bounds__((SW + 1) * 32, 4) q8_beam_kernel(const Q8Param
         JV_PHASE(5)
         if (PROF && lane == 0 && p.dbg) {
             unsigned long long *ph = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p.dbg) + 64);
-            for (int i = 0; i < 7; i++) atomicAdd(ph + i, (unsigned long long)ck[i]);
+            for (int i = 0; i < 7; i++)
+                if (i != 1 && i != 2) atomicAdd(ph + i, (unsigned long long)ck[i]);
             atomicAdd(ph + 7, (unsigned long long)issued);
             for (int i = 11; i < 16; i++) atomicAdd(ph + i, (unsigned long long)ck[i]);
         }
@@ -493,7 +522,7 @@ bool q8_beam_supported(const jv_index *ix, int L, int R, int E) {
 
 template <int NJ, int SW, bool PROF>
 static int32_t launch_beam_typed(jv_index *ix, SearchCtx *ctx, Q8Params &p, int depth) {
-    constexpr int kT = (SW + 1) * 32;
+    constexpr int kT = (SW + 2) * 32;
     auto kern = q8_beam_kernel<NJ, SW, PROF>;
     const size_t fixed = (size_t)p.lutb + kBeamList * 8 + 2 * kBeamPool * 8 + 2 * kBeamPool * 4;
     const size_t sm_total = 228 * 1024;
