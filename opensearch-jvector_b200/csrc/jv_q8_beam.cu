@@ -21,7 +21,8 @@
 //                      manager published with the pool are queued (one shared-memory atomic per warp and pass).
 //
 // Hand-over is three named barriers per step (bar.arrive / bar.sync, ids by step parity), so a waiting warp costs no issue
-// slots.  With depth 2 the manager selects and issues step s+1 BEFORE it merges the scores of step s: its bookkeeping
+// slots; the barrier itself orders the producer's shared-memory writes before the consumer's reads (PTX ISA, bar: producer /
+// consumer example), no fence instruction on the chain.  With depth 2 the manager selects and issues step s+1 BEFORE it merges the scores of step s: its bookkeeping
 // overlaps the scorers' DRAM round trip and lookups.  The selection then lags one step behind the scores — the same relaxation
 // as a wider step — and the result does not depend on timing (survivors are ranked by key, whatever their queue order).
 // expand_width = 1 runs at depth 1: exactly the best-first order of the oracle's 8-bit mode.
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
         }
         for (int i = tid; i < H; i += kT) filter[i] = tagged ? 0u : kEmpty;
         if (tid < kBeamList) lm[tid] = 0ull;
+        for (int i = tid; i < 2 * kBeamPool; i += kT) survq[i] = 0ull;
         const float4 qp = __ldg(p.qparams + qi);
         const float delta = qp.x, base = qp.y, qnorm = qp.z;
         auto score_of = [&](uint32_t isum, int32_t nb) -> float {
@@ -219,7 +221,6 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                     else if (left > 0)
                         pass(i0, std::integral_constant<int, 1>());
                 }
-                __threadfence_block();
                 nbar_arrive(kBarDone + par, kTS + 32); // the survivors of this step are queued
                 if (sw == 0) JV_PHASE(10)
             }
@@ -240,7 +241,6 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                 const int nsel = s_nsel[par];
                 if (nsel < 0) { // query finished: the scorers leave their loop
                     if (lane == 0) s_nn[par] = -1;
-                    __threadfence_block();
                     nbar_arrive(kBarPool + par, kTS + 32);
                     break;
                 }
@@ -319,7 +319,6 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                     }
                 }
                 if (lane == 0) s_nn[par] = nn; // an empty pool is a step like any other: the scorers arrive at once
-                __threadfence_block();
                 nbar_arrive(kBarPool + par, kTS + 32);
                 JV_PHASE(1)
             }
@@ -375,8 +374,8 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                     const int r0 = __popc(b0 & lt), r1 = c0 + __popc(b1 & lt);
                     if (un0 && r0 < 2 * E) ws[r0] = qkey_node(k0);
                     if (un1 && r1 < 2 * E) ws[r1] = qkey_node(k1);
-                    if (un0 && r0 < nsel) k0 &= ~1ull;
-                    if (un1 && r1 < nsel) k1 &= ~1ull;
+                    if (un0 && r0 < nsel) lm[lane] = (k0 &= ~1ull); // the merge gathers from the shared-memory copy
+                    if (un1 && r1 < nsel) lm[lane + 32] = (k1 &= ~1ull);
                     uint64_t worst = 0ull; // admission threshold: the L-th entry once the list is full
                     if (n >= L) worst = shfl64(L > 32 ? k1 : k0, (L - 1) & 31) >> 1;
                     if (lane == 0) {
@@ -384,7 +383,6 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                         s_ru[par] = found - nsel < nsel ? found - nsel : nsel;
                         s_worst[par] = worst;
                     }
-                    __threadfence_block();
                     nbar_arrive(kBarSel + par, 64);
                     issued++;
                     expanded += nsel;
@@ -397,69 +395,83 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
             nbar_sync(kBarDone + par, kTS + 32);
             const int ns = s_ns[par];
             visited += s_nn[par];
-            const uint64_t *sr0 = survq + par * kBeamPool;
+            uint64_t *sr0 = survq + par * kBeamPool;
             uint64_t a_first = lane < ns ? sr0[lane] : 0ull;
             if (PROF) {
                 asm volatile("" ::"l"(a_first));
                 JV_PHASE(3)
                 ck[14] += ns;
             }
-            // rounds of <= 32 survivors (more than one round only while the list is still filling up)
+            // rounds of <= 32 survivors (more than one round only while the list is still filling up).  A survivor's slot is
+            // (list entries better than it: binary search) + (survivors of the round better than it: counting over broadcast
+            // reads); the list entries fill the remaining slots in order (occupancy mask + gather) — no loop over the list.
             for (int r0 = 0; r0 < ns; r0 += 32) {
-                const int t = r0 + lane;
                 const int cnt = ns - r0 < 32 ? ns - r0 : 32;
-                uint64_t *sr = survq + par * kBeamPool + r0;
-                uint64_t a = r0 == 0 ? a_first : (t < ns ? sr[lane] : 0ull);
-                if (n >= L) { // the list may have improved since the threshold was published
+                uint64_t *sr = sr0 + r0;
+                uint64_t a = r0 == 0 ? a_first : (lane < cnt ? sr[lane] : 0ull);
+                if (n >= L) { // the list may have improved since the threshold was published: such survivors are worse than
+                              // every survivor that stays, so they do not disturb the ranks
                     const uint64_t worst = shfl64(L > 32 ? k1 : k0, (L - 1) & 31) >> 1;
                     if (a <= worst) a = 0ull;
                 }
-                bool sv = a != 0ull;
-                int lo = 0; // list entries better than the survivor
-                if (sv) {
-                    const uint64_t A = (a << 1) | 1ull;
+                const bool live = a != 0ull;
+                const uint64_t A = (a << 1) | 1ull;
+                // binary search: list entries better than the survivor; rank count: survivors of the round better than it (the
+                // queue is zero beyond its end: 16-byte reads, no tail)
+                int lo = 0, cs = 0;
+                if (live) {
 #pragma unroll
                     for (int st = 32; st >= 1; st >>= 1)
                         if ((lm[lo + st - 1] | 1ull) > A) lo += st;
-                    if ((lm[lo] | 1ull) == A) sv = false; // a re-scored list member (evicted from the visited filter earlier)
                 }
+                {
+                    const ulonglong2 *sr2 = reinterpret_cast<const ulonglong2 *>(sr);
+#pragma unroll 2
+                    for (int j = 0; j < cnt; j += 4) {
+                        const ulonglong2 u = sr2[j >> 1], v = sr2[(j >> 1) + 1];
+                        cs += (u.x > a ? 1 : 0) + (u.y > a ? 1 : 0) + (v.x > a ? 1 : 0) + (v.y > a ? 1 : 0);
+                    }
+                }
+                bool sv = live && (lm[lo] | 1ull) != A; // equal: a re-scored list member (evicted from the visited filter earlier)
                 uint32_t mask = __ballot_sync(JV_FULL_MASK, sv);
-                if (mask) {
-                    if (sv) { // the same node twice in one step (lost or evicted filter entry): keep the first copy
+                JV_PHASE(11)
+                if (!mask) {
+                    if (lane < cnt) sr[lane] = 0ull;
+                    continue;
+                }
+                // rare: a dropped list member was counted by the survivors behind it, or the same node was scored twice in this
+                // step (lost or evicted filter entry: equal keys, equal ranks) — drop the copies and count again
+                if (__ballot_sync(JV_FULL_MASK, live && !sv) != 0u || __popc(__reduce_or_sync(JV_FULL_MASK, sv ? 1u << cs : 0u)) != __popc(mask)) {
+                    if (PROF) ck[15] += 1;
+                    if (sv) {
                         const uint32_t same = __match_any_sync(mask, a);
                         if ((same & (0u - same)) != (1u << lane)) sv = false;
                     }
                     mask = __ballot_sync(JV_FULL_MASK, sv);
-                }
-                if (mask != (cnt == 32 ? 0xffffffffu : (1u << cnt) - 1u)) { // dropped entries count for nobody
-                    if (!sv && t < ns) sr[lane] = 0ull;
+                    if (lane < cnt) sr[lane] = sv ? a : 0ull;
                     __syncwarp();
+                    cs = 0;
+                    for (int j = 0; j < cnt; j++) cs += sr[j] > a ? 1 : 0;
                 }
-                JV_PHASE(11)
-                if (PROF) ck[15] += 1;
-                if (!mask) continue;
-                // ranks by counting against the round's survivors: mine among them, my two list entries' shifts
-                const uint64_t e0 = k0 >> 1, e1 = k1 >> 1;
-                int cs = 0, sh0 = 0, sh1 = 0;
-#pragma unroll 4
-                for (int j = 0; j < cnt; j++) {
-                    const uint64_t sj = sr[j];
-                    cs += sj > a ? 1 : 0;
-                    sh0 += sj > e0 ? 1 : 0;
-                    sh1 += sj > e1 ? 1 : 0;
-                }
-                if (PROF) {
-                    asm volatile("" ::"r"(cs + sh0 + sh1));
-                    JV_PHASE(12)
-                }
-                if (sv && lo + cs < L) lm[lo + cs] = (a << 1) | 1ull;
-                if (lane < n && lane + sh0 < L) lm[lane + sh0] = k0;
-                if (lane + 32 < n && lane + 32 + sh1 < L) lm[lane + 32 + sh1] = k1;
+                const int pos = lo + cs;
+                const bool in = sv && pos < L;
+                const uint32_t occ0 = __reduce_or_sync(JV_FULL_MASK, in && pos < 32 ? 1u << pos : 0u);
+                const uint32_t occ1 = __reduce_or_sync(JV_FULL_MASK, in && pos >= 32 ? 1u << (pos - 32) : 0u);
+                const bool s0 = (occ0 >> lane) & 1u, s1 = (occ1 >> lane) & 1u; // my two slots are taken by survivors
+                const int i0 = lane - __popc(occ0 & lt), i1 = lane + 32 - __popc(occ0) - __popc(occ1 & lt);
+                const uint64_t v0 = (!s0 && i0 < n && lane < L) ? lm[i0] : 0ull;
+                const uint64_t v1 = (!s1 && i1 < n && lane + 32 < L) ? lm[i1] : 0ull;
                 __syncwarp();
+                JV_PHASE(12)
+                if (in) lm[pos] = A;
+                if (!s0 && i0 != lane) lm[lane] = v0;
+                if (!s1 && i1 != lane + 32) lm[lane + 32] = v1;
+                __syncwarp();
+                if (lane < cnt) sr[lane] = 0ull; // the queue stays zero beyond its end
                 n += __popc(mask);
                 n = n < L ? n : L;
-                k0 = lm[lane];
-                k1 = lm[lane + 32];
+                k0 = s0 ? lm[lane] : v0;
+                k1 = s1 ? lm[lane + 32] : v1;
                 if (PROF) {
                     asm volatile("" ::"l"(k0 | k1));
                     JV_PHASE(13)
@@ -473,7 +485,6 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
         {
             const int par = issued & 1;
             if (lane == 0) s_nsel[par] = -1;
-            __threadfence_block();
             nbar_arrive(kBarSel + par, 64);
         }
         // ---- emit the approximate result list, best first, in the (score, ~node) key format of the rerank step
