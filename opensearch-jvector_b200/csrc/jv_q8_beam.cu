@@ -70,7 +70,7 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
     sp += 2 * kBeamPool * 4;
     uint32_t *filter = reinterpret_cast<uint32_t *>(sp);
 
-    __shared__ __align__(8) uint64_t s_bar, s_worst[2];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_query, s_nn[2], s_ns[2], s_nsel[2], s_ru[2], w_sel[2][2 * kQMaxE];
 
     const bool tagged = p.n <= ((int64_t)1 << (p.hash_log2 + 15));
@@ -156,7 +156,10 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                 nbar_sync(kBarPool + par, kTS + 32); // the expander's pool of this step is complete
                 const int nn = s_nn[par];
                 if (nn < 0) break; // query finished
-                const uint64_t worst = s_worst[par]; // the list's worst entry when the pool was issued (it only improves)
+                // admission threshold: the L-th list entry (0 until the list is full), read from the manager's live copy — it only
+                // improves, the manager checks every survivor against the current list again, and whatever is admitted in between
+                // is dropped there, so the result does not depend on when this read happens
+                const uint64_t worst = lm[L - 1] >> 1;
                 if (sw == 0) JV_PHASE(8)
                 const int32_t *pl = pool + par * kBeamPool;
                 uint64_t *sq = survq + par * kBeamPool;
@@ -376,12 +379,9 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                     if (un1 && r1 < 2 * E) ws[r1] = qkey_node(k1);
                     if (un0 && r0 < nsel) lm[lane] = (k0 &= ~1ull); // the merge gathers from the shared-memory copy
                     if (un1 && r1 < nsel) lm[lane + 32] = (k1 &= ~1ull);
-                    uint64_t worst = 0ull; // admission threshold: the L-th entry once the list is full
-                    if (n >= L) worst = shfl64(L > 32 ? k1 : k0, (L - 1) & 31) >> 1;
                     if (lane == 0) {
                         s_nsel[par] = nsel;
                         s_ru[par] = found - nsel < nsel ? found - nsel : nsel;
-                        s_worst[par] = worst;
                     }
                     nbar_arrive(kBarSel + par, 64);
                     issued++;
@@ -409,9 +409,9 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                 const int cnt = ns - r0 < 32 ? ns - r0 : 32;
                 uint64_t *sr = sr0 + r0;
                 uint64_t a = r0 == 0 ? a_first : (lane < cnt ? sr[lane] : 0ull);
-                if (n >= L) { // the list may have improved since the threshold was published: such survivors are worse than
-                              // every survivor that stays, so they do not disturb the ranks
-                    const uint64_t worst = shfl64(L > 32 ? k1 : k0, (L - 1) & 31) >> 1;
+                { // the list may have improved since the scorers read the threshold: such survivors are worse than every survivor
+                  // that stays, so they do not disturb the ranks
+                    const uint64_t worst = lm[L - 1] >> 1;
                     if (a <= worst) a = 0ull;
                 }
                 const bool live = a != 0ull;
