@@ -301,6 +301,14 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                                 filter[fset[t]] = ftag[t];
                             }
                         }
+                        if (fresh[t]) {
+                            // the scorers read the code row after the barrier: start DRAM -> L2 as early as possible (rows are
+                            // 32-byte aligned and <= 256 bytes: the lines of the first and of the last byte cover them)
+                            const char *row = reinterpret_cast<const char *>(p.codes_q8 + (int64_t)nb[t] * (NJ * 32));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                            if (NJ * 32 > 128 || (reinterpret_cast<uintptr_t>(row) & 127) + NJ * 32 > 128)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + NJ * 32 - 1));
+                        }
                         __syncwarp();
                     }
                 }
@@ -309,15 +317,7 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                 for (int t = 0; t < 4; t++) {
                     if (t < total) {
                         const uint32_t bal = __ballot_sync(JV_FULL_MASK, fresh[t]);
-                        if (fresh[t]) {
-                            pl[nn + __popc(bal & lt)] = nb[t];
-                            // the scorers read the code row after the barrier: start DRAM -> L2 now (rows are 32-byte aligned
-                            // and <= 256 bytes: the lines of the first and of the last byte cover them)
-                            const char *row = reinterpret_cast<const char *>(p.codes_q8 + (int64_t)nb[t] * (NJ * 32));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-                            if (NJ * 32 > 128 || (reinterpret_cast<uintptr_t>(row) & 127) + NJ * 32 > 128)
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + NJ * 32 - 1));
-                        }
+                        if (fresh[t]) pl[nn + __popc(bal & lt)] = nb[t];
                         nn += __popc(bal);
                     }
                 }
