@@ -699,7 +699,7 @@ def main():
         "visited_set_overflows": gi.visited_overflows(),
         # dominant kernel: the traversal (K2).  With the 8-bit table the table build (K1) is a separate launch whose time is
         # measured by its own event pair and reported next to it; the fp16/fp32 kernels fuse K1 into the traversal.
-        "roofline": {"bound": "hbm", "kernel": ("q8_search_kernel<FILT> (K2 beam search + ADC over accepted and rejected nodes, 8-bit table staged with TMA)" if h_bits is not None else None) or {3: "q8_beam_kernel (K2 beam search + ADC: 8-bit table staged with TMA, manager warp + scorer warps, 2 steps in flight)",
+        "roofline": {"bound": "hbm", "kernel": ("q8_search_kernel<FILT> (K2 beam search + ADC over accepted and rejected nodes, 8-bit table staged with TMA)" if h_bits is not None else None) or {3: "q8_beam_kernel (K2 beam search + ADC: 8-bit table staged with TMA, manager + expander + scorer warps, 2 steps in flight)",
                                                 2: "q8_search_kernel (K2 beam search + ADC, 8-bit table staged with TMA, round-synchronous)"}.get(used_kernel)
                      or ("fast_search_kernel (K4 beam search with exact scores, un-quantised segment)" if m == 0
                          else "fast_search_kernel (K1 LUT + K2 beam search + ADC)"),

@@ -156,7 +156,7 @@ enum {
     JV_KERNEL_STRICT = 0,   /* search_kernel: candidate heap + result heap, reference order (jv_search.cu)             */
     JV_KERNEL_FAST = 1,     /* fast_search_kernel: fp32 / fp16 table or exact scores, wide steps (jv_search_fast.cu)   */
     JV_KERNEL_Q8_SYNC = 2,  /* q8_search_kernel: 8-bit table, round-synchronous CTA per query (jv_q8.cu)               */
-    JV_KERNEL_Q8_BEAM = 3   /* q8_beam_kernel: 8-bit table, manager warp + scorer warps, two steps in flight (jv_q8_beam.cu) */
+    JV_KERNEL_Q8_BEAM = 3   /* q8_beam_kernel: 8-bit table, manager + expander + scorer warps, two steps in flight (jv_q8_beam.cu) */
 };
 
 typedef struct jv_search_params {

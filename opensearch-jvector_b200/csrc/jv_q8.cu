@@ -939,7 +939,7 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
     // wider step costs few wasted visits and saves steps (measured at 10 % selectivity: 2/4/6/8 -> 265k/453k/514k/460k queries/s;
     // at 50 %: 4 -> 1.13 M, 8 -> 1.08 M)
     // the manager / scorer kernel (M = 161..192, no filter, list <= 64) works two steps deep: 3 candidates per step measured best
-    // there (cfg2: 3 -> 1.46 ms / 1 078 visited, 4 -> 1.47 ms / 1 218 visited; cfg4 shape: 1.26 / 1.31 ms)
+    // there (cfg2: 3 -> 1.26 ms / 1 078 visited, 4 -> 1.29 ms / 1 218 visited)
     const bool beam_shape = !q8_knobs().sync && a.d_accept == nullptr && q8_beam_supported(ix, a.rerank_k, ix->R, 3);
     const int dflt = a.d_accept != nullptr ? 6 : beam_shape ? 3 : 4;
     int E = a.expand_width <= 0 ? dflt : (a.expand_width > kQMaxE ? kQMaxE : a.expand_width);
