@@ -436,6 +436,7 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                 uint32_t mask = __ballot_sync(JV_FULL_MASK, sv);
                 JV_PHASE(11)
                 if (!mask) {
+                    __syncwarp(); // every lane is done reading the queue
                     if (lane < cnt) sr[lane] = 0ull;
                     continue;
                 }
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                         if ((same & (0u - same)) != (1u << lane)) sv = false;
                     }
                     mask = __ballot_sync(JV_FULL_MASK, sv);
+                    __syncwarp(); // every lane is done reading the queue
                     if (lane < cnt) sr[lane] = sv ? a : 0ull;
                     __syncwarp();
                     cs = 0;
