@@ -270,7 +270,8 @@ __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Param
                 // visited filter (the expander is its only owner: plain loads and stores).  Hashes of all chunks first
                 // (independent), then one short read-test-write per chunk — a chunk must see the entries of the chunks before
                 // it (the rows of one step share many neighbours).  Two lanes of one chunk that map to the same set can
-                // overwrite each other's tag: the loser may be scored again later and is then dropped by the merge.
+                // overwrite each other's tag: the loser may be scored again later and is then dropped by the merge (the result
+                // list does not depend on which one survives; the visited counter can differ by a few re-scored nodes).
                 uint32_t fset[4], ftag[4];
                 bool fresh[4];
 #pragma unroll

@@ -273,3 +273,42 @@ def test_every_table_size_instantiation(jv, m, sub):
         rf = gi.search(q, 10, 50, accept_bits=bits)
         gf, _, _ = gi.exact_topk(q, 10, bits)
         assert recall(rf.docs, gf) >= 0.95
+
+
+@pytest.fixture(scope="module")
+def fx_dot192_wide():  # M = 192, sub-dim 2, R = 64 (two adjacency chunks per row): the manager / expander / scorer kernel at its limits
+    base, q = embedded(12000, 384, 48, seed=45)
+    return make_fixture(O.SIM_DOT, base, q, max_degree=64, pq_m=192)
+
+
+def test_beam_kernel_full_list_wide_rows_and_filter_evictions(jv, fx_dot192_wide):
+    """rerankK = 64 fills the register-held list, R = 64 makes every step read two adjacency chunks per candidate, and ~3 000 visits
+    against the 2 048-tag visited filter of the M = 192 shape evict entries all the time: re-scored list members and nodes scored
+    twice in one step go through the merge's second counting pass.  The result must stay a set (no document twice), follow the
+    oracle's 8-bit order at width 1, keep the recall gate at the default width and be identical from run to run."""
+    fx = fx_dot192_wide
+    ora = fx.oracle_index(adc_order=-8)
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        gt, _, _ = gi.exact_topk(fx.queries, 10)
+        wd, ws, wc, wst = ora.search(fx.queries, 10, 64)
+        for width in (1, 0, 2):
+            r = gi.search(fx.queries, 10, 64, expand_width=width)
+            # two adjacency chunks per candidate: steps of <= 2 candidates run on q8_beam_kernel, the default width on the synchronous kernel
+            assert r.timing["traversal_kernel"] == (3 if width else 2)
+            np.testing.assert_array_equal(r.counts, wc)
+            for row in r.docs:
+                live = row[row >= 0]
+                assert len(set(live.tolist())) == len(live)
+            assert (r.stats[:, 3] == 64).all()
+            assert recall(r.docs, gt) >= recall(wd, gt) - 0.015
+            if width == 1:
+                same = np.mean([np.array_equal(a, b) for a, b in zip(r.docs, wd)])
+                assert same >= 0.9, same
+                assert r.stats[:, 0].mean() >= wst[:, 0].mean()  # evictions only ever add visits
+            r2 = gi.search(fx.queries, 10, 64, expand_width=width)
+            np.testing.assert_array_equal(r.docs, r2.docs)
+            np.testing.assert_array_equal(r.scores, r2.scores)
+            # expansions follow the list, which is deterministic; the visited counter also counts re-scored nodes, and which of two
+            # same-set tags written by one adjacency chunk survives in the visited filter is up to the hardware
+            np.testing.assert_array_equal(r.stats[:, 1:], r2.stats[:, 1:])
+            assert np.abs(r.stats[:, 0].astype(np.int64) - r2.stats[:, 0]).max() <= 0.02 * r.stats[:, 0].max() + 8
