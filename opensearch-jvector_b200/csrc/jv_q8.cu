@@ -404,12 +404,15 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
     // ADC lane geometry: group g = lane / 8 scores one code row, lane sl owns subspaces m = 8t + sl.  At lookup (j, i) the
     // group reads bank quarter (i + g) & 3, so the 32 lanes of a warp always hit 32 different banks.
     const int g = lane >> 3, sl = lane & 7;
-    uint32_t sel[4], lb[4];
+    // per code word (4 codes): one mask (c & 63 in every byte) and one shift-mask-or (c >> 6 plus the lane's bank bits in every
+    // byte: the byte used at slot i carries the bank quarter (i + g) & 3); then ONE byte permute per lookup assembles the clean
+    // offset ((c & 63) << 8) | bank * 4 | (c >> 6) — bytes 2 and 3 come from the replicated sign bit of a (c & 63) byte, i.e. zero
+    uint32_t sel[4], lbw = 0u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t qd = (uint32_t)(i + g) & 3u;
-        sel[i] = 0x4400u | (qd << 4) | (4u + qd); // byte 0 <- (cw >> 6).byte[qd], byte 1 <- cw.byte[qd]
-        lb[i] = qd * 32u + (uint32_t)sl * 4u;
+        sel[i] = 0x8800u | (qd << 4) | (4u + qd);
+        lbw |= (qd * 32u + (uint32_t)sl * 4u) << (8u * qd);
     }
 
     if (tid == 0) {
@@ -420,13 +423,14 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
 
     // table entries selected by code word j of this lane (4 subspaces); caller reduces over the 8 lanes of the group
     auto lookup4 = [&](uint32_t cw, int j) -> uint32_t {
-        const uint32_t sh = cw >> 6;
+        const uint32_t lo6 = cw & 0x3F3F3F3Fu, hi2 = ((cw >> 6) & 0x03030303u) | lbw;
         const uint8_t *base = lut + (j >> 1) * 16384 + (j & 1) * 128;
         uint32_t s = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t v = __byte_perm(cw, sh, sel[i]);
-            s += base[(v & 0x3F03u) | lb[i]];
+            uint32_t off; // (__byte_perm ignores the sign-replication bit of the selector nibbles: PTX prmt in its default mode)
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(off) : "r"(lo6), "r"(hi2), "r"(sel[i]));
+            s += base[off];
         }
         return s;
     };
