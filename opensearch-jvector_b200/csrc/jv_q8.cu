@@ -942,10 +942,9 @@ int32_t launch_search_q8(jv_index *ix, SearchCtx *ctx, const SearchLaunch &a, in
     // default width: 4 (measured best without a filter); filtered queries need ~1/selectivity more expansions anyway, so a
     // wider step costs few wasted visits and saves steps (measured at 10 % selectivity: 2/4/6/8 -> 265k/453k/514k/460k queries/s;
     // at 50 %: 4 -> 1.13 M, 8 -> 1.08 M)
-    // the manager / scorer kernel (M = 161..192, no filter, list <= 64) works two steps deep: 3 candidates per step measured best
-    // there (cfg2: 3 -> 1.26 ms / 1 078 visited, 4 -> 1.29 ms / 1 218 visited)
-    const bool beam_shape = !q8_knobs().sync && a.d_accept == nullptr && q8_beam_supported(ix, a.rerank_k, ix->R, 3);
-    const int dflt = a.d_accept != nullptr ? 6 : beam_shape ? 3 : 4;
+    // the manager / expander / scorer kernel (M = 161..192, no filter, list <= 64) works two steps deep; measured at cfg2: 3 candidates
+    // per step -> 1.19 ms / 1 078 visited / recall 0.9947, 4 -> 1.21 ms / 1 218 visited / recall 0.9962: width 4 everywhere
+    const int dflt = a.d_accept != nullptr ? 6 : 4;
     int E = a.expand_width <= 0 ? dflt : (a.expand_width > kQMaxE ? kQMaxE : a.expand_width);
     for (int q0 = 0; q0 < a.nq; q0 += chunk) {
         const int nqc = a.nq - q0 < chunk ? a.nq - q0 : chunk;
