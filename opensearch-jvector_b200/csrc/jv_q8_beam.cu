@@ -6,29 +6,31 @@
 // kernel of jv_q8.cu, which stays the path of filtered queries and of lists longer than 64).  The warps are specialised:
 //
 //   manager warp       owns the list.  The sorted list of the best L visited nodes (L <= 64) lives in its REGISTERS, two keys per
-//                      lane (shared memory holds the copy the merge scatters through); selection and the list merge are
-//                      warp-synchronous — no block barrier, no shared-memory atomics on the list, nothing replicated across
-//                      warps.  Per step: pick the E best unexpanded entries and hand them to the expander.  Merge: binary search
-//                      per survivor (one per lane), duplicates of list members dropped, ranks by counting over broadcast reads
-//                      of the survivor queue, scatter, reload.
+//                      lane (shared memory holds the copy the merge gathers and scatters through); selection and the list merge
+//                      are warp-synchronous — no block barrier, no shared-memory atomics on the list, nothing replicated across
+//                      warps.  Per step: pick the E best unexpanded entries and hand them to the expander.  Merge, without a loop
+//                      over the list: one survivor per lane; its slot = list entries better than it (binary search) + survivors
+//                      of the step better than it (counting over 16-byte broadcast reads of the queue); the list entries fill
+//                      the remaining slots in order — an occupancy mask of the survivor slots (two REDUX.OR) tells every output
+//                      slot which old entry it takes; one gather, one scatter, reload.
 //   expander warp      owns the visited filter (plain loads and stores, no atomics).  Per step: read the adjacency rows of the
 //                      selected entries (one coalesced 128-byte load each, all in flight together), test-and-insert the filter,
-//                      write the fresh ids to the pool, start their code rows towards L2, hand the pool to the scorers.  With the
-//                      manager merging step s while the expander prepares step s+1, neither the adjacency round trip nor the
+//                      start the fresh code rows towards L2, write the fresh ids to the pool, hand the pool to the scorers.  With
+//                      the manager merging step s while the expander prepares step s+1, neither the adjacency round trip nor the
 //                      filter chain is on the manager's critical path.
 //   scorer warps       score pools: 8 lanes per code row, all 16-byte code loads of a group's rows in flight before the first
-//                      table lookup, bank-conflict-free lookups (layout in jv_q8.cu); sums that beat the admission threshold the
-//                      manager published with the pool are queued (one shared-memory atomic per warp and pass).
+//                      table lookup, bank-conflict-free lookups at 3.25 instructions each (layout in jv_q8.cu); sums that beat the
+//                      list's worst entry — read from the manager's live copy — are queued (one shared-memory atomic per warp
+//                      and pass).
 //
 // Hand-over is three named barriers per step (bar.arrive / bar.sync, ids by step parity), so a waiting warp costs no issue
 // slots; the barrier itself orders the producer's shared-memory writes before the consumer's reads (PTX ISA, bar: producer /
-// consumer example), no fence instruction on the chain.  With depth 2 the manager selects and issues step s+1 BEFORE it merges the scores of step s: its bookkeeping
-// overlaps the scorers' DRAM round trip and lookups.  The selection then lags one step behind the scores — the same relaxation
-// as a wider step — and the result does not depend on timing (survivors are ranked by key, whatever their queue order).
-// expand_width = 1 runs at depth 1: exactly the best-first order of the oracle's 8-bit mode.
+// consumer example), no fence instruction on the chain.  With depth 2 the manager selects and issues step s+1 BEFORE it merges
+// the scores of step s: selection, expansion, scoring and merge of neighbouring steps overlap.  The selection then lags one step
+// behind the scores — the same relaxation as a wider step — and the result does not depend on timing (survivors are ranked by
+// key, whatever their queue order).  expand_width = 1 runs at depth 1: exactly the best-first order of the oracle's 8-bit mode.
 //
-// Measured alternatives: list merge on a 4-warp team with the expander as a separate warp (more
-// instructions per query, slower), manager-side threshold + compaction (1.1 k cycles per step on the critical path).
+// Measured alternatives: DESIGN.md section 6 (items 1-16).
 #include "jv_q8.cuh"
 
 namespace jv {
@@ -46,9 +48,9 @@ constexpr int kBarPool = 1;    // +parity: expander arrives, scorers sync (the p
 constexpr int kBarDone = 3;    // +parity: scorers arrive, manager syncs (the survivors of a step are queued)
 constexpr int kBarSel = 5;     // +parity: manager arrives, expander syncs (the selection of a step is published)
 
-// PROF: cycles of the manager (0 select, 3 wait for the scorers + survivors in registers, 11 binary search + duplicates, 12 rank loop, 13 scatter + reload, 6 rest of the merge, 4 query setup,
-// 5 emit), of the expander (2 wait for a selection, 1 adjacency + filter + pool) and of scorer warp 0 (8 wait for a pool,
-// 9 code words in registers, 10 lookups + queue); 7 = steps, 14 = survivors, 15 = merge rounds
+// PROF: cycles of the manager (0 select, 3 wait for the scorers + survivors in registers, 11 binary search + rank count, 12 occupancy
+// mask + gather, 13 scatter + reload, 6 rest of the merge, 4 query setup, 5 emit), of the expander (2 wait for a selection, 1 adjacency + filter + pool) and of scorer warp 0 (8 wait for a pool,
+// 9 code words in registers, 10 lookups + queue); 7 = steps, 14 = survivors, 15 = merge rounds that had to drop a copy
 template <int NJ, int SW, bool PROF>
 __global__ void __launch_bounds__((SW + 2) * 32, 4) q8_beam_kernel(const Q8Params p, const int depth) {
     constexpr int kT = (SW + 2) * 32, NG = SW * 4, kTS = SW * 32; // threads per CTA / row groups / scorer threads
