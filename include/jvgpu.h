@@ -166,7 +166,7 @@ typedef struct jv_search_params {
     float threshold;       /* JVectorKnnCollector.getThreshold(), default 0                      */
     float rerank_floor;    /* JVectorKnnCollector.getRerankFloor(), default 0                    */
     int32_t expand_width;  /* traversal schedule (GPU-side knob, not part of the reference API):
-                            *   0  default: the production kernel expands the 4 best unexpanded candidates per step
+                            *   0  default: the production kernel expands the 4 best unexpanded candidates per step (6 with accept_bits)
                             *   1..8 explicit width (clamped to what the kernel supports); 1 = the reference's best-first
                             *      order (up to exact score ties)
                             *  -1  strict kernel: candidate heap + result heap exactly as GraphSearcher;
