@@ -30,7 +30,7 @@
 // behind the scores — the same relaxation as a wider step — and the result does not depend on timing (survivors are ranked by
 // key, whatever their queue order).  expand_width = 1 runs at depth 1: exactly the best-first order of the oracle's 8-bit mode.
 //
-// Measured alternatives: DESIGN.md section 6 (items 1-16).
+// Measured alternatives: DESIGN.md section 6 (items 1-17).
 #include "jv_q8.cuh"
 
 namespace jv {
