@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(256, 2) lut_q8_kernel(const LutQ8Params p) {
         if (lane == 0) qn_s[t] = qn;
     }
     __syncthreads();
-    if (tid < QT) {
+    if (tid < QT) { // (every code-range slice of a tile computes the same scale; slice 0 publishes it)
         const float range = __uint_as_float(range_s[tid]);
         const float inv = range > 0.f ? __fdiv_rn(255.0f, range) : 0.f;
         float base = 0.f;
         for (int m = 0; m < p.M; m++) base = __fadd_rn(base, lo_s[tid * MP + m]);
         inv_s[tid] = inv;
-        if (q0 + tid < p.nq) p.qparams[q0 + tid] = make_float4(__fdiv_rn(range, 255.0f), base, qn_s[tid], 0.f);
+        if (q0 + tid < p.nq && blockIdx.y == 0) p.qparams[q0 + tid] = make_float4(__fdiv_rn(range, 255.0f), base, qn_s[tid], 0.f);
     }
     __syncthreads();
 
@@ -238,10 +238,13 @@ __global__ void __launch_bounds__(256, 2) lut_q8_kernel(const LutQ8Params p) {
             }
             cp_async_commit();
         };
-        issue(0, 0);
-        for (int ch = 0; ch < NCHUNK; ch++) {
+        // small batches: gridDim.y CTAs share a tile, each builds the entries of a range of code chunks (latency: one query's table
+        // is the work of NJ warps x gridDim.y CTAs instead of NJ warps)
+        const int ch0 = (int)blockIdx.y * NCHUNK / (int)gridDim.y, ch1 = ((int)blockIdx.y + 1) * NCHUNK / (int)gridDim.y;
+        issue(ch0, ch0 & 1);
+        for (int ch = ch0; ch < ch1; ch++) {
             const int buf = ch & 1;
-            if (ch + 1 < NCHUNK) {
+            if (ch + 1 < ch1) {
                 issue(ch + 1, buf ^ 1);
                 cp_async_wait<1>();
             } else {
@@ -333,11 +336,14 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
     const size_t smem = lut_q8_smem(nw, S, p.NJ * 32);
     const int qt = S == 2 ? 8 : 32 / S;
     const int grid = (nq + qt - 1) / qt;
+    // code-range slices per tile: fill the machine when the batch alone does not (2 CTAs per SM)
+    int slices = 1;
+    while (slices < 8 && grid * slices * 2 <= 2 * ix->sm_count) slices *= 2;
     const bool l2 = ix->sim == JV_SIM_EUCLIDEAN;
 #define JV_LUT_LAUNCH(SV, LV)                                                                                              \
     do {                                                                                                                   \
         JV_CUDA_TRY(cudaFuncSetAttribute(lut_q8_kernel<SV, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        lut_q8_kernel<SV, LV><<<grid, nw * 32, smem, stream>>>(p);                                                          \
+        lut_q8_kernel<SV, LV><<<dim3(grid, slices), nw * 32, smem, stream>>>(p);                                                          \
     } while (0)
     if (S == 4) {
         if (l2) JV_LUT_LAUNCH(4, true); else JV_LUT_LAUNCH(4, false);
