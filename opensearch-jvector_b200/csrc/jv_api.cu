@@ -583,10 +583,16 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
     SearchCtx *c = lease.c;
     const size_t qbytes = (size_t)nq * ix->dim * 4, kb = (size_t)nq * p->k * 4;
     JV_TRY(c->queries.ensure(qbytes));
-    JV_TRY(c->out_doc.ensure(kb));
+    // small batches (latency path): ids, scores, counts and counters share one device buffer and leave in ONE copy into the
+    // context's page-locked staging area, from where the host splits them into the caller's buffers (4 small copies -> 1)
+    const size_t sb = (size_t)nq * sizeof(jv_query_stats);
+    const size_t packed_bytes = 2 * kb + (size_t)nq * 4 + sb;
+    const bool packed = packed_bytes <= 64 * 1024;
+    JV_TRY(c->out_doc.ensure(packed ? packed_bytes : kb));
     JV_TRY(c->out_score.ensure(kb));
     JV_TRY(c->out_count.ensure((size_t)nq * 4));
-    JV_TRY(c->stats.ensure((size_t)nq * sizeof(jv_query_stats)));
+    JV_TRY(c->stats.ensure(sb));
+    if (packed) JV_TRY(c->ensure_pinned(packed_bytes));
     const uint64_t *d_accept = nullptr;
     size_t abytes = 0;
     if (p->accept_bits) {
@@ -674,6 +680,22 @@ int32_t jv_search_batch(jv_index *ix, const float *queries, int32_t nq, const jv
         return JV_OK;
     } else {
         if (!zero_copy) JV_CUDA_TRY(cudaMemcpyAsync(c->queries.p, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+        if (packed) {
+            char *base = static_cast<char *>(c->out_doc.p);
+            JV_TRY(search_core(ix, c, d_q, nq, p, d_accept, reinterpret_cast<int32_t *>(base), reinterpret_cast<float *>(base + kb),
+                               reinterpret_cast<int32_t *>(base + 2 * kb), reinterpret_cast<jv_query_stats *>(base + 2 * kb + (size_t)nq * 4),
+                               &launches));
+            JV_CUDA_TRY(cudaMemcpyAsync(c->pinned, base, stats ? packed_bytes : packed_bytes - sb, cudaMemcpyDeviceToHost, c->stream));
+            JV_CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+            JV_CUDA_TRY(cudaStreamSynchronize(c->stream));
+            const char *h = static_cast<const char *>(c->pinned);
+            memcpy(out_doc, h, kb);
+            memcpy(out_score, h + kb, kb);
+            memcpy(out_count, h + 2 * kb, (size_t)nq * 4);
+            if (stats) memcpy(stats, h + 2 * kb + (size_t)nq * 4, sb);
+            fill_timing(c, timing, launches, true);
+            return JV_OK;
+        }
         JV_TRY(search_core(ix, c, d_q, nq, p, d_accept, c->out_doc.as<int32_t>(), c->out_score.as<float>(),
                            c->out_count.as<int32_t>(), c->stats.as<jv_query_stats>(), &launches));
     }

@@ -45,7 +45,7 @@ int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int 
                       const uint64_t *d_approx_keys, const int32_t *d_approx_count, int32_t *d_out_doc, float *d_out_score,
                       int32_t *d_out_count, jv_query_stats *d_stats, int *launches) {
     if (nq <= 0) return JV_OK;
-    const int threads = nq * 4 <= ix->sm_count ? 512 : kRerankThreads; // a batch that leaves most SMs empty: wide CTAs
+    const int threads = nq <= ix->sm_count ? 512 : kRerankThreads; // a batch that leaves SMs empty: wide CTAs
     size_t smem = ((((size_t)ix->dim * 4) + 15) & ~(size_t)15) + (size_t)rerank_k * 8;
     NvqView nvq{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
     if (ix->has_nvq) {

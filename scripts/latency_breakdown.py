@@ -16,7 +16,8 @@ hq = torch.from_numpy(host["queries"]).pin_memory()
 h_doc = torch.empty(64, k, dtype=torch.int32).pin_memory()
 h_score = torch.empty(64, k, dtype=torch.float32).pin_memory()
 h_cnt = torch.empty(64, dtype=torch.int32).pin_memory()
-p = gi._params(k, rk, 0.0, 0.0, None, 0, 0)
+E = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # expand width (0 = library default)
+p = gi._params(k, rk, 0.0, 0.0, None, 0, E)
 t = N.BatchTiming()
 for nq in (1, 8, 64):
     rows = []
@@ -26,4 +27,4 @@ for nq in (1, 8, 64):
                                     h_cnt.data_ptr(), None, C.addressof(t)))
         rows.append(((time.perf_counter() - t0) * 1e3, t.total_ms, t.h2d_ms, t.lut_ms, t.search_ms, t.rerank_ms, t.d2h_ms))
     r = np.median(np.array(rows[20:]), axis=0)
-    print(f"nq {nq:3d}: wall {r[0]*1e3:6.1f} us | device total {r[1]*1e3:6.1f} us = h2d {r[2]*1e3:5.1f} + search {r[4]*1e3:5.1f} (table build {r[3]*1e3:5.1f}) + rerank {r[5]*1e3:5.1f} + d2h {r[6]*1e3:5.1f}")
+    print(f"E {E} nq {nq:3d}: wall {r[0]*1e3:6.1f} us | device total {r[1]*1e3:6.1f} us = h2d {r[2]*1e3:5.1f} + search {r[4]*1e3:5.1f} (table build {r[3]*1e3:5.1f}) + rerank {r[5]*1e3:5.1f} + d2h {r[6]*1e3:5.1f}")
