@@ -312,3 +312,22 @@ def test_beam_kernel_full_list_wide_rows_and_filter_evictions(jv, fx_dot192_wide
             # same-set tags written by one adjacency chunk survives in the visited filter is up to the hardware
             np.testing.assert_array_equal(r.stats[:, 1:], r2.stats[:, 1:])
             assert np.abs(r.stats[:, 0].astype(np.int64) - r2.stats[:, 0]).max() <= 0.02 * r.stats[:, 0].max() + 8
+
+
+def test_small_batches_take_the_latency_shapes_and_return_the_same_results(jv, fx_dot192):
+    """One query at a time (table build split over 8 CTAs, 16-warp rerank, one packed result copy) against the same queries inside a
+    batch large enough for the throughput shapes: ids, score bits and counters must be identical."""
+    fx = fx_dot192
+    with fx.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
+        big = np.tile(fx.queries, (5, 1))  # 320 queries: more than one per SM
+        rb = gi.search(big, 10, 50)
+        for nq in (1, 3, len(fx.queries)):
+            rs = gi.search(fx.queries[:nq], 10, 50)
+            np.testing.assert_array_equal(rs.docs, rb.docs[:nq])
+            np.testing.assert_array_equal(rs.scores, rb.scores[:nq])
+            np.testing.assert_array_equal(rs.counts, rb.counts[:nq])
+            np.testing.assert_array_equal(rs.stats[:, 1:], rb.stats[:nq, 1:])
+        q8_one, prm_one = gi.pq_lut_q8(fx.queries[:1])  # 8 code-range slices
+        q8_all, prm_all = gi.pq_lut_q8(big)             # 2 slices
+        np.testing.assert_array_equal(q8_one[0], q8_all[0])
+        np.testing.assert_array_equal(prm_one[0].view(np.uint32), prm_all[0].view(np.uint32))
