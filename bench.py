@@ -631,6 +631,23 @@ def main():
     e2e_pageable = nq * psteps / (time.perf_counter() - e0)
     pageable_same = bool((pg[0] == h_doc).all())
 
+    # ---- serving view: the same call with 1 and 64 queries (wall clock per call, page-locked buffers; the CPU arm's single-thread
+    # latency per query is `cpu_baseline.one_thread_ms_per_query`)
+    latency = None
+    if world == 1 and h_bits is None:
+        latency = {"unit": "ms per jv_search_batch call (wall clock, median of 100)"}
+        for lnq in (1, 64):
+            if lnq > nq:
+                continue
+            ts = []
+            for it in range(120):
+                off = (it * lnq) % max(1, nq - lnq)
+                t0 = time.perf_counter()
+                N.check(lib.jv_search_batch(gi.handle, hq_p + off * dim * 4, lnq, C.addressof(p), h_doc_p, h_score_p, h_cnt_p, None, None))
+                ts.append((time.perf_counter() - t0) * 1e3)
+            latency[f"batch_{lnq}"] = float(np.median(ts[20:]))
+        N.check(lib.jv_search_batch(gi.handle, hq_p, nq, C.addressof(p), h_doc_p, h_score_p, h_cnt_p, h_stats_p, None))  # restore the batch results
+
     # ---- the same call from TWO host threads at once (Lucene searches the leaves of a shard from a thread pool, and the
     # reference reader is shared between threads: KNNJVectorTests.java:982-1028): the copies of one caller overlap the kernels
     # of the other.  Reported next to the single-caller number, never instead of it.
@@ -721,6 +738,7 @@ def main():
         "e2e_pageable": {"value": e2e_pageable, "unit": "queries/s", "note": "same jv_search_batch call from pageable host buffers (single rank figure)",
                          "results_identical": pageable_same},
         "e2e_two_callers": e2e_conc,
+        "latency": latency,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
