@@ -17,6 +17,8 @@ struct SearchCtx {
     DevBuf visited;                   // global visited tables (fallback when they do not fit in smem)
     DevBuf lut8, qparams;             // 8-bit ADC tables of the current chunk + per-query (delta, base, ||q||^2)
     DevBuf slice_doc, slice_score;    // brute force: per-slice partial top-k
+    DevBuf dd_bitmap, dd_base, dd_blocks, dd_uniq, dd_rows; // de-duplicated rerank rows of a batch (vectors in host memory): bitmap over
+                                      // the ordinals, rank base per bitmap word, block sums, marked ordinals, gathered rows
     DevBuf tc_q, tc_f, tc_chunk, tc_cand, tc_cnt, tc_redo; // brute force on the tensor cores (jv_exact_tc.cu): bf16 queries, per-query floats,
                                       // pass-A chunk maxima, pass-B candidates + counts
     bool lut_timed = false;           // ev[5] was recorded after the first chunk's table build
@@ -82,6 +84,7 @@ struct Q8Knobs {
     bool fused = false; // JVGPU_Q8_FUSED: K3 as the epilogue of the synchronous kernel
     bool sync = false;  // JVGPU_Q8_SYNC: the round-synchronous kernel of jv_q8.cu instead of the manager / scorer kernel (jv_q8_beam.cu)
     int depth = 0;      // JVGPU_Q8_DEPTH: steps in flight of the manager / scorer kernel (1 or 2; default 2)
+    int rerank_dedupe = -1; // JVGPU_RERANK_DEDUPE: gather the rerank rows of a batch once when the vectors live in host memory (1 always, 0 never, unset = large batches)
     bool h2d_single = false; // JVGPU_H2D_SINGLE: no chunked H2D pipeline in jv_search_batch
     int exact_tc = -1;  // JVGPU_EXACT_TC: brute force on the tensor cores (jv_exact_tc.cu): 1 always (tests), 0 never, unset = by size
 };

@@ -41,6 +41,7 @@ void q8_knobs_refresh() {
     v.fused = getenv("JVGPU_Q8_FUSED") != nullptr;
     v.sync = getenv("JVGPU_Q8_SYNC") != nullptr;
     if (const char *e = getenv("JVGPU_Q8_DEPTH")) v.depth = atoi(e);
+    if (const char *e = getenv("JVGPU_RERANK_DEDUPE")) v.rerank_dedupe = atoi(e) != 0 ? 1 : 0;
     v.h2d_single = getenv("JVGPU_H2D_SINGLE") != nullptr;
     if (const char *e = getenv("JVGPU_EXACT_TC")) v.exact_tc = atoi(e) != 0 ? 1 : 0;
     g_knobs = v;

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(THREADS)
 rerank_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_norm, const int32_t *__restrict__ ord_to_doc,
               int dim, int sim, int has_pq, const float *__restrict__ queries, int k, int L, float rerank_floor,
               const uint64_t *__restrict__ approx_keys, const int32_t *__restrict__ approx_count, int32_t *out_doc,
-              float *out_score, int32_t *out_count, jv_query_stats *stats, NvqView nvq) {
+              float *out_score, int32_t *out_count, jv_query_stats *stats, NvqView nvq, RowMap rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sq = reinterpret_cast<float *>(smem_raw);
     const size_t qb = (((size_t)dim * 4) + 15) & ~(size_t)15;
@@ -37,8 +37,153 @@ rerank_kernel(const float *__restrict__ vectors, const float *__restrict__ vec_n
     const bool vec4 = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
     const int reranked = rerank_query<THREADS>(vectors, vec_norm, ord_to_doc, dim, sim, has_pq, queries + (int64_t)qi * dim, vec4, k,
                                                       approx_count[qi], rerank_floor, approx_keys + (int64_t)qi * L, sq, keys,
-                                                      out_doc + (int64_t)qi * k, out_score + (int64_t)qi * k, out_count + qi, nvq);
+                                                      out_doc + (int64_t)qi * k, out_score + (int64_t)qi * k, out_count + qi, nvq, rows);
     if (threadIdx.x == 0 && stats) stats[qi].reranked = reranked;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Rerank rows of a batch, de-duplicated (rerank vectors in pinned host memory, BASELINE config 5): the candidates of the 10k
+// queries of a batch overlap, and every row read by the rerank kernel crosses PCIe.  Mark the rows the batch needs in a bitmap
+// over the ordinals, rank the set bits (popcount prefix sum), stream every needed row ONCE from host memory into a dense staging
+// array in HBM (one warp per row, 16-byte loads, many rows in flight), and let the rerank kernel read the staging array through
+// the row map.  Same rows, same arithmetic: ids and score bits are unchanged.
+// ------------------------------------------------------------------------------------------------
+__global__ void dd_mark_kernel(const uint64_t *__restrict__ approx_keys, const int32_t *__restrict__ approx_count, int nq, int L, int64_t n,
+                               uint32_t *bitmap) {
+    const int64_t total = (int64_t)nq * L;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i / L), j = (int)(i - (int64_t)q * L);
+        if (j >= approx_count[q]) continue;
+        const uint64_t key = approx_keys[i];
+        if (key == 0ull) continue;
+        const int32_t node = jv_key_id(key);
+        if (node >= 0 && node < n) atomicOr(bitmap + (node >> 5), 1u << (node & 31));
+    }
+}
+constexpr int kDdBlock = 256, kDdWordsPerThread = 4, kDdWordsPerBlock = kDdBlock * kDdWordsPerThread;
+// pass 1: set bits per block of 1024 bitmap words
+__global__ void __launch_bounds__(kDdBlock) dd_block_sums_kernel(const uint32_t *__restrict__ bitmap, int64_t words, int32_t *block_sums) {
+    __shared__ int s_warp[kDdBlock / 32];
+    const int64_t w0 = (int64_t)blockIdx.x * kDdWordsPerBlock + (int64_t)threadIdx.x * kDdWordsPerThread;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kDdWordsPerThread; i++)
+        if (w0 + i < words) c += __popc(bitmap[w0 + i]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(JV_FULL_MASK, c, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < kDdBlock / 32; i++) t += s_warp[i];
+        block_sums[blockIdx.x] = t;
+    }
+}
+// pass 2 (one block): exclusive prefix sum of the block sums in place, total behind them
+__global__ void __launch_bounds__(1024) dd_scan_blocks_kernel(int32_t *block_sums, int nblocks, int32_t *total) {
+    __shared__ int s_part[1024];
+    const int per = (nblocks + 1023) / 1024, b0 = threadIdx.x * per;
+    int c = 0;
+    for (int i = 0; i < per; i++)
+        if (b0 + i < nblocks) c += block_sums[b0 + i];
+    s_part[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan
+        const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_part[threadIdx.x] - c; // exclusive prefix of this thread's range
+    for (int i = 0; i < per; i++)
+        if (b0 + i < nblocks) {
+            const int v = block_sums[b0 + i];
+            block_sums[b0 + i] = run;
+            run += v;
+        }
+    if (threadIdx.x == 1023) *total = s_part[1023];
+}
+// pass 3: rank base of every bitmap word + the list of marked ordinals in ascending order
+__global__ void __launch_bounds__(kDdBlock) dd_rank_kernel(const uint32_t *__restrict__ bitmap, int64_t words, const int32_t *__restrict__ block_sums,
+                                                           int32_t *base, int32_t *uniq) {
+    __shared__ int s_warp[kDdBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * kDdWordsPerBlock + (int64_t)threadIdx.x * kDdWordsPerThread;
+    uint32_t bits[kDdWordsPerThread];
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kDdWordsPerThread; i++) {
+        bits[i] = w0 + i < words ? bitmap[w0 + i] : 0u;
+        c += __popc(bits[i]);
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(JV_FULL_MASK, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int run = block_sums[blockIdx.x] + incl - c;
+    for (int i = 0; i < warp; i++) run += s_warp[i];
+#pragma unroll
+    for (int i = 0; i < kDdWordsPerThread; i++) {
+        if (w0 + i >= words) break;
+        base[w0 + i] = run;
+        uint32_t b = bits[i];
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1u;
+            uniq[run++] = (int32_t)((w0 + i) * 32 + bit);
+        }
+    }
+}
+// gather: one warp per needed row, host (zero-copy) -> staging in HBM
+__global__ void __launch_bounds__(256) dd_gather_kernel(const float *__restrict__ vectors, const int32_t *__restrict__ uniq, const int32_t *__restrict__ total,
+                                                        int dim, float *staging) {
+    const int n_rows = *total, lane = threadIdx.x & 31;
+    const int warps = (int)((gridDim.x * blockDim.x) >> 5);
+    const bool v4 = (dim & 3) == 0;
+    for (int r = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_rows; r += warps) {
+        const float *src = vectors + (int64_t)uniq[r] * dim;
+        float *dst = staging + (int64_t)r * dim;
+        if (v4) {
+            for (int i = lane; i < dim / 4; i += 32) reinterpret_cast<float4 *>(dst)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+        } else {
+            for (int i = lane; i < dim; i += 32) dst[i] = __ldg(src + i);
+        }
+    }
+}
+
+// builds the row map of a batch on ctx->stream; returns the staging array to read instead of the host vectors
+static int32_t dedupe_rows(jv_index *ix, SearchCtx *ctx, int nq, int L, const uint64_t *d_approx_keys, const int32_t *d_approx_count, RowMap *rows,
+                           const float **staging, int *launches) {
+    const int64_t words = (ix->n + 31) / 32;
+    const int nblocks = (int)((words + kDdWordsPerBlock - 1) / kDdWordsPerBlock);
+    int64_t cap = (int64_t)nq * L; // rows the batch can need at most
+    if (cap > ix->n) cap = ix->n;
+    JV_TRY(ctx->dd_bitmap.ensure((size_t)words * 4));
+    JV_TRY(ctx->dd_base.ensure((size_t)words * 4));
+    JV_TRY(ctx->dd_blocks.ensure((size_t)(nblocks + 1) * 4));
+    JV_TRY(ctx->dd_uniq.ensure((size_t)cap * 4));
+    JV_TRY(ctx->dd_rows.ensure((size_t)cap * ix->dim * 4));
+    uint32_t *bitmap = ctx->dd_bitmap.as<uint32_t>();
+    int32_t *blocks = ctx->dd_blocks.as<int32_t>(), *total = blocks + nblocks;
+    JV_CUDA_TRY(cudaMemsetAsync(bitmap, 0, (size_t)words * 4, ctx->stream));
+    int64_t mb = ((int64_t)nq * L + 255) / 256;
+    if (mb > 148 * 32) mb = 148 * 32;
+    dd_mark_kernel<<<(int)mb, 256, 0, ctx->stream>>>(d_approx_keys, d_approx_count, nq, L, ix->n, bitmap);
+    dd_block_sums_kernel<<<nblocks, kDdBlock, 0, ctx->stream>>>(bitmap, words, blocks);
+    dd_scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(blocks, nblocks, total);
+    dd_rank_kernel<<<nblocks, kDdBlock, 0, ctx->stream>>>(bitmap, words, blocks, ctx->dd_base.as<int32_t>(), ctx->dd_uniq.as<int32_t>());
+    dd_gather_kernel<<<ix->sm_count * 8, 256, 0, ctx->stream>>>(ix->vectors_dev, ctx->dd_uniq.as<int32_t>(), total, ix->dim, ctx->dd_rows.as<float>());
+    JV_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 5;
+    rows->bitmap = bitmap;
+    rows->base = ctx->dd_base.as<int32_t>();
+    *staging = ctx->dd_rows.as<float>();
+    return JV_OK;
 }
 
 int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int nq, int k, int rerank_k, float rerank_floor,
@@ -57,16 +202,23 @@ int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int 
         smem = ((smem + 15) & ~(size_t)15) + (size_t)(threads / 32) * (((((size_t)ix->dim * 4) + 15) & ~(size_t)15) + (size_t)ix->nvq_m * 16);
     }
     JV_REQUIRE(smem <= ix->smem_optin - 1024, "rerank_k %d too large for shared memory", rerank_k);
+    // rerank vectors in host memory: every row crosses PCIe, so large batches gather the rows they need once (JVGPU_RERANK_DEDUPE=1
+    // forces it for any batch, =0 turns it off)
+    RowMap rows{nullptr, nullptr};
+    const float *vectors = ix->vectors_dev;
+    const int dd = q8_knobs().rerank_dedupe;
+    if (ix->vectors_on_host && ix->has_pq && !ix->has_nvq && dd != 0 && (dd == 1 || (int64_t)nq * rerank_k >= 65536))
+        JV_TRY(dedupe_rows(ix, ctx, nq, rerank_k, d_approx_keys, d_approx_count, &rows, &vectors, launches));
     if (threads == 512) {
         JV_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rerank_kernel<512><<<nq, 512, smem, ctx->stream>>>(
-            ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, ix->has_pq ? 1 : 0,
-            d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats, nvq);
+            vectors, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, ix->has_pq ? 1 : 0,
+            d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats, nvq, rows);
     } else {
         JV_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel<kRerankThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rerank_kernel<kRerankThreads><<<nq, kRerankThreads, smem, ctx->stream>>>(
-            ix->vectors_dev, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, ix->has_pq ? 1 : 0,
-            d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats, nvq);
+            vectors, ix->vec_norm.as<float>(), ix->ord_to_doc.as<int32_t>(), ix->dim, ix->sim, ix->has_pq ? 1 : 0,
+            d_queries, k, rerank_k, rerank_floor, d_approx_keys, d_approx_count, d_out_doc, d_out_score, d_out_count, d_stats, nvq, rows);
     }
     JV_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;

@@ -67,12 +67,26 @@ __device__ __forceinline__ const float *nvq_decode_warp(const NvqView &v, int32_
 // sq: shared memory for the query (dim floats, 16-B aligned); keys: shared memory for cnt keys; akeys: the approximate
 // list, best first (shared or global memory).  All THREADS threads of the CTA must call this (it synchronises).
 // Returns (in every thread) the number of reranked candidates.
+// Row map of a de-duplicated batch (rerank vectors in host memory, jv_rerank.cu): the rows every query of the batch needs were
+// gathered once into a dense staging array in HBM; row(node) = base[node / 32] + popc(bits of the word below the node's).
+// bitmap == nullptr: the identity (vectors indexed by ordinal).
+struct RowMap {
+    const uint32_t *bitmap;
+    const int32_t *base;
+};
+__device__ __forceinline__ int64_t row_of(const RowMap &m, int32_t node) {
+    if (m.bitmap == nullptr) return node;
+    const uint32_t w = __ldg(m.bitmap + (node >> 5));
+    return (int64_t)__ldg(m.base + (node >> 5)) + __popc(w & ((1u << (node & 31)) - 1u));
+}
+
 template <int THREADS>
 __device__ __forceinline__ int rerank_query(const float *__restrict__ vectors, const float *__restrict__ vec_norm,
                                             const int32_t *__restrict__ ord_to_doc, int dim, int sim, int has_pq,
                                             const float *__restrict__ gq, bool vec4, int k, int cnt, float rerank_floor,
                                             const uint64_t *akeys, float *sq, uint64_t *keys, int32_t *out_doc, float *out_score,
-                                            int32_t *out_count, const NvqView nvq = NvqView{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr}) {
+                                            int32_t *out_count, const NvqView nvq = NvqView{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr},
+                                            const RowMap rows = RowMap{nullptr, nullptr}) {
     __shared__ float s_qnorm;
     __shared__ int s_valid, s_reranked;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -103,7 +117,7 @@ __device__ __forceinline__ int rerank_query(const float *__restrict__ vectors, c
                                                   : jv_warp_reduce_pair<false, false>(sq, x, dim, lane, v4);
                     if (sim == JV_SIM_COSINE) xn = jv_warp_reduce_pair<false, false>(x, x, dim, lane, v4);
                 } else {
-                    const float *x = vectors + (int64_t)node * dim;
+                    const float *x = vectors + row_of(rows, node) * dim;
                     raw = sim == JV_SIM_EUCLIDEAN ? jv_warp_reduce_pair<true>(sq, x, dim, lane, vec4)
                                                   : jv_warp_reduce_pair<false>(sq, x, dim, lane, vec4);
                     if (sim == JV_SIM_COSINE) xn = __ldg(vec_norm + node);

@@ -228,7 +228,7 @@ def test_large_host_batches_are_pipelined_in_chunks(jv, fx_dot):
                 np.testing.assert_array_equal(r.stats[t:t + m, 1:], small.stats[:m, 1:])
 
 
-def test_vectors_in_pinned_host_memory_and_wide_graphs(jv, fx_dot):
+def test_vectors_in_pinned_host_memory_and_wide_graphs(jv, fx_dot, monkeypatch):
     """cfg 5 flavour: fp32 rerank vectors stay in pinned host memory (K3 gathers them over PCIe) while the 8-bit table
     traversal runs from HBM; and a graph with R = 64 (two adjacency chunks per candidate, <= 256 queued survivors)."""
     fx = fx_dot
@@ -237,6 +237,27 @@ def test_vectors_in_pinned_host_memory_and_wide_graphs(jv, fx_dot):
         ra, rb = a.search(fx.queries, 10, 50), b.search(fx.queries, 10, 50)
         np.testing.assert_array_equal(ra.docs, rb.docs)
         np.testing.assert_array_equal(ra.scores, rb.scores)
+        # large batches gather the rows they need ONCE from host memory into HBM (bitmap over the ordinals, popcount ranks, dense
+        # staging array, row map in the rerank kernel): forced here for a small batch, same ids / score bits / counters; repeated
+        # queries make most rows duplicates
+        many = np.tile(fx.queries, (3, 1))
+        for knob in ("1", "0"):
+            monkeypatch.setenv("JVGPU_RERANK_DEDUPE", knob)
+            b.refresh_knobs()
+            rk = b.search(many, 10, 50)
+            for t in range(3):
+                sl = slice(t * len(fx.queries), (t + 1) * len(fx.queries))
+                np.testing.assert_array_equal(rk.docs[sl], ra.docs)
+                np.testing.assert_array_equal(rk.scores[sl], ra.scores)
+                np.testing.assert_array_equal(rk.stats[sl, 1:], ra.stats[:, 1:])
+            rt = b.search(fx.queries[:7], 20, 200, rerank_floor=float(np.median(ra.scores)))  # rows below the floor are marked but not read
+            monkeypatch.setenv("JVGPU_RERANK_DEDUPE", "0")
+            b.refresh_knobs()
+            r0 = b.search(fx.queries[:7], 20, 200, rerank_floor=float(np.median(ra.scores)))
+            np.testing.assert_array_equal(rt.docs, r0.docs)
+            np.testing.assert_array_equal(rt.scores, r0.scores)
+        monkeypatch.delenv("JVGPU_RERANK_DEDUPE")
+        b.refresh_knobs()
     base, q = clustered(4000, 64, 40, seed=12, normalize=True)
     wide = make_fixture(O.SIM_DOT, base, q, max_degree=64, pq_m=16)
     with wide.gpu_index(jv, flags=jv.native.FLAG_LUT_U8) as gi:
