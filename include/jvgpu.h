@@ -85,7 +85,8 @@ typedef enum jv_status {
                                           (R*M bytes per node) so one expansion is one contiguous read */
 #define JV_INDEX_FLAG_LUT_F16 2u      /* hold the per-query ADC table in fp16 in shared memory
                                           (steering scores only; final scores are the exact rerank) */
-#define JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE 4u /* keep the fp32 vectors in pinned host memory (cfg 5) */
+#define JV_INDEX_FLAG_NO_VECTORS_ON_DEVICE 4u /* keep the fp32 vectors in pinned host memory (cfg 5): the rerank reads them over PCIe;
+                                               * large batches gather the rows they need once into HBM (de-duplicated), results unchanged */
 #define JV_INDEX_FLAG_LUT_U8 8u      /* production traversal: per-query ADC table quantised to bytes with one scale per
                                           query (integer sums, fused-ADC style), built by a batched kernel and staged
                                           into shared memory with TMA; needs K = 256 and dim % M == 0 with sub-vector
