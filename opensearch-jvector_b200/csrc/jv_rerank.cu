@@ -207,8 +207,13 @@ int32_t launch_rerank(jv_index *ix, SearchCtx *ctx, const float *d_queries, int 
     RowMap rows{nullptr, nullptr};
     const float *vectors = ix->vectors_dev;
     const int dd = q8_knobs().rerank_dedupe;
-    if (ix->vectors_on_host && ix->has_pq && !ix->has_nvq && dd != 0 && (dd == 1 || (int64_t)nq * rerank_k >= 65536))
-        JV_TRY(dedupe_rows(ix, ctx, nq, rerank_k, d_approx_keys, d_approx_count, &rows, &vectors, launches));
+    if (ix->vectors_on_host && ix->has_pq && !ix->has_nvq && dd != 0 && (dd == 1 || (int64_t)nq * rerank_k >= 65536)) {
+        if (dedupe_rows(ix, ctx, nq, rerank_k, d_approx_keys, d_approx_count, &rows, &vectors, launches) != JV_OK) {
+            cudaGetLastError(); // no room for the staging array: read the rows in place, as before
+            rows = RowMap{nullptr, nullptr};
+            vectors = ix->vectors_dev;
+        }
+    }
     if (threads == 512) {
         JV_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rerank_kernel<512><<<nq, 512, smem, ctx->stream>>>(
