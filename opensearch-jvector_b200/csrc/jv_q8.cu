@@ -404,6 +404,10 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
 
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_query, s_ns[2], s_nn[2], s_ndup[2], w_sel[kQW][2 * kQMaxE], w_pos[kQW][2 * kQMaxE];
+    // filtered queries: (an upper bound of) the accepted entries in the list and a lower bound of the first unexpanded position —
+    // while fewer than L entries are accepted there is no admission threshold inside the list and every unexpanded entry is
+    // eligible, so the selection scans from the first unexpanded entry and stops at 2E instead of walking the whole list
+    __shared__ int s_nacc, s_first;
 
     const bool tagged = p.n <= ((int64_t)1 << (p.hash_log2 + 15));
     const bool isum_keys = p.sim != JV_SIM_COSINE;
@@ -511,8 +515,13 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
             if (warp == 0) {
                 const uint32_t s = row_sum(g == 0 ? p.entry : -1);
                 if (lane == 0) {
-                    list0[0] = pack_key(s, p.entry);
+                    const uint64_t ek = pack_key(s, p.entry);
+                    list0[0] = ek;
                     q_filter_insert(filter, p.hash_log2, tagged, p.entry);
+                    if (FILT) {
+                        s_nacc = (ek & 2ull) ? 1 : 0;
+                        s_first = 0;
+                    }
                 }
             }
             n = 1;
@@ -541,6 +550,24 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                     if (found >= 2 * E) break;
                 }
                 worst = n >= L ? (list[L - 1] >> 1) : 0ull;
+            } else if (s_nacc < L) {
+                // fewer than L accepted entries in the whole list: no threshold, every unexpanded entry is eligible
+                for (int c0 = s_first & ~31; c0 < n; c0 += 32) {
+                    const int i = c0 + lane;
+                    const uint64_t k = i < n ? list[i] : 0ull;
+                    const bool un = i < n && (k & 1ull);
+                    const uint32_t ballot = __ballot_sync(JV_FULL_MASK, un);
+                    const int rank = found + __popc(ballot & ((1u << lane) - 1u));
+                    if (un && rank < 2 * E) {
+                        w_sel[warp][rank] = qkey_node_f(k);
+                        w_pos[warp][rank] = i;
+                    }
+                    found += __popc(ballot);
+                    if (found >= 2 * E) break;
+                }
+                worst = n >= Lc ? (list[Lc - 1] >> 1) : 0ull;
+                __syncwarp();
+                if (tid == 0 && found > 0) s_first = w_pos[0][0]; // entries in front of it are expanded (they only move down)
             } else {
                 // only entries with fewer than L accepted entries in front of them can still be expanded; the L-th accepted
                 // entry's key is the admission threshold (the worst of rerankK accepted results)
@@ -763,10 +790,25 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                     const uint64_t a = surv[t];
                     // copies of my key among this warp's 32 survivors (one MATCH instruction); earlier queue index wins ties
                     const uint32_t same = __match_any_sync(__activemask(), a) & ((1u << lane) - 1u);
+                    int ins_pos = 0x7fffffff;
+                    bool ins_acc = false;
                     if (a != 0ull) {
                         const int t0 = t & ~31; // this warp's survivors start here
                         const int pos = (c == 0 ? my_pos0 : my_pos1) + count_better(t0, a) + __popc(same);
-                        if (pos < Lc) out[pos] = (a << 1) | 1ull;
+                        if (pos < Lc) {
+                            out[pos] = (a << 1) | 1ull;
+                            ins_pos = pos;
+                            ins_acc = (a & 1ull) != 0ull; // bit 1 of the list key
+                        }
+                    }
+                    if (FILT) { // bookkeeping of the selection's fast path: accepted entries gained, first unexpanded position
+                        const uint32_t am = __activemask();
+                        const int lo_pos = __reduce_min_sync(am, ins_pos);
+                        const int gained = __popc(__ballot_sync(am, ins_acc));
+                        if (lane == __ffs(am) - 1) {
+                            if (gained) atomicAdd(&s_nacc, gained);
+                            if (lo_pos != 0x7fffffff) atomicMin(&s_first, lo_pos);
+                        }
                     }
                 }
             }
@@ -793,11 +835,19 @@ __global__ void __launch_bounds__(W * 32, q8_min_ctas(NJ_T, W, FILT)) q8_search_
                     const int d = w_pos[warp][e] - c0;
                     if (d >= 0 && d < 32) selmask |= 1u << d;
                 }
+                bool lost_acc = false;
                 if (t < n) {
                     uint64_t k = list[t];
                     if ((selmask >> lane) & 1u) k &= ~1ull;
                     const int pos = t + offset + v;
-                    if (pos < Lc) out[pos] = k;
+                    if (pos < Lc)
+                        out[pos] = k;
+                    else
+                        lost_acc = FILT && (k & 2ull) != 0ull; // an accepted entry falls off the end of the list
+                }
+                if (FILT) {
+                    const int lost = __popc(__ballot_sync(JV_FULL_MASK, lost_acc));
+                    if (lost && lane == 0) atomicSub(&s_nacc, lost);
                 }
             }
             __syncthreads(); // B2
