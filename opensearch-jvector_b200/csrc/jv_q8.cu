@@ -371,7 +371,7 @@ int32_t launch_lut_q8(jv_index *ix, cudaStream_t stream, const float *d_queries,
 // but 8 / 6 / 5 with the 16 / 24 / 32 KB tables of M <= 64 / 96 / 128 — there the register file must not be the limit
 // (65536 / (128 threads * CTAs) registers per thread).
 constexpr int q8_min_ctas(int nj, int warps, bool filt) {
-    return filt ? 2 : warps != 4 ? 4 : (nj == 1 || nj == 2) ? 8 : nj == 3 ? 6 : nj == 4 ? 5 : 4;
+    return filt ? 3 : warps != 4 ? 4 : (nj == 1 || nj == 2) ? 8 : nj == 3 ? 6 : nj == 4 ? 5 : 4;
 }
 
 // FUSE = K3 as the epilogue (diagnostic, JVGPU_Q8_FUSED): a separate instantiation so that the production kernel does not
